@@ -1,0 +1,48 @@
+"""Python side of the hand-written sm_100a attention kernels (csrc/attention_sm100.cu)."""
+from __future__ import annotations
+
+import os
+
+import torch
+
+from . import _ext
+
+
+def supported(q, k, v, causal, window, dropout_p) -> bool:
+    if os.environ.get("MLB200_ATTN", "1") == "0":
+        return False
+    try:
+        mod = _ext.load()
+    except Exception:
+        return False
+    if not hasattr(mod, "attn_fwd"):
+        return False
+    hn = q.size(-1)
+    return (q.dtype == torch.bfloat16 and hn == 128 and dropout_p == 0.0 and causal
+            and q.size(1) == k.size(1) and q.size(1) % 128 == 0 and q.size(2) % k.size(2) == 0)
+
+
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, causal, window, scale):
+        mod = _ext.load()
+        out, lse = mod.attn_fwd(q, k, v, causal, -1 if window is None else int(window), float(scale))
+        _ext.count()
+        ctx.save_for_backward(q, k, v, out, lse)
+        ctx.causal, ctx.window, ctx.scale = causal, window, scale
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q, k, v, out, lse = ctx.saved_tensors
+        mod = _ext.load()
+        dq, dk, dv = mod.attn_bwd(dout.contiguous(), q, k, v, out, lse, ctx.causal,
+                                  -1 if ctx.window is None else int(ctx.window), float(ctx.scale))
+        _ext.count(2)
+        return dq, dk, dv, None, None, None
+
+
+def attention(q, k, v, causal, window, scale):
+    import math
+    scale = scale if scale is not None else 1.0 / math.sqrt(q.size(-1))
+    return _AttnFn.apply(q, k, v, causal, window, scale)
