@@ -164,14 +164,15 @@ __global__ void finalize_sum_kernel(const float* __restrict__ partial, int npart
   if (threadIdx.x == 0) out[0] = accumulate ? out[0] + t : t;
 }
 
-// clip_coef = min(1, max_norm / (sqrt(total_sq) + 1e-6)); norm_out = sqrt(total_sq); found_inf = !isfinite
+// nrm = sqrt(total_sq) * norm_scale (norm_scale = 1/loss_scale for fp16, else 1)
+// coef_out = min(1, max_norm / (nrm + 1e-6)) * norm_scale  -> the single multiplier the optimizer applies to grads
 __global__ void clip_coef_kernel(const float* __restrict__ total_sq, float max_norm, float* __restrict__ norm_out,
-                                 float* __restrict__ coef_out, int* __restrict__ found_inf, float extra_scale) {
-  const float nrm = sqrtf(total_sq[0]);
+                                 float* __restrict__ coef_out, int* __restrict__ found_inf, float norm_scale) {
+  const float nrm = sqrtf(total_sq[0]) * norm_scale;
   norm_out[0] = nrm;
   float coef = 1.f;
   if (max_norm > 0.f) coef = fminf(1.f, max_norm / (nrm + 1.0e-6f));
-  coef_out[0] = coef * extra_scale;
+  coef_out[0] = coef * norm_scale;
   if (found_inf) found_inf[0] = isfinite(nrm) ? 0 : 1;
 }
 

@@ -1,0 +1,89 @@
+"""ZeRO-1 distributed optimizer (parity: megatron/optimizer/distrib_optimizer.py).
+
+Reference behaviour kept: the grad buffer is padded to a DP multiple and each DP rank owns a contiguous slice
+that ignores parameter boundaries (:119-164); grads are reduce-scattered (:553-567), the fp32 shard is stepped,
+and the updated weights are all-gathered (:592-600).  Differences: slices are per *bucket* so the
+reduce-scatter of a bucket can overlap backward; the bf16 weights live in a flat buffer with the same offsets,
+so the AdamW kernel writes the updated bf16 slice in place and the all-gather runs in place on that buffer (the
+reference aliases the param buffer onto the grad buffer storage and copies back per tensor, :380-389,603-608).
+Optimizer state is saved per DP rank as flat shards.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from ..parallel import state as ps
+from .optimizer import FlatOptimizer
+
+
+class DistributedOptimizer(FlatOptimizer):
+    def __init__(self, optimizer_config, clip_grad, log_num_zeros_in_grad, params_have_main_grad,
+                 use_contiguous_buffers_in_local_ddp, fp16, bf16, params_dtype, grad_scaler, models):
+        assert use_contiguous_buffers_in_local_ddp
+        super().__init__(optimizer_config, clip_grad, log_num_zeros_in_grad, params_have_main_grad,
+                         use_contiguous_buffers_in_local_ddp, fp16, bf16, params_dtype, grad_scaler, models,
+                         shard_over_dp=True)
+
+    def _norm_reduce_group(self):
+        """Every (tp, pp, dp) rank holds a distinct slice of the gradients: reduce over the whole world."""
+        return dist.group.WORLD if dist.is_initialized() else None
+
+    def get_model_parallel_group(self):
+        return None
+
+    def reduce_model_grads(self, args, timers):
+        """SP norm grads (TP all-reduce) -> DP reduce-scatter (per bucket, possibly already overlapped with
+        backward) -> tied-embedding all-reduce."""
+        timers("layernorm-grads-all-reduce", log_level=1).start(barrier=args.barrier_with_L1_time)
+        self.allreduce_layernorm_grads(args)
+        timers("layernorm-grads-all-reduce").stop()
+        timers("embedding-grads-all-reduce", log_level=1).start(barrier=args.barrier_with_L1_time)
+        self.allreduce_embedding_grads(args)
+        timers("embedding-grads-all-reduce").stop()
+        timers("grads-reduce-scatter", log_level=1).start(barrier=args.barrier_with_L1_time)
+        for model in self.models:
+            model.allreduce_gradients()
+        timers("grads-reduce-scatter").stop()
+
+    def gather_model_params(self, args, timers):
+        """All-gather the updated weight slices in place (bf16 buffer; fp32 buffer for fp32 models)."""
+        timers("params-all-gather", log_level=1).start(barrier=args.barrier_with_L1_time)
+        w = ps.get_data_parallel_world_size()
+        if w > 1:
+            group = ps.get_data_parallel_group()
+            for g in self.groups:
+                buf = g.model_param_buffer
+                s, e = g.shard
+                n = e - s
+                r = ps.get_data_parallel_rank()
+                region = buf[s - r * n: s - r * n + w * n]
+                if buf.is_cuda:
+                    dist.all_gather_into_tensor(region, buf[s:e], group=group)
+                else:
+                    parts = [torch.empty(n, dtype=buf.dtype) for _ in range(w)]
+                    dist.all_gather(parts, buf[s:e].clone(), group=group)
+                    region.copy_(torch.cat(parts))
+        timers("params-all-gather").stop()
+
+    # ---- per-DP-rank flat state -------------------------------------------------------------------
+    def state_dict(self):
+        sd = {"step_count": self.step_count,
+              "param_groups": [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups],
+              "shards": [{"range": g.shard, "main_param": g.main_param.clone(), "exp_avg": g.exp_avg.clone(),
+                          "exp_avg_sq": g.exp_avg_sq.clone()} for g in self.groups]}
+        if self.grad_scaler:
+            sd["grad_scaler"] = self.grad_scaler.state_dict()
+        return sd
+
+    def load_state_dict(self, state_dict):
+        self.step_count = state_dict["step_count"]
+        for grp, saved in zip(self.param_groups, state_dict["param_groups"]):
+            grp.update(saved)
+        for g, sh in zip(self.groups, state_dict["shards"]):
+            assert tuple(sh["range"]) == tuple(g.shard), "optimizer shard layout changed (different DP size?)"
+            g.main_param.copy_(sh["main_param"])
+            g.exp_avg.copy_(sh["exp_avg"])
+            g.exp_avg_sq.copy_(sh["exp_avg_sq"])
+        if self.grad_scaler and "grad_scaler" in state_dict:
+            self.grad_scaler.load_state_dict(state_dict["grad_scaler"])

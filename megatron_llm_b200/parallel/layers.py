@@ -163,6 +163,9 @@ def _wgrad(grad_output2d, total_input2d, weight, gradient_accumulation_fusion):
     """dW = dY^T X.  With accumulation fusion the GEMM epilogue adds into fp32/bf16 ``weight.main_grad``."""
     if gradient_accumulation_fusion and getattr(weight, "main_grad", None) is not None:
         ops.gemm_tn(grad_output2d, total_input2d, out=weight.main_grad, accumulate=True)
+        cb = getattr(weight, "_grad_ready_callback", None)
+        if cb is not None:
+            cb()  # tells the DDP bucket tracker this param's gradient is final (no autograd hook will fire)
         return None
     return ops.gemm_tn(grad_output2d, total_input2d).to(weight.dtype)
 
