@@ -1,0 +1,262 @@
+"""Headline benchmark: Llama-2-7B training step, bf16, seq 4096, TP = #GPUs (sequence parallel), synthetic data,
+random-init weights -> tokens/s for the whole job (BASELINE.json metric).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...      # the unmodified reference (baseline/_ref) on the same config
+
+Timing: W untimed warm-up steps, then exactly K steps bracketed by barrier + torch.cuda.synchronize(), measured with
+CUDA events on the launching stream, MAX over ranks.  Two timed phases through the SAME public API
+(``setup_model_and_optimizer`` + ``train_step`` + ``finetune.forward_step``):
+  * ``value``: inputs already resident on the device, loss left on the device;
+  * ``e2e``:   every micro-batch is copied host->device from pinned memory inside the timed region and the step's
+               loss is read back to the host every step.
+Every step streams > 100 GB of weights/grads/optimizer state, far larger than the 126 MB L2, so no explicit L2
+flush is needed between iterations.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODELS = {
+    # name: (layers, hidden, heads, kv_heads, ffn, vocab)
+    "llama2-7b": (32, 4096, 32, 32, 11008, 32000),
+    "llama2-70b": (80, 8192, 64, 8, 28672, 32000),
+    "mistral-7b": (32, 4096, 32, 8, 14336, 32000),
+    "llama2-tiny": (4, 1024, 8, 8, 2816, 32000),
+}
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--model", default="llama2-7b", choices=list(MODELS))
+    p.add_argument("--seq", type=int, default=4096)
+    p.add_argument("--global_batch", type=int, default=8)
+    p.add_argument("--micro_batch", type=int, default=1)
+    p.add_argument("--layers", type=int, default=None, help="DEV ONLY: override layer count (invalidates the number)")
+    p.add_argument("--no_e2e", action="store_true")
+    return p.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def megatron_argv(a, n_gpus):
+    layers, hidden, heads, kv, ffn, vocab = MODELS[a.model]
+    if a.layers:
+        layers = a.layers
+    argv = ["--model_name", "mistral" if a.model.startswith("mistral") else "llama2",
+            "--num_layers", str(layers), "--hidden_size", str(hidden), "--num_attention_heads", str(heads),
+            "--num_attention_heads_kv", str(kv), "--ffn_hidden_size", str(ffn), "--seq_length", str(a.seq),
+            "--max_position_embeddings", str(a.seq), "--micro_batch_size", str(a.micro_batch),
+            "--global_batch_size", str(a.global_batch), "--tensor_model_parallel_size", str(n_gpus),
+            "--pipeline_model_parallel_size", "1", "--train_iters", "1000000", "--lr", "1e-5", "--min_lr", "1e-6",
+            "--lr_decay_style", "cosine", "--weight_decay", "0.1", "--clip_grad", "1.0", "--adam_beta1", "0.9",
+            "--adam_beta2", "0.95", "--adam_eps", "1e-5", "--bf16", "--use_flash_attn", "--use_rms_norm",
+            "--glu_activation", "swiglu", "--no_tie_embed_logits", "--position_embedding_type", "rotary",
+            "--hidden_dropout", "0.0", "--attention_dropout", "0.0", "--layernorm_epsilon", "1e-5",
+            "--no_bias_gelu_fusion", "--no_bias_dropout_fusion", "--log_interval", "1000000", "--eval_iters", "0",
+            "--eval_interval", "1000000", "--num_workers", "0", "--seed", "1234"]
+    if n_gpus > 1:
+        argv.append("--sequence_parallel")
+    if a.model.startswith("mistral"):
+        argv += ["--sliding_window_size", "4096"]
+    return argv, vocab
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29577")
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    assert world == a.gpus, f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}"
+
+    import finetune
+    from megatron_llm_b200 import get_args, ops
+    from megatron_llm_b200.initialize import initialize_megatron
+    from megatron_llm_b200.models import ModelType
+    from megatron_llm_b200.training import setup_model_and_optimizer, train_step
+
+    argv, vocab = megatron_argv(a, a.gpus)
+    argv += ["--tokenizer_type", "NullTokenizer", "--vocab_file", str(vocab), "--data_type", "synthetic"]
+    devnull = open(os.devnull, "w")
+    real_stdout = sys.stdout
+    sys.stdout = devnull if rank == 0 else sys.stdout      # keep the JSON line the only rank-0 output
+    try:
+        initialize_megatron(finetune.extra_args, {}, args_list=argv)
+        args = get_args()
+        model, optimizer, scheduler = setup_model_and_optimizer(finetune.model_provider, ModelType.encoder_or_decoder)
+        for m in model:
+            m.train()
+    finally:
+        pass
+    dev = torch.device("cuda", torch.cuda.current_device())
+    n_mb = a.global_batch // a.micro_batch
+    g = torch.Generator().manual_seed(1234)
+    # a pool of distinct synthetic micro-batches, pinned on the host
+    pool = [torch.randint(0, vocab, (a.micro_batch, a.seq + 1), generator=g, dtype=torch.int64).pin_memory()
+            for _ in range(max(n_mb, 8))]
+    pool_dev = [t.to(dev) for t in pool]
+    tp_rank0 = True  # TP-rank 0 feeds the data; other TP ranks get it via broadcast_data
+
+    def host_iter():
+        i = 0
+        while True:
+            yield {"text": pool[i % len(pool)]}
+            i += 1
+
+    def dev_iter():
+        i = 0
+        while True:
+            yield {"text": pool_dev[i % len(pool_dev)]}
+            i += 1
+
+    from megatron_llm_b200.parallel import state as ps
+    feeds = ps.get_tensor_model_parallel_rank() == 0
+    it_dev = dev_iter() if feeds else None
+    it_host = host_iter() if feeds else None
+
+    def step(it):
+        loss, skipped, gnorm, _ = train_step(finetune.forward_step, it, model, optimizer, scheduler)
+        return loss
+
+    def timed(it, k, read_loss):
+        dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = ops.launches()
+        s.record()
+        last = None
+        for _ in range(k):
+            loss = step(it)
+            if read_loss and loss:
+                last = loss["lm loss"].item()          # D2H read of the step's result, every step
+        e.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        ms = torch.tensor([s.elapsed_time(e)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item(), ops.launches() - n0, last
+
+    for _ in range(a.warmup):
+        step(it_dev)
+    sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, _ = timed(it_dev, a.steps, read_loss=False)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e = None
+    if not a.no_e2e:
+        step(it_host)  # one untimed step on the host-fed path
+        ms_e2e, _, last_loss = timed(it_host, a.steps, read_loss=True)
+        tokens = a.steps * a.global_batch * a.seq
+        e2e = {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s",
+               "h2d_bytes_per_step": n_mb * a.micro_batch * (a.seq + 1) * 8, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / a.steps, "last_loss": last_loss}
+    sys.stdout = real_stdout
+    if rank == 0:
+        tokens = a.steps * a.global_batch * a.seq
+        out = {"metric": "tokens/sec (whole job, device-timed, max over ranks), Llama-2-7B TP=#GPUs seq4096 training step",
+               "value": tokens / (ms_dev / 1e3), "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps,
+               "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+               "impl": "ours",
+               "config": {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
+                          "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
+                          "parallelism": f"tp{a.gpus}" + ("+sp" if a.gpus > 1 else ""),
+                          "optimizer": "AdamW fp32 master (in timed region), clip 1.0",
+                          "l2": "no flush needed: each step streams >100 GB of weights/grads/optimizer state (>> 126 MB L2)"},
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def run_reference(a):
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "megatron")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/megatron is missing (reference not installed)"}))
+        return
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import reference_runner
+        reference_runner.main(a, MODELS, ClockSampler)
+    except SystemExit:
+        raise
+    except Exception as e:
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"reference failed to run: {type(e).__name__}: {e}"[:300]}))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -234,10 +234,11 @@ class ParallelAttention(MegatronModule):
         if self.attention_type == AttnType.self_attn:
             mixed, _ = self.query_key_value(hidden_states)      # [sq, b, (np + 2 nkv) hn]
             sq, b = mixed.shape[:2]
-            qkv = mixed.view(sq, b, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn)
             if self.position_embedding_type == PositionEmbeddingType.rotary:
                 pid = position_ids if inference_params is None else None
-                qkv = ops.rope_qkv_(qkv, self.rope_table, pid, pos_offset)
+                mixed = ops.rope_qkv_(mixed, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn,
+                                      self.rope_table, pid, pos_offset)
+            qkv = mixed.view(sq, b, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn)
             if self.q_per_kv == 1:
                 query_layer = qkv[:, :, :, 0]                                     # view [sq,b,np,hn]
             else:

@@ -247,41 +247,44 @@ def _rope_ref(x, table, pos, inverse):
     return out.reshape(x.shape).to(x.dtype)
 
 
-def _rope_qkv_apply_(qkv, table, position_ids, pos_offset, inverse):
-    """qkv [s, b, ng, g+2, hn]: rotate q heads and the k head in place."""
-    s, b, ng, hpg, hn = qkv.shape
-    if cuda_ops_available(qkv) and qkv.stride(-1) == 1 and hn % 8 == 0 and \
-            qkv.stride(3) == hn and qkv.stride(2) == hpg * hn and qkv.stride(0) == b * qkv.stride(1):
-        _C().rope_qkv(qkv, table, position_ids, s * b, b, ng, hpg, hn, pos_offset, inverse, qkv.stride(1))
+def _rope_qkv_apply_(mixed, nkv, hpg, hn, table, position_ids, pos_offset, inverse):
+    """mixed [s, b, nkv*hpg*hn] viewed as [s, b, nkv, hpg, hn]: rotate the q heads and the k head in place."""
+    s, b = mixed.shape[:2]
+    if cuda_ops_available(mixed) and mixed.is_contiguous() and hn % 8 == 0:
+        _C().rope_qkv(mixed, table, position_ids, s * b, b, nkv, hpg, hn, pos_offset, inverse, nkv * hpg * hn)
         _count()
-        return qkv
+        return mixed
+    qkv = mixed.view(s, b, nkv, hpg, hn)
     if position_ids is not None:
         pos = position_ids.t().reshape(s, b, 1, 1)
     else:
-        pos = (torch.arange(s, device=qkv.device) + pos_offset).view(s, 1, 1, 1)
+        pos = (torch.arange(s, device=mixed.device) + pos_offset).view(s, 1, 1, 1)
     rot = qkv[:, :, :, :-1]
-    rot.copy_(_rope_ref(rot, table, pos.expand(s, b, ng, hpg - 1), inverse))
-    return qkv
+    rot.copy_(_rope_ref(rot, table, pos.expand(s, b, nkv, hpg - 1), inverse))
+    return mixed
 
 
 class _RopeQKVFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, qkv, table, position_ids, pos_offset):
+    def forward(ctx, mixed, nkv, hpg, hn, table, position_ids, pos_offset):
         ctx.save_for_backward(table, position_ids)
-        ctx.pos_offset = pos_offset
-        ctx.mark_dirty(qkv)
-        return _rope_qkv_apply_(qkv, table, position_ids, pos_offset, False)
+        ctx.meta = (nkv, hpg, hn, pos_offset)
+        ctx.mark_dirty(mixed)
+        return _rope_qkv_apply_(mixed, nkv, hpg, hn, table, position_ids, pos_offset, False)
 
     @staticmethod
     def backward(ctx, g):
         table, position_ids = ctx.saved_tensors
+        nkv, hpg, hn, pos_offset = ctx.meta
         g = g.contiguous()
-        return _rope_qkv_apply_(g, table, position_ids, ctx.pos_offset, True), None, None, None
+        return _rope_qkv_apply_(g, nkv, hpg, hn, table, position_ids, pos_offset, True), None, None, None, None, \
+            None, None
 
 
-def rope_qkv_(qkv, table, position_ids=None, pos_offset=0):
-    """In-place RoPE on the packed [s,b,ng,g+2,hn] QKV buffer (differentiable)."""
-    return _RopeQKVFn.apply(qkv, table, position_ids, pos_offset)
+def rope_qkv_(mixed, nkv, heads_per_group, hn, table, position_ids=None, pos_offset=0):
+    """In-place RoPE on the packed QKV GEMM output ``mixed`` [s, b, nkv*(g+2)*hn] (differentiable).  ``mixed`` must
+    be a base tensor (the Linear autograd function returns one), not a view."""
+    return _RopeQKVFn.apply(mixed, nkv, heads_per_group, hn, table, position_ids, pos_offset)
 
 
 # =============================================================================================

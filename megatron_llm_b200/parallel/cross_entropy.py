@@ -58,9 +58,10 @@ class _VocabParallelCrossEntropy(torch.autograd.Function):
         else:
             stats = _local_stats_torch(logits2d, tgt, vocab_start)
         if world > 1:
-            gathered = torch.empty((world,) + tuple(stats.shape), dtype=stats.dtype, device=stats.device)
+            gathered = torch.empty((world * stats.size(0), stats.size(1)), dtype=stats.dtype, device=stats.device)
             dist.all_gather_into_tensor(gathered, stats.contiguous(),
                                         group=ps.get_tensor_model_parallel_group())
+            gathered = gathered.view(world, stats.size(0), stats.size(1))
         else:
             gathered = stats[None]
         M, logS, tlogit, xsum = _combine(gathered)
@@ -118,7 +119,8 @@ def vocab_parallel_max_indices(logits: torch.Tensor) -> torch.Tensor:
         return idx
     group = ps.get_tensor_model_parallel_group()
     packed = torch.stack([vals, idx.to(vals.dtype)], dim=0).contiguous()
-    allp = torch.empty((world,) + tuple(packed.shape), dtype=packed.dtype, device=packed.device)
+    allp = torch.empty((world * packed.size(0),) + tuple(packed.shape[1:]), dtype=packed.dtype, device=packed.device)
     dist.all_gather_into_tensor(allp, packed, group=group)
+    allp = allp.view((world,) + tuple(packed.shape))
     best = allp[:, 0].argmax(dim=0, keepdim=True)
     return allp[:, 1].gather(0, best).squeeze(0).long()

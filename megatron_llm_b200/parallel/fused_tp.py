@@ -23,9 +23,9 @@ def active(x: torch.Tensor) -> bool:
     return _COMM is not None and x.is_cuda and x.dtype == torch.bfloat16 and _COMM.enabled
 
 
-def ag_gemm(x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
+def ag_gemm(x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None):
     """all-gather(x_shard along dim 0) then GEMM.  Returns (out2d [s*b, N], gathered input)."""
-    return _COMM.ag_gemm(x_shard, weight, transposed_weight)
+    return _COMM.ag_gemm(x_shard, weight, transposed_weight, out=out)
 
 
 def gemm_rs(x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):

@@ -170,6 +170,14 @@ def _wgrad(grad_output2d, total_input2d, weight, gradient_accumulation_fusion):
     return ops.gemm_tn(grad_output2d, total_input2d).to(weight.dtype)
 
 
+def _linear_fwd(x, weight):
+    """x[..., K] @ weight[N, K]^T -> [..., N], written straight into a tensor of the final shape so the autograd
+    Function returns a base tensor (not a view): downstream kernels (RoPE) may then update it in place."""
+    out = torch.empty(*x.shape[:-1], weight.size(0), dtype=x.dtype, device=x.device)
+    ops.gemm_nt(x.reshape(-1, x.size(-1)), weight, out=out.view(-1, weight.size(0)))
+    return out
+
+
 class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
     """y = x W^T (+b) with (a) SP all-gather of x in fwd, (b) dgrad overlapped with the SP re-gather / the
     TP all-reduce of dX, (c) dX reduce-scatter overlapped with wgrad, (d) wgrad accumulated into main_grad."""
@@ -185,12 +193,12 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         ctx.fused = fused
         if ctx.sequence_parallel:
             if fused:
-                out2d, total_input = fused_tp.ag_gemm(input, weight)
-                output = out2d.view(*total_input.shape[:-1], weight.size(0))
+                output = torch.empty(input.size(0) * ps.get_tensor_model_parallel_world_size(), *input.shape[1:-1],
+                                     weight.size(0), dtype=input.dtype, device=input.device)
+                _, total_input = fused_tp.ag_gemm(input, weight, out=output.view(-1, weight.size(0)))
             else:
                 total_input, _ = _all_gather_first(input)
-                output = ops.gemm_nt(total_input.reshape(-1, total_input.size(-1)), weight).view(
-                    *total_input.shape[:-1], weight.size(0))
+                output = _linear_fwd(total_input, weight)
             if _keep_gathered():
                 ctx.save_for_backward(total_input, weight)
                 ctx.saved_gathered = True
@@ -200,7 +208,7 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         else:
             ctx.save_for_backward(input, weight)
             ctx.saved_gathered = True
-            output = ops.gemm_nt(input.reshape(-1, input.size(-1)), weight).view(*input.shape[:-1], weight.size(0))
+            output = _linear_fwd(input, weight)
         if bias is not None:
             output = output + bias
         return output

@@ -35,6 +35,8 @@ def _identity(x):
 def _reduce(x):
     if _tp() == 1:
         return x
+    if not x.is_contiguous():
+        x = x.contiguous()   # e.g. the stride-0 expanded grad of ``sum()``; never reduce into aliased storage
     dist.all_reduce(x, group=_group())
     return x
 
@@ -61,10 +63,10 @@ def _gather_along_last_dim(x):
     if world == 1:
         return x
     x = x.contiguous()
-    full = torch.empty((world,) + tuple(x.shape), dtype=x.dtype, device=x.device)
-    dist.all_gather_into_tensor(full, x, group=_group())
-    # [w, ..., c] -> [..., w*c]
-    return torch.cat(list(full.unbind(0)), dim=-1).contiguous()
+    flat = torch.empty((world * x.size(0),) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, x, group=_group())
+    # [w*d0, ..., c] -> [d0, ..., w*c]
+    return torch.cat(list(flat.chunk(world, dim=0)), dim=-1).contiguous()
 
 
 def _gather_along_first_dim(x):

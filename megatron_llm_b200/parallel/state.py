@@ -159,14 +159,8 @@ def model_parallel_is_initialized() -> bool:
 
 
 def destroy_model_parallel() -> None:
+    """Forget all groups (the communicators themselves are released with the default process group)."""
     global _S
-    for g in (_S.tp_group, _S.pp_group, _S.dp_group, _S.mp_group, _S.embedding_group,
-              _S.position_embedding_group):
-        try:
-            if g is not None and dist.is_initialized():
-                dist.destroy_process_group(g)
-        except Exception:
-            pass
     _S = _State()
 
 
