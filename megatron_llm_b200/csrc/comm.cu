@@ -1,0 +1,116 @@
+// Data-parallel gradient reduction over NVLink peer memory (sm_100a), fused with the 1/DP scale.
+//
+// Replaces the reference's single blocking NCCL all-reduce of the whole fp32 grad buffer after backward
+// (megatron/model/distributed.py:202-209) and the distributed optimizer's reduce_scatter_tensor
+// (optimizer/distrib_optimizer.py:553-567).  Every rank's fp32 bucket lives in symmetric memory mapped into all
+// peers.  Two-shot algorithm, one kernel per bucket, launched from the backward hooks on a side stream:
+//   1. handshake: publish "my bucket is complete" to all peers / wait for theirs        (st.release.sys / ld.acquire.sys)
+//   2. reduce-scatter: rank r sums slice r of every peer's bucket with 16-byte loads over NVLink, scales by 1/DP,
+//      writes its own slice;
+//   3. (all-reduce only) all-gather: the reduced slice is stored into every peer's bucket over NVLink;
+//   4. handshake out: a rank's kernel retires only when every peer has finished reading from / writing into its bucket.
+#include "gemm_types.h"
+#include "ptx.cuh"
+
+namespace mlb {
+
+enum DpPadSlot : int { DP_READY = 0, DP_DONE = 8, DP_CTA_COUNTER = 40 };
+
+struct DpArgs {
+  float* peer[GEMM_MAX_PEERS];
+  int* pad_peer[GEMM_MAX_PEERS];
+  int* pad_local;
+  long long n;
+  int rank, world, epoch;
+  float scale;
+  int reduce_scatter;
+};
+
+__global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p)
+        if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_READY + a.rank, a.epoch);
+    }
+    for (int p = 0; p < a.world; ++p)
+      if (p != a.rank) {
+        long long polls = 0;
+        while (ld_acquire_sys(a.pad_local + DP_READY + p) < a.epoch) {
+          __nanosleep(100);
+          if (++polls > (1LL << 25)) break;
+        }
+      }
+  }
+  __syncthreads();
+
+  const long long slice = a.n / a.world;          // n is padded to a multiple of world*4 by the caller
+  const long long begin = slice * a.rank;
+  const long long nvec = slice / 4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long e = begin + i * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < GEMM_MAX_PEERS; ++k) {
+      if (k < a.world) {
+        const int p = (a.rank + k) % a.world;      // start with the local copy, spread NVLink reads across peers
+        const uint4 u = ld_v4_relaxed_sys(a.peer[p] + e);
+        acc.x += __uint_as_float(u.x); acc.y += __uint_as_float(u.y);
+        acc.z += __uint_as_float(u.z); acc.w += __uint_as_float(u.w);
+      }
+    }
+    acc.x *= a.scale; acc.y *= a.scale; acc.z *= a.scale; acc.w *= a.scale;
+    const uint4 o = make_uint4(__float_as_uint(acc.x), __float_as_uint(acc.y), __float_as_uint(acc.z),
+                               __float_as_uint(acc.w));
+    if (a.reduce_scatter) {
+      st_v4(a.peer[a.rank] + e, o);
+    } else {
+#pragma unroll
+      for (int k = 0; k < GEMM_MAX_PEERS; ++k)
+        if (k < a.world) st_v4(a.peer[(a.rank + k) % a.world] + e, o);
+    }
+  }
+
+  // handshake out (last CTA of this rank)
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(a.pad_local + DP_CTA_COUNTER, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    a.pad_local[DP_CTA_COUNTER] = 0;
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p)
+      if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_DONE + a.rank, a.epoch);
+    for (int p = 0; p < a.world; ++p)
+      if (p != a.rank) {
+        long long polls = 0;
+        while (ld_acquire_sys(a.pad_local + DP_DONE + p) < a.epoch) {
+          __nanosleep(100);
+          if (++polls > (1LL << 25)) break;
+        }
+      }
+  }
+}
+
+}  // namespace mlb
+
+extern "C" int mlb_dp_reduce(int reduce_scatter, float* local, const long long* peer_ptrs, int* pad_local,
+                             const long long* pad_peer_ptrs, long long n, int rank, int world, int epoch,
+                             float scale, int num_ctas, cudaStream_t st) {
+  using namespace mlb;
+  if (world > GEMM_MAX_PEERS || n % (world * 4) != 0) return -2;
+  DpArgs a;
+  for (int i = 0; i < GEMM_MAX_PEERS; ++i) {
+    a.peer[i] = i < world ? reinterpret_cast<float*>(peer_ptrs[i]) : nullptr;
+    a.pad_peer[i] = i < world ? reinterpret_cast<int*>(pad_peer_ptrs[i]) : nullptr;
+  }
+  a.peer[rank] = local;
+  a.pad_local = pad_local;
+  a.n = n; a.rank = rank; a.world = world; a.epoch = epoch; a.scale = scale; a.reduce_scatter = reduce_scatter;
+  dp_reduce_kernel<<<num_ctas > 0 ? num_ctas : 32, 512, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}

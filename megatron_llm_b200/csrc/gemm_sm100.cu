@@ -4,6 +4,7 @@
 #include <cudaTypedefs.h>
 #include <mutex>
 #include <stdio.h>
+#include <string.h>
 
 namespace mlb {
 
@@ -35,11 +36,11 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int MODE = MODE_PLAIN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                   cudaStream_t stream) {
   using S = GemmSmem<BLOCK_N>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, EPI, MODE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
@@ -49,7 +50,13 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   const int num_m = (p.M + GEMM_BLOCK_M - 1) / GEMM_BLOCK_M;
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   int grid = num_m * num_n;
-  if (grid > num_sms) grid = num_sms;
+  if (MODE == MODE_AG_GEMM) {
+    const int compute = num_sms - p.comm.num_comm_ctas;
+    if (grid > compute) grid = compute;
+    grid += p.comm.num_comm_ctas;   // trailing CTAs are the NVLink pullers; all CTAs must be co-resident
+  } else if (grid > num_sms) {
+    grid = num_sms;
+  }
   kern<<<grid, GEMM_THREADS, S::TOTAL, stream>>>(tmA, tmB, p);
   return (int)cudaGetLastError();
 }
@@ -75,6 +82,27 @@ static int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, c
   return dispatch_epi<BLOCK_N, true, false>(epi, tmA, tmB, p, num_sms, stream);
 }
 
+template <int BLOCK_N>
+static int dispatch_fused(int mode, int b_mn, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                          int num_sms, cudaStream_t stream) {
+  if (mode == MODE_AG_GEMM)
+    return b_mn ? launch<BLOCK_N, false, true, EPI_BF16, MODE_AG_GEMM>(tmA, tmB, p, num_sms, stream)
+                : launch<BLOCK_N, false, false, EPI_BF16, MODE_AG_GEMM>(tmA, tmB, p, num_sms, stream);
+  if (mode == MODE_GEMM_RS)
+    return b_mn ? launch<BLOCK_N, false, true, EPI_BF16, MODE_GEMM_RS>(tmA, tmB, p, num_sms, stream)
+                : launch<BLOCK_N, false, false, EPI_BF16, MODE_GEMM_RS>(tmA, tmB, p, num_sms, stream);
+  return -3;
+}
+
+static int pick_block_n(int M, int N, int num_sms) {
+  auto cost = [&](int bn) {
+    long tiles = (long)((M + 127) / 128) * ((N + bn - 1) / bn);
+    long w = (tiles + num_sms - 1) / num_sms;
+    return w * bn;  // ~ waves x tile width
+  };
+  return (cost(256) <= cost(128)) ? 256 : 128;
+}
+
 }  // namespace mlb
 
 // D[M,N] = A * B^T with fp32 accumulation on tcgen05.
@@ -83,7 +111,7 @@ static int dispatch_major(int a_mn, int b_mn, int epi, const CUtensorMap& tmA, c
 // `comm` may be null (plain GEMM).  Returns 0 on success.
 extern "C" int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
                              int ldc, int a_mn_major, int b_mn_major, int epilogue, int block_n,
-                             const mlb::GemmComm* comm, int num_sms, cudaStream_t stream) {
+                             const void* /*unused*/, int num_sms, cudaStream_t stream) {
   using namespace mlb;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap tmA, tmB;
@@ -91,26 +119,37 @@ extern "C" int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
   if (!a_mn_major) r = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, GEMM_BLOCK_M);
   else r = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BLOCK_K);
   if (r) return 1000 + r;
-  if (block_n != 128 && block_n != 256) {
-    // heuristic: fewest waves, then the larger tile
-    auto waves = [&](int bn) {
-      long tiles = (long)((M + 127) / 128) * ((N + bn - 1) / bn);
-      long w = (tiles + num_sms - 1) / num_sms;
-      return w * bn;  // cost ~ waves * tile width
-    };
-    block_n = (waves(256) <= waves(128)) ? 256 : 128;
-  }
+  if (block_n != 128 && block_n != 256) block_n = pick_block_n(M, N, num_sms);
   if (!b_mn_major) r = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, block_n);
   else r = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BLOCK_K);
   if (r) return 2000 + r;
   GemmParams p;
+  memset(&p, 0, sizeof(p));
   p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
-  if (comm) p.comm = *comm;
-  else {
-    p.comm.a_ready_flags = nullptr; p.comm.a_chunk_rows = 0; p.comm.a_ready_epoch = 0; p.comm.m_rotate_blocks = 0;
-    p.comm.out_chunk_rows = 0;
-    for (int i = 0; i < GEMM_MAX_PEERS; ++i) { p.comm.out_ptrs[i] = nullptr; p.comm.tile_counters[i] = nullptr; }
-  }
   if (block_n == 256) return dispatch_major<256>(a_mn_major, b_mn_major, epilogue, tmA, tmB, p, num_sms, stream);
   return dispatch_major<128>(a_mn_major, b_mn_major, epilogue, tmA, tmB, p, num_sms, stream);
+}
+
+// Fused GEMM + collective (see gemm_sm100.cuh).  A is always K-major ([M, lda]); bf16 output.
+//   mode 1 (all-gather -> GEMM): A = comm->ag_dst (local gathered buffer the puller CTAs fill), C = out [M, ldc]
+//   mode 2 (GEMM -> reduce-scatter): A = local activations; tiles go to comm->rs_dst[], C unused
+extern "C" int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda,
+                                   int ldb, int ldc, int b_mn_major, const mlb::GemmComm* comm, int num_sms,
+                                   cudaStream_t stream) {
+  using namespace mlb;
+  if (M <= 0 || N <= 0 || K <= 0 || comm == nullptr) return -1;
+  CUtensorMap tmA, tmB;
+  int r = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, GEMM_BLOCK_M);
+  if (r) return 1000 + r;
+  const int compute_sms = num_sms - (mode == MODE_AG_GEMM ? comm->num_comm_ctas : 0);
+  const int block_n = pick_block_n(M, N, compute_sms);
+  if (!b_mn_major) r = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, block_n);
+  else r = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BLOCK_K);
+  if (r) return 2000 + r;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.comm = *comm;
+  if (block_n == 256) return dispatch_fused<256>(mode, b_mn_major, tmA, tmB, p, num_sms, stream);
+  return dispatch_fused<128>(mode, b_mn_major, tmA, tmB, p, num_sms, stream);
 }

@@ -8,48 +8,24 @@
 // (megatron/core/tensor_parallel/layers.py:240 fwd, :267 dgrad, :298-307 wgrad) and the orphaned
 // fused_weight_gradient_dense.cu (cublasGemmEx beta=1 into fp32 main_grad).
 //
-// The same kernel is the compute half of the fused GEMM+collective kernels (comm.cuh hooks):
-//   * producer side: wait on per-chunk arrival flags before TMA-loading A rows (all-gather -> GEMM),
-//     with the m-block order rotated so a rank starts on its local shard;
-//   * epilogue side: scatter output row-chunks straight into peer (NVLink-mapped) buffers and
-//     publish per-destination tile counters with release.sys (GEMM -> reduce-scatter).
+// MODE selects the fused collective (one kernel = math + NVLink transfer, tile by tile):
+//   MODE_PLAIN   : GEMM only.
+//   MODE_AG_GEMM : all-gather -> GEMM (ColumnParallelLinear fwd under sequence parallelism, RowParallel dgrad).
+//                  The last `num_comm_ctas` CTAs of the grid are "puller" CTAs: they stream every peer's
+//                  activation shard out of NVLink-mapped symmetric memory with cp.async.bulk (peer global ->
+//                  smem -> local gathered buffer) and publish a flag per 128-row chunk; the GEMM CTAs' TMA
+//                  producer warp acquires the flag of the chunk a tile needs, and walks the m-blocks starting at
+//                  the local shard, so math on early chunks overlaps the arrival of later ones.
+//   MODE_GEMM_RS : GEMM -> reduce-scatter (RowParallelLinear fwd, ColumnParallel dgrad).  The epilogue stores
+//                  each output tile straight into the destination rank's receive slot over NVLink (remote chunks
+//                  first, local chunk last) and bumps that rank's arrival counter with red.release.sys; when a
+//                  CTA runs out of tiles it joins the reduction of the local chunk (sum of the `world` slots in
+//                  fp32) as soon as all sources have delivered.
 #pragma once
+#include "gemm_types.h"
 #include "ptx.cuh"
 
 namespace mlb {
-
-constexpr int GEMM_BLOCK_M = 128;
-constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128B swizzle row
-constexpr int GEMM_THREADS = 256;
-constexpr int GEMM_MAX_PEERS = 8;
-
-enum GemmEpilogue : int {
-  EPI_BF16 = 0,        // C(bf16) = acc
-  EPI_F32_ACCUM = 1,   // C(fp32) += acc      (wgrad into main_grad)
-  EPI_F32 = 2,         // C(fp32) = acc
-  EPI_BF16_ACCUM = 3,  // C(bf16) += acc
-};
-
-struct GemmComm {
-  // all-gather -> GEMM: A rows [c*a_chunk_rows, (c+1)*a_chunk_rows) are valid once
-  // a_ready_flags[c] >= a_ready_epoch (written with release.sys by the producer of that chunk).
-  const int* a_ready_flags;
-  int a_chunk_rows;
-  int a_ready_epoch;
-  int m_rotate_blocks;  // first m-block processed (local shard first)
-  // GEMM -> scatter: output rows of chunk c go to out_ptrs[c] (row index relative to the chunk).
-  void* out_ptrs[GEMM_MAX_PEERS];
-  int out_chunk_rows;  // 0 = disabled
-  // after each finished output tile: red.release.sys.add(tile_counters[c], 1) on the destination
-  int* tile_counters[GEMM_MAX_PEERS];
-};
-
-struct GemmParams {
-  void* C;
-  int M, N, K;
-  int ldc;  // elements
-  GemmComm comm;
-};
 
 template <int BLOCK_N>
 struct GemmSmem {
@@ -61,7 +37,123 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int EPI>
+// bounded spin: a lost peer must not hang the GPU box; after ~2^26 polls mark the pad and carry on
+__device__ __forceinline__ void spin_until_ge(const int* flag, int value, int* pad_local) {
+  long long polls = 0;
+  while (ld_acquire_sys(flag) < value) {
+    __nanosleep(40);
+    if (++polls > (1LL << 26)) {
+      if (pad_local) st_release_sys(pad_local + PAD_ERROR, 1);
+      break;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// puller CTA: all-gather peer shards into the local gathered buffer with bulk async copies
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+constexpr int AG_PIECE_BYTES = 32 * 1024;
+constexpr int AG_STAGES = 6;  // 192 KB of smem in flight per puller CTA
+
+__device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
+  // one thread drives the whole copy pipeline (bulk copies are issued by a single thread anyway)
+  if (threadIdx.x != 0) return;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);
+  for (int i = 0; i < AG_STAGES; ++i) mbar_init(&bars[i], 1);
+  fence_barrier_init();
+  fence_proxy_async_smem();
+
+  const int chunks_per_rank = c.ag_rows_per_rank / GEMM_BLOCK_M;
+  const long long chunk_bytes = (long long)GEMM_BLOCK_M * c.ag_row_bytes;
+  const int pieces_per_chunk = (int)((chunk_bytes + AG_PIECE_BYTES - 1) / AG_PIECE_BYTES);
+  uint32_t phase_bits = 0;  // per-stage mbarrier parity
+  long long piece_seq = 0;  // pieces issued so far by this CTA (stage = seq % AG_STAGES)
+
+  if (comm_id == 0) {
+    // my shard was written by earlier stream-ordered work: publish it to every peer
+    __threadfence_system();
+    for (int p = 0; p < c.world; ++p)
+      if (p != c.rank) st_release_sys(c.pad_peer[p] + PAD_AG_READY + c.rank, c.epoch);
+  }
+
+  for (int i = 0; i < c.world; ++i) {
+    const int p = (c.rank + i) % c.world;
+    bool waited = false;
+    for (int j = 0; j < chunks_per_rank; ++j) {
+      const int g = i * chunks_per_rank + j;
+      if (g % c.num_comm_ctas != comm_id) continue;
+      if (!waited && p != c.rank) {
+        spin_until_ge(c.pad_local + PAD_AG_READY + p, c.epoch, c.pad_local);
+        fence_proxy_async_global();
+        waited = true;
+      }
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(c.ag_src[p]) + (long long)j * chunk_bytes;
+      uint8_t* dst = reinterpret_cast<uint8_t*>(c.ag_dst) + ((long long)p * chunks_per_rank + j) * chunk_bytes;
+      // software pipeline: keep up to AG_STAGES-1 loads in flight
+      int issued = 0, stored = 0;
+      auto issue = [&](int k) {
+        const int stage = (int)((piece_seq + k) % AG_STAGES);
+        const long long off = (long long)k * AG_PIECE_BYTES;
+        const uint32_t bytes = (uint32_t)min((long long)AG_PIECE_BYTES, chunk_bytes - off);
+        mbar_arrive_expect_tx(&bars[stage], bytes);
+        bulk_g2s(smem + stage * AG_PIECE_BYTES, src + off, bytes, &bars[stage]);
+      };
+      while (issued < pieces_per_chunk && issued < AG_STAGES - 1) issue(issued++);
+      while (stored < pieces_per_chunk) {
+        const int stage = (int)((piece_seq + stored) % AG_STAGES);
+        mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
+        phase_bits ^= (1u << stage);
+        const long long off = (long long)stored * AG_PIECE_BYTES;
+        const uint32_t bytes = (uint32_t)min((long long)AG_PIECE_BYTES, chunk_bytes - off);
+        bulk_s2g(dst + off, smem + stage * AG_PIECE_BYTES, bytes);
+        tma_store_commit();
+        ++stored;
+        if (issued < pieces_per_chunk) {
+          // the stage about to be refilled is the one whose store was committed one iteration ago
+          tma_store_wait_read<1>();
+          issue(issued++);
+        }
+      }
+      piece_seq += pieces_per_chunk;
+      tma_store_wait<0>();          // all bytes of the chunk are in local HBM
+      fence_proxy_async_global();
+      __threadfence();
+      st_release_sys(c.ag_chunk_flags + p * chunks_per_rank + j, c.epoch);
+    }
+    if (p != c.rank) {
+      // tell the owner when ALL of this rank's pullers are done with its shard
+      __threadfence();
+      const int done = atomicAdd(c.ag_read_counters + p, 1) + 1;
+      if (done == c.num_comm_ctas) {
+        c.ag_read_counters[p] = 0;
+        __threadfence_system();
+        st_release_sys(c.pad_peer[p] + PAD_AG_ACK + c.rank, c.epoch);
+      }
+    }
+  }
+  if (comm_id == 0) {
+    // my published shard may be overwritten by the next call only once every peer has read it
+    for (int p = 0; p < c.world; ++p)
+      if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, c.epoch, c.pad_local);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// the GEMM kernel
+// ------------------------------------------------------------------------------------------------
+template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int MODE>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const GemmParams p) {
@@ -69,9 +161,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
   constexpr uint32_t IDESC = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, A_MN, B_MN, true);
+  constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  int num_compute_ctas = gridDim.x;
+  if constexpr (MODE == MODE_AG_GEMM) {
+    num_compute_ctas = gridDim.x - p.comm.num_comm_ctas;
+    if ((int)blockIdx.x >= num_compute_ctas) {
+      ag_puller(p.comm, smem, blockIdx.x - num_compute_ctas);
+      return;
+    }
+  }
+
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -109,7 +212,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int num_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_k = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int total_tiles = num_m * num_n;
-  constexpr int GROUP_M = 8;
+  // plain GEMM: groups of 8 m-blocks share B tiles through L2.  fused modes: one m-block row at a time in
+  // rotated order so work follows the arrival (AG) / departure (RS) order of the chunks.
+  constexpr int GROUP_M = (MODE == MODE_PLAIN) ? 8 : 1;
 
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     const int per_group = GROUP_M * num_n;
@@ -119,8 +224,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int in_group = tile - group * per_group;
     m_blk = first_m + in_group % gsize;
     n_blk = in_group / gsize;
-    m_blk += p.comm.m_rotate_blocks;
-    if (m_blk >= num_m) m_blk -= num_m;
+    if constexpr (MODE != MODE_PLAIN) {
+      m_blk += p.comm.m_rotate_blocks;
+      if (m_blk >= num_m) m_blk -= num_m;
+    }
   };
 
   if (warp == 0) {
@@ -128,16 +235,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += num_compute_ctas) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
-        if (p.comm.a_ready_flags != nullptr) {
-          const int c_lo = m0 / p.comm.a_chunk_rows;
-          const int c_hi = (min(m0 + GEMM_BLOCK_M, p.M) - 1) / p.comm.a_chunk_rows;
-          for (int c = c_lo; c <= c_hi; ++c) {
-            while (ld_acquire_sys(p.comm.a_ready_flags + c) < p.comm.a_ready_epoch) __nanosleep(64);
-          }
+        if constexpr (MODE == MODE_AG_GEMM) {
+          spin_until_ge(p.comm.ag_chunk_flags + m_blk, p.comm.epoch, p.comm.pad_local);
           fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
         }
         for (int kb = 0; kb < num_k; ++kb) {
@@ -171,7 +274,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = blockIdx.x; tile < total_tiles; tile += num_compute_ctas) {
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
@@ -186,9 +289,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // MN-major SW128: 64-element MN chunks BLOCK_K*128B apart (LBO), 8-row K groups 1024B apart
             // (SBO), advance 16 K-rows = 2048B per UMMA_K.
             const uint64_t da = A_MN ? make_smem_desc(sA + k * 2048, GEMM_BLOCK_K * 128, 1024, kSwizzle128B)
-                                     : make_smem_desc(sA + k * 32, 0, 1024, kSwizzle128B);
+                                     : make_smem_desc(sA + k * 32, 16, 1024, kSwizzle128B);
             const uint64_t db = B_MN ? make_smem_desc(sB + k * 2048, GEMM_BLOCK_K * 128, 1024, kSwizzle128B)
-                                     : make_smem_desc(sB + k * 32, 0, 1024, kSwizzle128B);
+                                     : make_smem_desc(sB + k * 32, 16, 1024, kSwizzle128B);
             umma_f16_ss<1>(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
           }
           umma_commit<1>(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
@@ -203,7 +306,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int q = warp - 4;  // == warp % 4 : the TMEM lane quadrant this warp may access
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    uint32_t free_checked = 0;  // RS: destinations whose receive slot we already know to be reusable
+    for (int tile = blockIdx.x; tile < total_tiles; tile += num_compute_ctas) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
@@ -211,18 +315,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
-      // destination row pointer (optionally scattered per m-chunk into peer buffers)
       uint8_t* crow;
-      int dst_chunk = 0;
-      if (p.comm.out_chunk_rows > 0) {
-        const int rr = row_ok ? row : m0;
-        dst_chunk = rr / p.comm.out_chunk_rows;
-        const int lr = rr - dst_chunk * p.comm.out_chunk_rows;
-        crow = reinterpret_cast<uint8_t*>(p.comm.out_ptrs[dst_chunk]) +
-               (size_t)lr * p.ldc * ((EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4);
+      int dst = 0;
+      if constexpr (MODE == MODE_GEMM_RS) {
+        dst = m0 / p.comm.rs_rows_per_rank;
+        if (!((free_checked >> dst) & 1u)) {
+          // the receive slot of this parity on `dst` was last used two calls ago: wait until dst reduced it
+          if (dst != p.comm.rank) spin_until_ge(p.comm.pad_local + PAD_RS_FREE + dst, p.comm.epoch - 2, p.comm.pad_local);
+          free_checked |= (1u << dst);
+        }
+        const int lr = (row_ok ? row : m0) - dst * p.comm.rs_rows_per_rank;
+        crow = reinterpret_cast<uint8_t*>(p.comm.rs_dst[dst]) + (size_t)lr * p.ldc * OUT_ELEM;
       } else {
-        crow = reinterpret_cast<uint8_t*>(p.C) +
-               (size_t)(row_ok ? row : 0) * p.ldc * ((EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4);
+        crow = reinterpret_cast<uint8_t*>(p.C) + (size_t)(row_ok ? row : 0) * p.ldc * OUT_ELEM;
       }
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * BLOCK_N;
 #pragma unroll 1
@@ -233,13 +338,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int col = n0 + c * 32;
         if (row_ok && col < p.N) {
           if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) {
-            uint4* dst = reinterpret_cast<uint4*>(crow + (size_t)col * 2);
+            uint4* dptr = reinterpret_cast<uint4*>(crow + (size_t)col * 2);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               if (col + v * 8 < p.N) {
                 uint4 o;
                 if constexpr (EPI == EPI_BF16_ACCUM) {
-                  const uint4 old = dst[v];
+                  const uint4 old = dptr[v];
                   float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z),
                          a3 = unpack_bf16x2(old.w);
                   o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) + a0.x, __uint_as_float(r[v * 8 + 1]) + a0.y);
@@ -252,21 +357,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                   o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
                   o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
                 }
-                dst[v] = o;
+                dptr[v] = o;
               }
             }
           } else {
-            float4* dst = reinterpret_cast<float4*>(crow + (size_t)col * 4);
+            float4* dptr = reinterpret_cast<float4*>(crow + (size_t)col * 4);
 #pragma unroll
             for (int v = 0; v < 8; ++v) {
               if (col + v * 4 < p.N) {
                 float4 o = make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
                                        __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
                 if constexpr (EPI == EPI_F32_ACCUM) {
-                  const float4 old = dst[v];
+                  const float4 old = dptr[v];
                   o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
                 }
-                dst[v] = o;
+                dptr[v] = o;
               }
             }
           }
@@ -276,13 +381,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (p.comm.out_chunk_rows > 0 && p.comm.tile_counters[0] != nullptr) {
-        // all 4 epilogue warps' stores of this tile must be visible before the tile is published
+      if constexpr (MODE == MODE_GEMM_RS) {
+        // every epilogue warp's stores of this tile must be visible at the destination before it is counted
+        __threadfence_system();
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (q == 0 && lane == 0) {
-          const int c0 = m0 / p.comm.out_chunk_rows;
-          __threadfence_system();
-          red_add_release_sys(p.comm.tile_counters[c0], 1);
+          int* counter = (dst == p.comm.rank ? p.comm.pad_local : p.comm.pad_peer[dst]) + PAD_RS_ARRIVED + p.comm.rank;
+          red_add_release_sys(counter, 1);
         }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -294,6 +399,50 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<1>(tmem_base, TMEM_COLS);
+  }
+
+  if constexpr (MODE == MODE_GEMM_RS) {
+    // ================================ reduce the local chunk ================================
+    const GemmComm& c = p.comm;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < c.world; ++s) spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, c.rs_expected_total, c.pad_local);
+    }
+    __syncthreads();
+    const int vec_per_row = p.N / 8;
+    const long long total_vec = (long long)c.rs_rows_per_rank * vec_per_row;
+    const size_t slot_elems = (size_t)c.rs_rows_per_rank * p.ldc;
+    const __nv_bfloat16* slots = reinterpret_cast<const __nv_bfloat16*>(c.rs_slots);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c.rs_out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / vec_per_row;
+      const int v = (int)(i - r * vec_per_row);
+      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < c.world; ++s) {
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(slots + s * slot_elems + r * p.ldc + v * 8));
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        acc8[0] += f0.x; acc8[1] += f0.y; acc8[2] += f1.x; acc8[3] += f1.y;
+        acc8[4] += f2.x; acc8[5] += f2.y; acc8[6] += f3.x; acc8[7] += f3.y;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(acc8[0], acc8[1]); o.y = pack_bf16x2(acc8[2], acc8[3]);
+      o.z = pack_bf16x2(acc8[4], acc8[5]); o.w = pack_bf16x2(acc8[6], acc8[7]);
+      *reinterpret_cast<uint4*>(out + r * p.ldc + v * 8) = o;
+    }
+    // last CTA out tells every peer that this rank's receive slot (this parity) is free again
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(c.rs_reduce_counter, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      *c.rs_reduce_counter = 0;
+      __threadfence_system();
+      for (int d = 0; d < c.world; ++d)
+        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, c.epoch);
+    }
   }
 }
 

@@ -1,0 +1,61 @@
+// Plain-C++ declarations shared by the CUDA kernels and the host bindings (no device code in here).
+#pragma once
+#include <stdint.h>
+
+namespace mlb {
+
+constexpr int GEMM_BLOCK_M = 128;
+constexpr int GEMM_BLOCK_K = 64;  // 64 bf16 = one 128B swizzle row
+constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_MAX_PEERS = 8;
+
+enum GemmEpilogue : int {
+  EPI_BF16 = 0,        // C(bf16) = acc
+  EPI_F32_ACCUM = 1,   // C(fp32) += acc      (wgrad into main_grad)
+  EPI_F32 = 2,         // C(fp32) = acc
+  EPI_BF16_ACCUM = 3,  // C(bf16) += acc
+};
+
+enum GemmMode : int { MODE_PLAIN = 0, MODE_AG_GEMM = 1, MODE_GEMM_RS = 2 };
+
+// int32 slots of the per-rank symmetric signal pad (every rank has the same layout, peers write into it)
+enum PadSlot : int {
+  PAD_AG_READY = 0,   // [src]  : src published its shard for epoch e
+  PAD_AG_ACK = 8,     // [rdr]  : rdr finished reading my shard of epoch e
+  PAD_RS_ARRIVED = 16,  // [src]: cumulative number of tiles src delivered into my receive slots
+  PAD_RS_FREE = 24,   // [dst]  : dst finished reducing epoch e (its receive slot of parity e may be reused)
+  PAD_ERROR = 32,     // spin-wait timeout marker (debug)
+  PAD_INTS = 64,
+};
+
+struct GemmComm {
+  int rank, world, epoch;
+  int num_comm_ctas;     // AG: trailing CTAs of the grid that pull peer shards
+  int m_rotate_blocks;   // first m-block processed
+  // ---- all-gather side
+  const void* ag_src[GEMM_MAX_PEERS];  // ag_src[p]: peer p's published shard [rows_per_rank, K] (NVLink-mapped)
+  void* ag_dst;                        // local gathered activations [world*rows_per_rank, K]
+  int ag_rows_per_rank;
+  int ag_row_bytes;                    // K * 2
+  int* ag_chunk_flags;                 // local, one per 128-row chunk of the gathered buffer: set to epoch
+  int* ag_read_counters;               // local, [world]: puller CTAs done with peer p (for the ack)
+  // ---- reduce-scatter side
+  void* rs_dst[GEMM_MAX_PEERS];        // rs_dst[d]: my receive slot on rank d: [rows_per_rank, N] bf16
+  const void* rs_slots;                // local receive buffer of this epoch parity: [world][rows_per_rank, N]
+  void* rs_out;                        // local reduced output [rows_per_rank, N]
+  int rs_rows_per_rank;
+  int rs_expected_total;               // cumulative tiles every source will have delivered after this call
+  int* rs_reduce_counter;              // local: CTAs that finished the reduction (last one frees the slot)
+  // ---- signal pads
+  int* pad_local;
+  int* pad_peer[GEMM_MAX_PEERS];
+};
+
+struct GemmParams {
+  void* C;
+  int M, N, K;
+  int ldc;  // elements
+  GemmComm comm;
+};
+
+}  // namespace mlb

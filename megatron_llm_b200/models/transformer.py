@@ -39,6 +39,20 @@ from .module import MegatronModule
 from .norms import LayerNorm, RMSNorm
 
 
+_ROPE_TABLES = {}
+
+
+def _shared_rope_table(cfg, device):
+    """One fp32 [len, hn/2, 2] (cos, sin) table per (config, device), built once and kept on the device."""
+    key = (cfg, str(device))
+    tab = _ROPE_TABLES.get(key)
+    if tab is None:
+        hn, length, theta, scaling = cfg
+        tab = ops.rope_table(hn, length, theta=theta, scaling_factor=scaling, device=device)
+        _ROPE_TABLES[key] = tab
+    return tab
+
+
 class DropPath(MegatronModule):
     """Stochastic depth per sample (input is [s, b, h]; one Bernoulli draw per batch element)."""
 
@@ -202,11 +216,10 @@ class ParallelAttention(MegatronModule):
             sequence_parallel_enabled=args.sequence_parallel, world_size=world_size)
         self.position_embedding_type = args.position_embedding_type
         if self.position_embedding_type == PositionEmbeddingType.rotary:
-            table_len = max(args.max_position_embeddings, args.seq_length)
-            self.register_buffer("rope_table", ops.rope_table(self.hidden_size_per_attention_head, table_len,
-                                                              theta=args.rope_theta,
-                                                              scaling_factor=args.rope_scaling_factor,
-                                                              device=current_device()), persistent=False)
+            # fp32 (cos, sin) table shared by all layers of the process.  NOT a module buffer: ``module.bfloat16()``
+            # (Float16Module) would silently down-cast a buffer and the kernel reads it as float2.
+            self._rope_cfg = (self.hidden_size_per_attention_head, max(args.max_position_embeddings, args.seq_length),
+                              float(args.rope_theta), float(args.rope_scaling_factor))
             # complex table kept for API parity (tools / verify scripts)
             self.freqs_cis = None
 
@@ -237,7 +250,7 @@ class ParallelAttention(MegatronModule):
             if self.position_embedding_type == PositionEmbeddingType.rotary:
                 pid = position_ids if inference_params is None else None
                 mixed = ops.rope_qkv_(mixed, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn,
-                                      self.rope_table, pid, pos_offset)
+                                      _shared_rope_table(self._rope_cfg, mixed.device), pid, pos_offset)
             qkv = mixed.view(sq, b, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn)
             if self.q_per_kv == 1:
                 query_layer = qkv[:, :, :, 0]                                     # view [sq,b,np,hn]

@@ -250,7 +250,10 @@ def _rope_ref(x, table, pos, inverse):
 def _rope_qkv_apply_(mixed, nkv, hpg, hn, table, position_ids, pos_offset, inverse):
     """mixed [s, b, nkv*hpg*hn] viewed as [s, b, nkv, hpg, hn]: rotate the q heads and the k head in place."""
     s, b = mixed.shape[:2]
+    assert table.dtype == torch.float32, "RoPE (cos, sin) table must stay fp32"
     if cuda_ops_available(mixed) and mixed.is_contiguous() and hn % 8 == 0:
+        if position_ids is not None and not position_ids.is_contiguous():
+            position_ids = position_ids.contiguous()
         _C().rope_qkv(mixed, table, position_ids, s * b, b, nkv, hpg, hn, pos_offset, inverse, nkv * hpg * hn)
         _count()
         return mixed
