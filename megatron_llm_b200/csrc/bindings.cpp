@@ -11,6 +11,8 @@ extern "C" {
 int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                   int a_mn_major, int b_mn_major, int epilogue, int block_n, const void* comm, int num_sms,
                   cudaStream_t stream);
+int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                       int a_mn_major, int b_mn_major, int epilogue, int num_sms, cudaStream_t stream);
 int mlb_norm_fwd(int dtype, const void* x, const void* res_in, const void* w, const void* b, void* y, void* res_out,
                  float* mean, float* rstd, int rows, int H, float eps, int rms, cudaStream_t st);
 int mlb_norm_bwd(int dtype, const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
@@ -86,6 +88,11 @@ static void gemm(const torch::Tensor& A, const torch::Tensor& B, torch::Tensor& 
   TORCH_CHECK(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && N % 8 == 0, "gemm: leading dims / N must be multiples of 8");
   c10::cuda::CUDAGuard guard(A.device());
   const void* cp = comm.has_value() ? comm->data_ptr() : nullptr;
+  if (block_n == 512) {  // 2-CTA (cta_group::2) 256x256 tiles
+    CHK(mlb_gemm_bf16_2cta(A.data_ptr(), B.data_ptr(), C.data_ptr(), (int)M, (int)N, (int)K, (int)lda, (int)ldb,
+                           (int)ldc, a_mn, b_mn, (int)epilogue, sms > 0 ? (int)sms : num_sms(), cur()));
+    return;
+  }
   CHK(mlb_gemm_bf16(A.data_ptr(), B.data_ptr(), C.data_ptr(), (int)M, (int)N, (int)K, (int)lda, (int)ldb, (int)ldc,
                     a_mn, b_mn, (int)epilogue, (int)block_n, cp, sms > 0 ? (int)sms : num_sms(), cur()));
 }

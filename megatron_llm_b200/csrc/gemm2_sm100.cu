@@ -1,0 +1,289 @@
+// 2-CTA (cta_group::2) variant of the persistent bf16 GEMM: a pair of SMs in one cluster works on a 256x256 output
+// tile.  Each CTA TMA-loads its 128 rows of A and its 128-row half of B (so B's shared-memory traffic per SM is
+// halved and the smem ring is 6 stages deep instead of 4), the leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (UMMA 256x256x16), accumulators live in both CTAs' TMEM (128 lanes x 256 columns each,
+// double buffered), and each CTA's four epilogue warps drain their own half.
+#include "gemm_types.h"
+#include "ptx.cuh"
+
+#include <cudaTypedefs.h>
+#include <string.h>
+
+namespace mlb {
+
+int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer);
+
+constexpr int G2_BLOCK_M = 256;      // per pair
+constexpr int G2_BLOCK_N = 256;
+constexpr int G2_HALF = 128;         // rows of A / rows of B held by one CTA
+constexpr int G2_STAGES = 6;
+constexpr int G2_A_BYTES = G2_HALF * GEMM_BLOCK_K * 2;   // 16 KB
+constexpr int G2_B_BYTES = G2_HALF * GEMM_BLOCK_K * 2;   // 16 KB
+constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB per CTA per stage
+constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_SMEM_TOTAL = G2_BAR_OFFSET + 256 + 1024;
+
+template <bool A_MN, bool B_MN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const GemmParams p) {
+  constexpr uint32_t TMEM_COLS = 2 * G2_BLOCK_N;  // two accumulator stages
+  constexpr uint32_t IDESC = make_idesc_f16(G2_BLOCK_M, G2_BLOCK_N, A_MN, B_MN, true);
+  constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + G2_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + G2_STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool leader = cta_rank == 0;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < G2_STAGES; ++i) {
+      mbar_init(&full_bar[i], 2);    // one arrival per CTA's producer (only the leader's copy is used)
+      mbar_init(&empty_bar[i], 1);   // tcgen05.commit multicast arrives on both CTAs' copies
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full_bar[i], 1);
+      mbar_init(&tmem_empty_bar[i], 8);  // 4 epilogue warps x 2 CTAs (leader's copy)
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<2>(tmem_ptr_smem, TMEM_COLS);
+    tmem_relinquish<2>();
+  }
+  tc_fence_before();
+  cluster_sync();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  const int num_m = (p.M + G2_BLOCK_M - 1) / G2_BLOCK_M;
+  const int num_n = (p.N + G2_BLOCK_N - 1) / G2_BLOCK_N;
+  const int num_k = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
+  const int total_tiles = num_m * num_n;
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  constexpr int GROUP_M = 8;
+
+  auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    const int per_group = GROUP_M * num_n;
+    const int group = tile / per_group;
+    const int first_m = group * GROUP_M;
+    const int gsize = min(GROUP_M, num_m - first_m);
+    const int in_group = tile - group * per_group;
+    m_blk = first_m + in_group % gsize;
+    n_blk = in_group / gsize;
+  };
+
+  if (warp == 0) {
+    // ================================ TMA producer (both CTAs) ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        int m_blk, n_blk;
+        tile_coords(tile, m_blk, n_blk);
+        const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
+        const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sA = smem + stage * G2_STAGE_BYTES;
+          uint8_t* sB = sA + G2_A_BYTES;
+          if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
+          else mbar_arrive_cluster(&full_bar[stage], 0);
+          const int k0 = kb * GEMM_BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d_2sm(sA, &tmA, &full_bar[stage], k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < G2_HALF / 64; ++i)
+              tma_load_2d_2sm(sA + i * (GEMM_BLOCK_K * 128), &tmA, &full_bar[stage], m0 + i * 64, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d_2sm(sB, &tmB, &full_bar[stage], k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < G2_HALF / 64; ++i)
+              tma_load_2d_2sm(sB + i * (GEMM_BLOCK_K * 128), &tmB, &full_bar[stage], n0 + i * 64, k0);
+          }
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ================================ MMA issuer (leader CTA only) ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * G2_BLOCK_N;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sA = smem_u32(smem + stage * G2_STAGE_BYTES);
+          const uint32_t sB = sA + G2_A_BYTES;
+#pragma unroll
+          for (int k = 0; k < GEMM_BLOCK_K / 16; ++k) {
+            const uint64_t da = A_MN ? make_smem_desc(sA + k * 2048, GEMM_BLOCK_K * 128, 1024, kSwizzle128B)
+                                     : make_smem_desc(sA + k * 32, 16, 1024, kSwizzle128B);
+            const uint64_t db = B_MN ? make_smem_desc(sB + k * 2048, GEMM_BLOCK_K * 128, 1024, kSwizzle128B)
+                                     : make_smem_desc(sB + k * 32, 16, 1024, kSwizzle128B);
+            umma_f16_ss<2>(tmem_d, da, db, IDESC, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit<2>(&empty_bar[stage]);     // frees the stage in BOTH CTAs
+          if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit<2>(&tmem_full_bar[acc]);     // accumulators ready in BOTH CTAs
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================ epilogue (both CTAs) ================================
+    const int q = warp - 4;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+      int m_blk, n_blk;
+      tile_coords(tile, m_blk, n_blk);
+      const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF, n0 = n_blk * G2_BLOCK_N;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+      uint8_t* crow = reinterpret_cast<uint8_t*>(p.C) + (size_t)(row_ok ? row : 0) * p.ldc * OUT_ELEM;
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * G2_BLOCK_N;
+#pragma unroll 1
+      for (int c = 0; c < G2_BLOCK_N / 64; ++c) {
+        uint32_t r0[32], r1[32];
+        tmem_ld_32x32(taddr + c * 64, r0);       // two loads in flight before the wait
+        tmem_ld_32x32(taddr + c * 64 + 32, r1);
+        tmem_ld_wait();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const uint32_t* r = h ? r1 : r0;
+          const int col = n0 + c * 64 + h * 32;
+          if (row_ok && col < p.N) {
+            if constexpr (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) {
+              uint4* dptr = reinterpret_cast<uint4*>(crow + (size_t)col * 2);
+#pragma unroll
+              for (int v = 0; v < 4; ++v) {
+                if (col + v * 8 < p.N) {
+                  uint4 o;
+                  if constexpr (EPI == EPI_BF16_ACCUM) {
+                    const uint4 old = dptr[v];
+                    float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z),
+                           a3 = unpack_bf16x2(old.w);
+                    o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) + a0.x, __uint_as_float(r[v * 8 + 1]) + a0.y);
+                    o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]) + a1.x, __uint_as_float(r[v * 8 + 3]) + a1.y);
+                    o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]) + a2.x, __uint_as_float(r[v * 8 + 5]) + a2.y);
+                    o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]) + a3.x, __uint_as_float(r[v * 8 + 7]) + a3.y);
+                  } else {
+                    o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+                    o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+                    o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+                    o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+                  }
+                  dptr[v] = o;
+                }
+              }
+            } else {
+              float4* dptr = reinterpret_cast<float4*>(crow + (size_t)col * 4);
+#pragma unroll
+              for (int v = 0; v < 8; ++v) {
+                if (col + v * 4 < p.N) {
+                  float4 o = make_float4(__uint_as_float(r[v * 4 + 0]), __uint_as_float(r[v * 4 + 1]),
+                                         __uint_as_float(r[v * 4 + 2]), __uint_as_float(r[v * 4 + 3]));
+                  if constexpr (EPI == EPI_F32_ACCUM) {
+                    const float4 old = dptr[v];
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                  }
+                  dptr[v] = o;
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread is the only waiter
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync();   // nobody may exit (or free TMEM) while the peer can still signal / read it
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<2>(tmem_base, TMEM_COLS);
+  }
+}
+
+template <bool A_MN, bool B_MN, int EPI>
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
+                   cudaStream_t stream) {
+  auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  const int tiles = ((p.M + G2_BLOCK_M - 1) / G2_BLOCK_M) * ((p.N + G2_BLOCK_N - 1) / G2_BLOCK_N);
+  int pairs = num_sms / 2;
+  if (pairs > tiles) pairs = tiles;
+  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  return (int)cudaGetLastError();
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch2_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int sms,
+                         cudaStream_t st) {
+  switch (epi) {
+    case EPI_BF16: return launch2<A_MN, B_MN, EPI_BF16>(a, b, p, sms, st);
+    case EPI_F32_ACCUM: return launch2<A_MN, B_MN, EPI_F32_ACCUM>(a, b, p, sms, st);
+    case EPI_F32: return launch2<A_MN, B_MN, EPI_F32>(a, b, p, sms, st);
+    case EPI_BF16_ACCUM: return launch2<A_MN, B_MN, EPI_BF16_ACCUM>(a, b, p, sms, st);
+  }
+  return -2;
+}
+
+}  // namespace mlb
+
+extern "C" int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
+                                  int ldc, int a_mn_major, int b_mn_major, int epilogue, int num_sms,
+                                  cudaStream_t stream) {
+  using namespace mlb;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  CUtensorMap tmA, tmB;
+  int r;
+  if (!a_mn_major) r = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, G2_HALF);
+  else r = make_tmap_2d_bf16(&tmA, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, GEMM_BLOCK_K);
+  if (r) return 1000 + r;
+  if (!b_mn_major) r = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, G2_HALF);
+  else r = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BLOCK_K);
+  if (r) return 2000 + r;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  if (!a_mn_major && !b_mn_major) return dispatch2_epi<false, false>(epilogue, tmA, tmB, p, num_sms, stream);
+  if (!a_mn_major && b_mn_major) return dispatch2_epi<false, true>(epilogue, tmA, tmB, p, num_sms, stream);
+  if (a_mn_major && b_mn_major) return dispatch2_epi<true, true>(epilogue, tmA, tmB, p, num_sms, stream);
+  return dispatch2_epi<true, false>(epilogue, tmA, tmB, p, num_sms, stream);
+}

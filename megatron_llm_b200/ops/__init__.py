@@ -35,6 +35,18 @@ def launches() -> int:
 _EPI_BF16, _EPI_F32_ACCUM, _EPI_F32, _EPI_BF16_ACCUM = 0, 1, 2, 3
 
 
+def _tile_cfg(M: int, N: int) -> int:
+    """block_n selector passed to the kernel launcher: 0 = 1-CTA kernel with the wave-quantisation heuristic,
+    512 = 2-CTA (cta_group::2) 256x256 tiles.  MLB200_GEMM_2CTA=0/1 forces one or the other."""
+    import os
+    mode = os.environ.get("MLB200_GEMM_2CTA", "auto")
+    if mode == "0":
+        return 0
+    if mode == "1":
+        return 512
+    return 0  # TODO(perf): switch to 512 once the 2-CTA kernel is validated on hardware
+
+
 def _gemm_ok(*ts) -> bool:
     for t in ts:
         if not (t.is_cuda and t.dtype == torch.bfloat16):
@@ -65,7 +77,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     N = b.size(0)
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-    _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), False, False, _EPI_BF16, 0, comm, sms)
+    _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), False, False, _EPI_BF16, _tile_cfg(M, N), comm, sms)
     _count()
     return out
 
@@ -84,7 +96,7 @@ def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     N = b.size(1)
     if out is None:
         out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
-    _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), False, True, _EPI_BF16, 0, comm, sms)
+    _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), False, True, _EPI_BF16, _tile_cfg(M, N), comm, sms)
     _count()
     return out
 
@@ -110,7 +122,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         epi = _EPI_F32_ACCUM if accumulate else _EPI_F32
     else:
         epi = _EPI_BF16_ACCUM if accumulate else _EPI_BF16
-    _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), True, True, epi, 0, None, sms)
+    _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), True, True, epi, _tile_cfg(M, N), None, sms)
     _count()
     return out
 

@@ -159,6 +159,16 @@ class DistributedDataParallel(DistributedDataParallelBase):
     def bind_symmetric_communicator(self, comm):
         self._symm = comm
 
+    def rehome_grad_buffer(self, gdt, new_storage: torch.Tensor):
+        """Move the grad buffer of dtype ``gdt`` into ``new_storage`` (symmetric memory) and re-point every
+        ``param.main_grad`` view at it."""
+        buf = self._grad_buffers[gdt]
+        assert new_storage.numel() >= buf.numel_padded and new_storage.dtype == gdt
+        new_storage[:buf.numel_padded].copy_(buf.data)
+        buf.data = new_storage[:buf.numel_padded]
+        for p, (s, e) in self._grad_buffer_param_index_map[gdt].items():
+            p.main_grad = buf.get(p.data.shape, s)
+
     def _make_param_hook(self, param):
         def hook(*unused):
             if param.grad is not None:

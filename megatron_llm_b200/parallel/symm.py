@@ -1,0 +1,224 @@
+"""Symmetric-memory communicators: peer-mapped buffers + signal pads for the fused collective kernels.
+
+The reference only ever calls NCCL through ``torch.distributed``.  Here every tensor-parallel /
+data-parallel group that lives inside one NVSwitch domain gets a small symmetric heap (allocated and exchanged with
+``torch.distributed._symmetric_memory``: VMM allocations mapped into all peers) and the hand-written kernels do the
+transfers themselves:
+
+* :class:`TPCommunicator`  -- ``ag_gemm`` (all-gather -> GEMM) and ``gemm_rs`` (GEMM -> reduce-scatter), see
+  ``csrc/gemm_sm100.cuh`` MODE_AG_GEMM / MODE_GEMM_RS.
+* :class:`DPCommunicator`  -- bucketed two-shot all-reduce / reduce-scatter of the fp32 gradient buffer fused with the
+  1/DP scale (``csrc/comm.cu``), launched from the backward hooks on a side stream.
+
+Everything degrades to the NCCL path (the checked fallback) if symmetric memory cannot be set up.
+"""
+from __future__ import annotations
+
+import os
+from typing import Optional
+
+import torch
+import torch.distributed as dist
+
+from ..ops import _ext
+from . import fused_tp
+from . import state as ps
+
+_PAD_INTS = 64
+
+
+def _symm():
+    import torch.distributed._symmetric_memory as symm_mem
+    return symm_mem
+
+
+def _alloc_symmetric(numel: int, dtype, device, group):
+    """(local tensor, handle) for a buffer mapped into every rank of ``group``."""
+    sm = _symm()
+    t = sm.empty(numel, dtype=dtype, device=device)
+    hdl = sm.rendezvous(t, group)
+    return t, hdl
+
+
+class TPCommunicator:
+    """Fused GEMM+collective for one tensor-parallel group.
+
+    Buffers (per rank, symmetric):
+      xs   [max_rows_per_rank * max_k]            bf16  -- this rank's published activation shard (all-gather source)
+      rs   [2][world][max_rows_per_rank * max_n]  bf16  -- receive slots for reduce-scatter tiles (2 epoch parities)
+      pad  [64] int32                                    -- ready / ack / arrived / free signals
+    """
+
+    def __init__(self, group, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 8):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.max_rows, self.max_k, self.max_n = max_rows_per_rank, max_k, max_n
+        self.num_comm_ctas = num_comm_ctas
+        self.enabled = False
+        self.mod = _ext.load()
+        self.xs, self.h_xs = _alloc_symmetric(max_rows_per_rank * max_k, torch.bfloat16, self.device, group)
+        self.rs, self.h_rs = _alloc_symmetric(2 * self.world * max_rows_per_rank * max_n, torch.bfloat16, self.device,
+                                              group)
+        self.pad, self.h_pad = _alloc_symmetric(_PAD_INTS, torch.int32, self.device, group)
+        self.pad.zero_()
+        self.xs_ptrs = [int(p) for p in self.h_xs.buffer_ptrs]
+        self.rs_ptrs = [int(p) for p in self.h_rs.buffer_ptrs]
+        self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
+        max_chunks = self.world * max_rows_per_rank // 128
+        self.chunk_flags = torch.zeros(max(max_chunks, 1), dtype=torch.int32, device=self.device)
+        self.read_counters = torch.zeros(8, dtype=torch.int32, device=self.device)
+        self.reduce_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.ag_epoch = 0
+        self.rs_epoch = 0
+        self.rs_arrived_total = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        self.enabled = True
+
+    # -------------------------------------------------------------------------------------------
+    def supports(self, rows_per_rank: int, k: int, n: int) -> bool:
+        return (self.enabled and rows_per_rank % 128 == 0 and rows_per_rank <= self.max_rows and k % 8 == 0
+                and n % 8 == 0)
+
+    def ag_gemm(self, x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None):
+        """x_shard [m, ..., K] (this rank's rows) -> (out [world*m*..., N], gathered [world*m, ..., K])."""
+        lead = x_shard.shape[:-1]
+        K = x_shard.size(-1)
+        x2d = x_shard.reshape(-1, K)
+        m = x2d.size(0)
+        N = weight.size(1) if transposed_weight else weight.size(0)
+        assert m <= self.max_rows and K <= self.max_k and m % 128 == 0, (m, K, self.max_rows, self.max_k)
+        # publish my shard (stream-ordered before the kernel; the previous call's kernel only retired after every
+        # peer had acknowledged reading the old content)
+        self.xs[: m * K].view(m, K).copy_(x2d)
+        gathered = torch.empty((self.world * m, K), dtype=torch.bfloat16, device=self.device)
+        if out is None:
+            out = torch.empty((self.world * m, N), dtype=torch.bfloat16, device=self.device)
+        self.ag_epoch += 1
+        w = weight if weight.stride(-1) == 1 else weight.contiguous()
+        self.mod.fused_ag_gemm(gathered, w, out, transposed_weight, self.xs_ptrs, m, self.chunk_flags,
+                               self.read_counters, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
+                               self.ag_epoch, self.num_comm_ctas, 0)
+        _ext.count()
+        return out, gathered.view(self.world * lead[0], *lead[1:], K)
+
+    def gemm_rs(self, x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
+        """reduce_scatter_rows(x2d [M, K] @ W^T or W) -> [M/world, N]."""
+        M, K = x2d.shape
+        N = weight.size(1) if transposed_weight else weight.size(0)
+        m = M // self.world
+        assert m <= self.max_rows and N <= self.max_n and m % 128 == 0, (m, N)
+        self.rs_epoch += 1
+        parity = self.rs_epoch % 2
+        slot_elems = m * N
+        # my receive slot on rank d for this parity: rs_d[parity][src=self.rank]
+        base = (parity * self.world) * self.max_rows * self.max_n
+        rs_dst = [self.rs_ptrs[d] + 2 * (base + self.rank * slot_elems) for d in range(self.world)]
+        rs_slots = self.rs_ptrs[self.rank] + 2 * base
+        num_n_256 = None  # tile count is computed with the same heuristic as the kernel launcher
+        out = torch.empty((m, N), dtype=torch.bfloat16, device=self.device)
+        tiles_per_dst = (m // 128) * self._num_n_tiles(M, N)
+        self.rs_arrived_total += tiles_per_dst
+        x = x2d if (x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0) else x2d.contiguous()
+        w = weight if weight.stride(-1) == 1 else weight.contiguous()
+        self.mod.fused_gemm_rs(x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total,
+                               self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
+                               self.rs_epoch, 0)
+        _ext.count()
+        return out
+
+    def _num_n_tiles(self, M: int, N: int) -> int:
+        """Mirror of ``pick_block_n`` in csrc/gemm_sm100.cu (the arrival counters count output tiles)."""
+        sms = self.mod.num_sms()
+
+        def cost(bn):
+            tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+            return ((tiles + sms - 1) // sms) * bn
+
+        bn = 256 if cost(256) <= cost(128) else 128
+        return (N + bn - 1) // bn
+
+    def error_flag(self) -> int:
+        return int(self.pad[32].item())
+
+
+class DPCommunicator:
+    """Peer-memory gradient reduction for one data-parallel group: the whole fp32 grad buffer is symmetric."""
+
+    def __init__(self, group, numel_padded: int, num_ctas: int = 32):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.mod = _ext.load()
+        self.num_ctas = num_ctas
+        self.enabled = False
+        self.buffer, self.h_buf = _alloc_symmetric(numel_padded, torch.float32, self.device, group)
+        self.buffer.zero_()
+        self.pad, self.h_pad = _alloc_symmetric(_PAD_INTS, torch.int32, self.device, group)
+        self.pad.zero_()
+        self.buf_ptrs = [int(p) for p in self.h_buf.buffer_ptrs]
+        self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
+        self.epoch = 0
+        self.stream = torch.cuda.Stream(priority=-1)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        self.enabled = True
+
+    def reduce_bucket(self, view: torch.Tensor, start: int, numel_padded: int, reduce_scatter: bool):
+        """``view`` = buffer[start:end] (a slice of the symmetric grad buffer).  Returns an object with ``wait()``."""
+        n = view.numel()
+        assert n % (self.world * 4) == 0
+        self.epoch += 1
+        ev = torch.cuda.Event()
+        ev.record()                       # the bucket's last gradient was produced on the current stream
+        with torch.cuda.stream(self.stream):
+            self.stream.wait_event(ev)
+            peers = [p + 4 * start for p in self.buf_ptrs]
+            self.mod.dp_reduce(view, peers, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
+                               self.epoch, 1.0 / self.world, reduce_scatter, self.num_ctas)
+            done = torch.cuda.Event()
+            done.record()
+        _ext.count()
+
+        class _Handle:
+            def wait(self_inner):
+                torch.cuda.current_stream().wait_event(done)
+        return _Handle()
+
+
+def bind_tp_communicator(args) -> Optional[TPCommunicator]:
+    """Create the TP group's communicator sized for this model and route ColumnParallel/RowParallel through it."""
+    if os.environ.get("MLB200_FUSED_TP", "1") == "0":
+        return None
+    tp = ps.get_tensor_model_parallel_world_size()
+    rows = args.seq_length * args.micro_batch_size // tp
+    if rows % 128 != 0:
+        return None
+    ffn = args.ffn_hidden_size * (2 if args.glu_activation else 1)
+    max_k = max(args.hidden_size, args.ffn_hidden_size // tp, ffn // tp)
+    vocab_shard = getattr(args, "padded_vocab_size", 0) // tp
+    max_n = max(args.hidden_size, ffn // tp, vocab_shard)
+    comm = TPCommunicator(ps.get_tensor_model_parallel_group(), rows, max_k, max_n,
+                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "8")))
+    fused_tp.bind(comm)
+    return comm
+
+
+def bind_dp_communicator(ddp_module, group=None) -> Optional[DPCommunicator]:
+    """Move a LocalDDP grad buffer into symmetric memory and reduce its buckets with the peer-memory kernel."""
+    if os.environ.get("MLB200_FUSED_DP", "1") == "0":
+        return None
+    group = group or ps.get_data_parallel_group()
+    if dist.get_world_size(group) == 1:
+        return None
+    bufs = ddp_module.grad_buffers()
+    if torch.float32 not in bufs:
+        return None
+    mb = bufs[torch.float32]
+    comm = DPCommunicator(group, mb.numel_padded)
+    ddp_module.rehome_grad_buffer(torch.float32, comm.buffer)
+    ddp_module.bind_symmetric_communicator(comm)
+    return comm

@@ -170,6 +170,14 @@ def get_model(model_provider_func: Callable, model_type=ModelType.encoder_or_dec
             if args.data_parallel_random_init:
                 for m in model:
                     m.broadcast_params()
+            if use_cuda() and args.distributed_backend == "nccl" and getattr(args, "fused_dp_comm", True) \
+                    and ps.get_data_parallel_world_size() > 1:
+                try:
+                    from .parallel import symm
+                    for m in model:
+                        symm.bind_dp_communicator(m)
+                except Exception as e:  # the NCCL bucketed path is the checked fallback
+                    print_rank_0(f"WARNING: peer-memory DP reduction unavailable ({e!r}); using NCCL")
         else:
             raise NotImplementedError("Unknown DDP implementation specified: {}. Exiting.".format(args.DDP_impl))
     return model

@@ -1,0 +1,83 @@
+"""Fused GEMM+collective kernels and the peer-memory DP reduction vs. the unfused NCCL path (needs >= 2 B200s)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+
+from tests.dist_utils import run_distributed
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+
+def _tp_kernels(rank, world):
+    from megatron_llm_b200.parallel import state as ps
+    from megatron_llm_b200.parallel.symm import TPCommunicator
+    ps.initialize_model_parallel(world, 1)
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(100 + rank)
+    m, K, N = 256, 512, 768
+    comm = TPCommunicator(ps.get_tensor_model_parallel_group(), max_rows_per_rank=512, max_k=2048, max_n=2048,
+                          num_comm_ctas=4)
+    group = ps.get_tensor_model_parallel_group()
+    for it in range(4):
+        # ---- all-gather -> GEMM (W [N,K]) and the transposed-weight form (W [K,N])
+        x = torch.randn(m, K, device=dev, dtype=torch.bfloat16)
+        torch.manual_seed(7 + it)
+        w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.05
+        wt = torch.randn(K, N, device=dev, dtype=torch.bfloat16) * 0.05
+        full = torch.empty(world * m, K, device=dev, dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(full, x, group=group)
+        out, gathered = comm.ag_gemm(x, w, False)
+        torch.cuda.synchronize()
+        assert torch.equal(gathered, full), f"gathered mismatch it={it}"
+        ref = full.float() @ w.float().t()
+        assert (out.float() - ref).abs().max() <= 2e-2 * ref.abs().max(), f"ag_gemm it={it}"
+        out2, _ = comm.ag_gemm(x, wt, True)
+        ref2 = full.float() @ wt.float()
+        assert (out2.float() - ref2).abs().max() <= 2e-2 * ref2.abs().max(), f"ag_gemm(T) it={it}"
+        # ---- GEMM -> reduce-scatter
+        M = world * m
+        a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
+        part = (a.float() @ w.float().t())
+        refs = torch.empty(m, N, device=dev, dtype=torch.float32)
+        dist.reduce_scatter_tensor(refs, part, group=group)
+        got = comm.gemm_rs(a, w, False)
+        torch.cuda.synchronize()
+        assert (got.float() - refs).abs().max() <= 3e-2 * refs.abs().max(), f"gemm_rs it={it}"
+        part2 = (a.float() @ wt.float())
+        dist.reduce_scatter_tensor(refs, part2, group=group)
+        got2 = comm.gemm_rs(a, wt, True)
+        assert (got2.float() - refs).abs().max() <= 3e-2 * refs.abs().max(), f"gemm_rs(T) it={it}"
+    assert comm.error_flag() == 0, "a spin-wait timed out"
+    ps.destroy_model_parallel()
+
+
+def test_fused_tp_kernels_match_nccl():
+    run_distributed(_tp_kernels, 2, backend="nccl")
+
+
+def _dp_reduce(rank, world):
+    from megatron_llm_b200.parallel import state as ps
+    from megatron_llm_b200.parallel.symm import DPCommunicator
+    ps.initialize_model_parallel(1, 1)
+    dev = torch.device("cuda", rank)
+    n = 1 << 20
+    comm = DPCommunicator(ps.get_data_parallel_group(), n)
+    for it in range(3):
+        torch.manual_seed(rank * 10 + it)
+        g = torch.randn(n, device=dev)
+        ref = g.clone()
+        dist.all_reduce(ref, group=ps.get_data_parallel_group())
+        ref /= world
+        comm.buffer.copy_(g)
+        h = comm.reduce_bucket(comm.buffer[: n // 2], 0, n, reduce_scatter=False)
+        h2 = comm.reduce_bucket(comm.buffer[n // 2:], n // 2, n, reduce_scatter=False)
+        h.wait(); h2.wait()
+        torch.cuda.synchronize()
+        assert torch.allclose(comm.buffer, ref, atol=1e-5), f"dp all-reduce it={it}"
+    ps.destroy_model_parallel()
+
+
+def test_dp_peer_memory_allreduce():
+    run_distributed(_dp_reduce, 2, backend="nccl")
