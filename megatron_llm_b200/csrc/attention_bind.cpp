@@ -1,3 +1,73 @@
 // Bindings for the sm_100a attention kernels (attention_sm100.cu).
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
-void register_attention(pybind11::module_& m) { (void)m; }
+
+#include <cuda_runtime.h>
+
+extern "C" {
+int mlb_attn_fwd(const void* q, const void* k, const void* v, const long long* q_str, const long long* k_str,
+                 const long long* v_str, int q_map_heads, int k_map_heads, int v_map_heads, const int* head_map,
+                 int q_per_kv, int seq, int batch, int heads, int window, float softmax_scale, void* out,
+                 long long out_s_stride, long long out_b_stride, float* lse, cudaStream_t stream);
+int mlb_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout, const long long* q_str,
+                 const long long* k_str, const long long* v_str, const long long* o_str, const long long* do_str,
+                 int q_map_heads, int k_map_heads, int v_map_heads, const int* head_map, int q_per_kv, int seq,
+                 int batch, int heads, int window, float softmax_scale, const float* lse, float* delta, void* dq,
+                 void* dk, void* dv, const long long* dq_str, const long long* dk_str, const long long* dv_str,
+                 cudaStream_t stream);
+}
+
+static cudaStream_t cur() { return at::cuda::getCurrentCUDAStream().stream(); }
+#define CHK(call) do { int _e = (call); TORCH_CHECK(_e == 0, #call " failed with code ", _e); } while (0)
+
+// tensors are [b, s, n, hn] views (any strides, hn contiguous); strides passed as (head, seq, batch)
+static void strides_of(const torch::Tensor& t, long long* s) {
+  TORCH_CHECK(t.dim() == 4 && t.stride(3) == 1 && t.size(3) == 128, "attention: expected [b, s, n, 128] with contiguous hn");
+  s[0] = t.stride(2); s[1] = t.stride(1); s[2] = t.stride(0);
+}
+
+// Separate q/k/v tensors.  Returns (out as a [b, s, n, hn] view over [s, b, n, hn] storage, lse [b, n, s]).
+static std::vector<torch::Tensor> attn_fwd(const torch::Tensor& q, const torch::Tensor& k, const torch::Tensor& v,
+                                           bool causal, int64_t window, double scale) {
+  TORCH_CHECK(causal, "attn_fwd: causal only");
+  c10::cuda::CUDAGuard guard(q.device());
+  const int b = q.size(0), s = q.size(1), n = q.size(2), nkv = k.size(2);
+  long long qs[3], ks[3], vs[3];
+  strides_of(q, qs); strides_of(k, ks); strides_of(v, vs);
+  auto out = torch::empty({s, b, n, 128}, q.options());
+  auto lse = torch::empty({b, n, s}, q.options().dtype(torch::kFloat32));
+  const int g = n / nkv;
+  int head_map[6] = {g, 0, 1, 0, 1, 0};
+  CHK(mlb_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), qs, ks, vs, n, nkv, nkv, head_map, g, s, b, n,
+                   (int)window, (float)scale, out.data_ptr(), (long long)b * n * 128, (long long)n * 128,
+                   lse.data_ptr<float>(), cur()));
+  return {out.permute({1, 0, 2, 3}), lse};
+}
+
+// Returns (dq, dk, dv) as [b, s, n, hn] views over [s, b, n, hn] storage.
+static std::vector<torch::Tensor> attn_bwd(const torch::Tensor& dout, const torch::Tensor& q, const torch::Tensor& k,
+                                           const torch::Tensor& v, const torch::Tensor& out, const torch::Tensor& lse,
+                                           bool causal, int64_t window, double scale) {
+  TORCH_CHECK(causal, "attn_bwd: causal only");
+  c10::cuda::CUDAGuard guard(q.device());
+  const int b = q.size(0), s = q.size(1), n = q.size(2), nkv = k.size(2);
+  long long qs[3], ks[3], vs[3], os[3], ds[3], dqs[3], dks[3], dvs[3];
+  strides_of(q, qs); strides_of(k, ks); strides_of(v, vs); strides_of(out, os); strides_of(dout, ds);
+  auto dq = torch::empty({s, b, n, 128}, q.options()).permute({1, 0, 2, 3});
+  auto dk = torch::empty({s, b, nkv, 128}, q.options()).permute({1, 0, 2, 3});
+  auto dv = torch::empty({s, b, nkv, 128}, q.options()).permute({1, 0, 2, 3});
+  strides_of(dq, dqs); strides_of(dk, dks); strides_of(dv, dvs);
+  auto delta = torch::empty({b, n, s}, q.options().dtype(torch::kFloat32));
+  const int g = n / nkv;
+  int head_map[6] = {g, 0, 1, 0, 1, 0};
+  CHK(mlb_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr(), dout.data_ptr(), qs, ks, vs, os, ds, n,
+                   nkv, nkv, head_map, g, s, b, n, (int)window, (float)scale, lse.data_ptr<float>(),
+                   delta.data_ptr<float>(), dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dqs, dks, dvs, cur()));
+  return {dq, dk, dv};
+}
+
+void register_attention(pybind11::module_& m) {
+  m.def("attn_fwd", &attn_fwd);
+  m.def("attn_bwd", &attn_bwd);
+}

@@ -1,0 +1,436 @@
+// Backward of the sm_100a attention (see attention_sm100.cu for the overall design).
+//
+//   delta   : D[b,h,s] = sum_d dO * O                                   (row-wise, memory bound)
+//   dK/dV   : one CTA per (kv tile, kv head, batch).  For every query tile i >= j (causal) of every query head in the
+//             GQA group:   S^T = K Q^T, dP^T = V dO^T  (kv rows on the TMEM lanes, queries on the columns)
+//                          P^T = exp2(S^T c - lse[q]),  dS^T = P^T o (dP^T - D[q]) * scale       (bf16, written in place
+//                          over the fp32 tiles they were computed from)
+//                          dV += P^T dO,  dK += dS^T Q                   (A operand from TMEM, B = MN-major view of the
+//                                                                         same smem tile that fed the first two MMAs)
+//   dQ      : one CTA per (query tile, query head, batch).  For every kv tile j <= i:
+//                          S = Q K^T, dP = dO V^T, dS = P o (dP - D) * scale (in place), dQ += dS K
+// Every accumulator lives in TMEM; nothing is accumulated with atomics, so the result is deterministic.
+#include "attention_common.cuh"
+
+namespace mlb {
+
+struct AttnBwdParams {
+  HeadMap hm;
+  int seq, batch, heads, kv_heads;
+  int window;
+  float scale, scale_log2;
+  const float* lse;     // [b, heads, seq]
+  const float* delta;   // [b, heads, seq]
+  RowAddr dq, dk, dv;   // strided outputs ([seq, batch, heads, 128])
+};
+
+// ------------------------------------------------------------------------------------------------
+// delta = rowsum(dO * O)
+// ------------------------------------------------------------------------------------------------
+__global__ void attn_delta_kernel(RowAddr o, RowAddr dout, float* __restrict__ delta, int seq, int batch, int heads) {
+  const int warps_per_block = blockDim.x >> 5;
+  const long long row_id = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  const long long total = (long long)seq * batch * heads;
+  if (row_id >= total) return;
+  const int lane = threadIdx.x & 31;
+  const int s = (int)(row_id % seq);
+  const int h = (int)((row_id / seq) % heads);
+  const int b = (int)(row_id / ((long long)seq * heads));
+  const uint2 a = *reinterpret_cast<const uint2*>(o.row(s, b, h) + lane * 4);
+  const uint2 g = *reinterpret_cast<const uint2*>(dout.row(s, b, h) + lane * 4);
+  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+  float v = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
+  v = warp_sum(v);
+  if (lane == 0) delta[((long long)b * heads + h) * seq + s] = v;
+}
+
+// TMEM column map (dK/dV kernel): the bf16 P^T / dS^T tiles alias the first 64 columns of the fp32 tiles
+constexpr uint32_t KV_ST = 0, KV_DPT = 128, KV_DV = 256, KV_DK = 384;
+constexpr int BWD_SMEM = 6 * AT_TILE_BYTES + 2 * 2 * 128 * 4 + 256 + 1024;   // K, V, 2 x (Q, dO), 2 x (lse, D)
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                     const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + AT_TILE_BYTES;
+  uint8_t* sQ = smem + 2 * AT_TILE_BYTES;     // 2 stages
+  uint8_t* sDO = smem + 4 * AT_TILE_BYTES;    // 2 stages
+  float* sLse = reinterpret_cast<float*>(smem + 6 * AT_TILE_BYTES);   // [2][128]  (log2 units)
+  float* sD = sLse + 2 * 128;                                          // [2][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sD + 2 * 128);
+  uint64_t* kv_full = bars;        // K and V landed
+  uint64_t* in_full = bars + 1;    // [2] Q + dO of stage s landed
+  uint64_t* in_empty = bars + 3;   // [2] dV/dK MMAs of the tile finished reading stage s
+  uint64_t* sdp_full = bars + 5;   // S^T and dP^T computed
+  uint64_t* pds_full = bars + 6;   // P^T and dS^T written (4 warps)
+  uint64_t* acc_done = bars + 7;   // all MMAs retired (epilogue)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int kv0 = j * AT_N;
+  const int n_q_tiles = p.seq / AT_M;
+  int i_hi = n_q_tiles - 1;
+  if (p.window > 0) i_hi = min(i_hi, (kv0 + AT_N - 1 + p.window) / AT_M);
+  const int tiles_per_head = i_hi - j + 1;
+  const int g = p.hm.q_per_kv;
+  const int n_iter = tiles_per_head * g;     // iteration it -> (head hq = it / tiles_per_head, tile i = j + it % tiles)
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc<1>(tmem_ptr_smem, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  constexpr uint32_t ID_KK = make_idesc_f16(AT_N, AT_M, false, false, true);   // A K-major smem, B K-major smem
+  constexpr uint32_t ID_TS = make_idesc_f16(AT_N, AT_D, false, true, true);    // A from TMEM, B MN-major smem
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(kv_full, 2 * AT_TILE_BYTES);
+      load_tile(sK, &tmK, kv_full, p.hm.k(kvh), kv0, b);
+      load_tile(sV, &tmV, kv_full, p.hm.v(kvh), kv0, b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const int hq = kvh * g + it / tiles_per_head;
+        const int q0 = (j + it % tiles_per_head) * AT_M;
+        mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&in_full[st], 2 * AT_TILE_BYTES);
+        load_tile(sQ + st * AT_TILE_BYTES, &tmQ, &in_full[st], p.hm.q(hq), q0, b);
+        load_tile(sDO + st * AT_TILE_BYTES, &tmDO, &in_full[st], hq, q0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
+      mbar_wait(kv_full, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t aQ = smem_u32(sQ + st * AT_TILE_BYTES), aDO = smem_u32(sDO + st * AT_TILE_BYTES);
+        mbar_wait(&in_full[st], (it >> 1) & 1);
+        tc_fence_after();
+        // S^T = K Q^T ; dP^T = V dO^T      (the previous tile's dV/dK MMAs precede these in the tensor pipe, so the
+        //                                   aliased P^T/dS^T columns are free by the time they are overwritten)
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_f16_ss<1>(tmem + KV_ST, desc_kmajor(aK, k), desc_kmajor(aQ, k), ID_KK, k != 0);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_f16_ss<1>(tmem + KV_DPT, desc_kmajor(aV, k), desc_kmajor(aDO, k), ID_KK, k != 0);
+        umma_commit<1>(sdp_full);
+        mbar_wait(pds_full, it & 1);
+        tc_fence_after();
+        // dV += P^T dO ; dK += dS^T Q
+#pragma unroll
+        for (int k = 0; k < AT_M / 16; ++k)
+          umma_f16_ts(tmem + KV_DV, tmem + KV_ST + k * 8, desc_mnmajor(aDO, k), ID_TS, (it | k) != 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < AT_M / 16; ++k)
+          umma_f16_ts(tmem + KV_DK, tmem + KV_DPT + k * 8, desc_mnmajor(aQ, k), ID_TS, (it | k) != 0 ? 1u : 0u);
+        umma_commit<1>(&in_empty[st]);
+      }
+      umma_commit<1>(acc_done);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int r = q * 32 + lane;          // kv row inside the tile (TMEM lane)
+    const int kv = kv0 + r;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    for (int it = 0; it < n_iter; ++it) {
+      const int st = it & 1;
+      const int hq = kvh * g + it / tiles_per_head;
+      const int q0 = (j + it % tiles_per_head) * AT_M;
+      // per-query statistics of this tile -> smem (one value per thread), visible to the 128 softmax threads
+      const long long stat = ((long long)b * p.heads + hq) * p.seq + q0 + r;
+      sLse[st * 128 + r] = p.lse[stat] * 1.4426950408889634f;
+      sD[st * 128 + r] = p.delta[stat];
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      const bool need_mask = (q0 < kv0 + AT_N - 1) || (p.window > 0 && q0 + AT_M - 1 > kv0 + p.window);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(tmem + lane_addr + KV_ST + c * 32, s);
+        tmem_ld_32x32(tmem + lane_addr + KV_DPT + c * 32, dp);
+        tmem_ld_wait();
+        uint32_t pk[16], dk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float pv[2], dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = c * 32 + 2 * i + e;     // query index inside the tile
+            float pe = fast_exp2(__uint_as_float(s[2 * i + e]) * p.scale_log2 - sLse[st * 128 + col]);
+            if (need_mask) {
+              const int qrow = q0 + col;
+              if (kv > qrow || (p.window > 0 && kv < qrow - p.window)) pe = 0.f;
+            }
+            pv[e] = pe;
+            dv[e] = pe * (__uint_as_float(dp[2 * i + e]) - sD[st * 128 + col]) * p.scale;
+          }
+          pk[i] = pack_bf16x2(pv[0], pv[1]);
+          dk[i] = pack_bf16x2(dv[0], dv[1]);
+        }
+        tmem_st_32x16(tmem + lane_addr + KV_ST + c * 16, pk);     // in place: only already-consumed columns
+        tmem_st_32x16(tmem + lane_addr + KV_DPT + c * 16, dk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(pds_full);
+    }
+    // epilogue: dV, dK -> bf16
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    if (kv < p.seq) {
+      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh) - p.hm.v_off + 0);   // output tensors have their own layout:
+      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh) - p.hm.k_off + 0);   // head coordinate = group index
+      dvrow = p.dv.row(kv, b, kvh);
+      dkrow = p.dk.row(kv, b, kvh);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t a[32], bb[32];
+        tmem_ld_32x32(tmem + lane_addr + KV_DV + c * 32, a);
+        tmem_ld_32x32(tmem + lane_addr + KV_DK + c * 32, bb);
+        tmem_ld_wait();
+        uint4* d0 = reinterpret_cast<uint4*>(dvrow + c * 32);
+        uint4* d1 = reinterpret_cast<uint4*>(dkrow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(a[i * 8 + 0]), __uint_as_float(a[i * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(a[i * 8 + 2]), __uint_as_float(a[i * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(a[i * 8 + 4]), __uint_as_float(a[i * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(a[i * 8 + 6]), __uint_as_float(a[i * 8 + 7]));
+          d0[i] = o;
+          o.x = pack_bf16x2(__uint_as_float(bb[i * 8 + 0]), __uint_as_float(bb[i * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(bb[i * 8 + 2]), __uint_as_float(bb[i * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(bb[i * 8 + 4]), __uint_as_float(bb[i * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(bb[i * 8 + 6]), __uint_as_float(bb[i * 8 + 7]));
+          d1[i] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<1>(tmem, 512); }
+}
+
+// TMEM column map (dQ kernel)
+constexpr uint32_t Q_S = 0, Q_DP = 128, Q_DQ = 256;
+constexpr int BWD_DQ_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;   // Q, dO, 2 x (K, V)
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
+                   const AttnBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;
+  uint8_t* sDO = smem + AT_TILE_BYTES;
+  uint8_t* sK = smem + 2 * AT_TILE_BYTES;    // 2 stages
+  uint8_t* sV = smem + 4 * AT_TILE_BYTES;    // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* in_full = bars + 1;    // [2]
+  uint64_t* in_empty = bars + 3;   // [2]
+  uint64_t* sdp_full = bars + 5;
+  uint64_t* ds_full = bars + 6;
+  uint64_t* acc_done = bars + 7;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = (int)gridDim.x - 1 - (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = i * AT_M;
+  const int kvh = h / p.hm.q_per_kv;
+  int j_lo = 0;
+  if (p.window > 0) j_lo = max(0, (q0 - p.window) / AT_N);
+  const int n_iter = i - j_lo + 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV); tma_prefetch_desc(&tmDO);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(ds_full, 4);
+    mbar_init(acc_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) { tmem_alloc<1>(tmem_ptr_smem, 512); tmem_relinquish<1>(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  constexpr uint32_t ID_KK = make_idesc_f16(AT_M, AT_N, false, false, true);
+  constexpr uint32_t ID_TS = make_idesc_f16(AT_M, AT_D, false, true, true);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+      load_tile(sQ, &tmQ, q_full, p.hm.q(h), q0, b);
+      load_tile(sDO, &tmDO, q_full, h, q0, b);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const int kv0 = (j_lo + it) * AT_N;
+        mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
+        mbar_arrive_expect_tx(&in_full[st], 2 * AT_TILE_BYTES);
+        load_tile(sK + st * AT_TILE_BYTES, &tmK, &in_full[st], p.hm.k(kvh), kv0, b);
+        load_tile(sV + st * AT_TILE_BYTES, &tmV, &in_full[st], p.hm.v(kvh), kv0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
+      mbar_wait(q_full, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        const int st = it & 1;
+        const uint32_t aK = smem_u32(sK + st * AT_TILE_BYTES), aV = smem_u32(sV + st * AT_TILE_BYTES);
+        mbar_wait(&in_full[st], (it >> 1) & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_f16_ss<1>(tmem + Q_S, desc_kmajor(aQ, k), desc_kmajor(aK, k), ID_KK, k != 0);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_f16_ss<1>(tmem + Q_DP, desc_kmajor(aDO, k), desc_kmajor(aV, k), ID_KK, k != 0);
+        umma_commit<1>(sdp_full);
+        mbar_wait(ds_full, it & 1);
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < AT_N / 16; ++k)
+          umma_f16_ts(tmem + Q_DQ, tmem + Q_DP + k * 8, desc_mnmajor(aK, k), ID_TS, (it | k) != 0 ? 1u : 0u);
+        umma_commit<1>(&in_empty[st]);
+      }
+      umma_commit<1>(acc_done);
+    }
+  } else if (warp >= 4) {
+    const int q = warp - 4;
+    const int r = q * 32 + lane;
+    const int row = q0 + r;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const long long stat = ((long long)b * p.heads + h) * p.seq + row;
+    const float lse2 = p.lse[stat] * 1.4426950408889634f;
+    const float dlt = p.delta[stat];
+    for (int it = 0; it < n_iter; ++it) {
+      const int kv0 = (j_lo + it) * AT_N;
+      mbar_wait(sdp_full, it & 1);
+      tc_fence_after();
+      const bool need_mask = (kv0 + AT_N - 1 > row) || (p.window > 0 && kv0 < row - p.window);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t s[32], dp[32];
+        tmem_ld_32x32(tmem + lane_addr + Q_S + c * 32, s);
+        tmem_ld_32x32(tmem + lane_addr + Q_DP + c * 32, dp);
+        tmem_ld_wait();
+        uint32_t dk[16];
+#pragma unroll
+        for (int e2 = 0; e2 < 16; ++e2) {
+          float dv[2];
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = kv0 + c * 32 + 2 * e2 + e;
+            float pe = fast_exp2(__uint_as_float(s[2 * e2 + e]) * p.scale_log2 - lse2);
+            if (need_mask && (col > row || (p.window > 0 && col < row - p.window))) pe = 0.f;
+            dv[e] = pe * (__uint_as_float(dp[2 * e2 + e]) - dlt) * p.scale;
+          }
+          dk[e2] = pack_bf16x2(dv[0], dv[1]);
+        }
+        tmem_st_32x16(tmem + lane_addr + Q_DP + c * 16, dk);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(ds_full);
+    }
+    mbar_wait(acc_done, 0);
+    tc_fence_after();
+    if (row < p.seq) {
+      __nv_bfloat16* dqrow = p.dq.row(row, b, h);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t a[32];
+        tmem_ld_32x32(tmem + lane_addr + Q_DQ + c * 32, a);
+        tmem_ld_wait();
+        uint4* d0 = reinterpret_cast<uint4*>(dqrow + c * 32);
+#pragma unroll
+        for (int i2 = 0; i2 < 4; ++i2) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(a[i2 * 8 + 0]), __uint_as_float(a[i2 * 8 + 1]));
+          o.y = pack_bf16x2(__uint_as_float(a[i2 * 8 + 2]), __uint_as_float(a[i2 * 8 + 3]));
+          o.z = pack_bf16x2(__uint_as_float(a[i2 * 8 + 4]), __uint_as_float(a[i2 * 8 + 5]));
+          o.w = pack_bf16x2(__uint_as_float(a[i2 * 8 + 6]), __uint_as_float(a[i2 * 8 + 7]));
+          d0[i2] = o;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) { tc_fence_after(); tmem_dealloc<1>(tmem, 512); }
+}
+
+}  // namespace mlb
+
+extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                            const long long* q_str, const long long* k_str, const long long* v_str,
+                            const long long* o_str, const long long* do_str, int q_map_heads, int k_map_heads,
+                            int v_map_heads, const int* head_map, int q_per_kv, int seq, int batch, int heads,
+                            int window, float softmax_scale, const float* lse, float* delta, void* dq, void* dk,
+                            void* dv, const long long* dq_str, const long long* dk_str, const long long* dv_str,
+                            cudaStream_t stream) {
+  using namespace mlb;
+  if (seq % AT_M != 0) return -2;
+  CUtensorMap tq, tk, tv, tdo;
+  int r = make_tmap_heads(&tq, q, AT_D, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
+  if (r) return 1000 + r;
+  r = make_tmap_heads(&tk, k, AT_D, k_map_heads, seq, batch, k_str[0], k_str[1], k_str[2], AT_N);
+  if (r) return 2000 + r;
+  r = make_tmap_heads(&tv, v, AT_D, v_map_heads, seq, batch, v_str[0], v_str[1], v_str[2], AT_N);
+  if (r) return 3000 + r;
+  r = make_tmap_heads(&tdo, dout, AT_D, heads, seq, batch, do_str[0], do_str[1], do_str[2], AT_M);
+  if (r) return 4000 + r;
+  AttnBwdParams p;
+  memset(&p, 0, sizeof(p));
+  p.hm.q_group_stride = head_map[0]; p.hm.q_off = head_map[1]; p.hm.k_group_stride = head_map[2];
+  p.hm.k_off = head_map[3]; p.hm.v_group_stride = head_map[4]; p.hm.v_off = head_map[5]; p.hm.q_per_kv = q_per_kv;
+  p.seq = seq; p.batch = batch; p.heads = heads; p.kv_heads = heads / q_per_kv; p.window = window;
+  p.scale = softmax_scale; p.scale_log2 = softmax_scale * 1.4426950408889634f;
+  p.lse = lse; p.delta = delta;
+  p.dq = RowAddr{dq, dq_str[0], dq_str[1], dq_str[2]};
+  p.dk = RowAddr{dk, dk_str[0], dk_str[1], dk_str[2]};
+  p.dv = RowAddr{dv, dv_str[0], dv_str[1], dv_str[2]};
+  RowAddr ro{const_cast<void*>(o), o_str[0], o_str[1], o_str[2]};
+  RowAddr rdo{const_cast<void*>(dout), do_str[0], do_str[1], do_str[2]};
+  const long long rows = (long long)seq * batch * heads;
+  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ro, rdo, delta, seq, batch, heads);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_DQ_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 g1(seq / AT_N, heads / q_per_kv, batch);
+  attn_bwd_dkdv_kernel<<<g1, AT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  dim3 g2(seq / AT_M, heads, batch);
+  attn_bwd_dq_kernel<<<g2, AT_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  return (int)cudaGetLastError();
+}

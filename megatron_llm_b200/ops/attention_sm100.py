@@ -36,7 +36,7 @@ class _AttnFn(torch.autograd.Function):
     def backward(ctx, dout):
         q, k, v, out, lse = ctx.saved_tensors
         mod = _ext.load()
-        dq, dk, dv = mod.attn_bwd(dout.contiguous(), q, k, v, out, lse, ctx.causal,
+        dq, dk, dv = mod.attn_bwd(dout if dout.stride(-1) == 1 else dout.contiguous(), q, k, v, out, lse, ctx.causal,
                                   -1 if ctx.window is None else int(ctx.window), float(ctx.scale))
         _ext.count(2)
         return dq, dk, dv, None, None, None

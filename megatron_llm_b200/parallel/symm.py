@@ -135,7 +135,7 @@ class TPCommunicator:
 
         def cost(bn):
             tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
-            return ((tiles + sms - 1) // sms) * bn
+            return ((tiles + sms - 1) // sms) * bn / (1.0 if bn == 256 else 0.78)
 
         bn = 256 if cost(256) <= cost(128) else 128
         return (N + bn - 1) // bn
