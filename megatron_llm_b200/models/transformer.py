@@ -507,13 +507,13 @@ class ParallelTransformer(MegatronModule):
         if args.virtual_pipeline_model_parallel_size is not None:
             assert args.num_layers % args.virtual_pipeline_model_parallel_size == 0, \
                 "num_layers_per_stage must be divisible by virtual_pipeline_model_parallel_size"
-            assert args.model_type != ModelType.encoder_and_decoder
+            assert model_type != ModelType.encoder_and_decoder
             self.num_layers = self.num_layers // args.virtual_pipeline_model_parallel_size
             offset = ps.get_virtual_pipeline_model_parallel_rank() * (
                 args.num_layers // args.virtual_pipeline_model_parallel_size) + \
                 (ps.get_pipeline_model_parallel_rank() * self.num_layers)
         else:
-            if args.model_type == ModelType.encoder_and_decoder and ps.get_pipeline_model_parallel_world_size() > 1:
+            if model_type == ModelType.encoder_and_decoder and ps.get_pipeline_model_parallel_world_size() > 1:
                 pipeline_rank = ps.get_pipeline_model_parallel_rank()
                 if layer_type == LayerType.encoder:
                     offset = pipeline_rank * self.num_layers
