@@ -67,3 +67,49 @@ def _load_and_forward(rank, world, path, tokens, ref):
     with torch.no_grad():
         out = model(tokens, pos, mask).float()
     assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+def _flatten(d, prefix=""):
+    out = {}
+    for k, v in d.items():
+        if isinstance(v, dict):
+            out.update(_flatten(v, f"{prefix}{k}."))
+        elif torch.is_tensor(v):
+            out[f"{prefix}{k}"] = v
+    return out
+
+
+def test_reshard_roundtrip_and_tp2_logits(tmp_path):
+    """tp1/pp1 -> tp2/pp2 -> tp1/pp1 is the identity; the tp2/pp1 checkpoint reproduces the HF logits on 2 ranks."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from tools import checkpoint_util
+    from weights_conversion.hf_to_megatron import (architecture_args, hf_llama_state_to_meta_names,
+                                                   llama_like_to_megatron, save_megatron)
+    from tests.dist_utils import run_distributed
+    hf = _tiny_hf_llama(2)
+    mw = llama_like_to_megatron(hf_llama_state_to_meta_names(dict(hf.state_dict())), 2, 64, 4, 2, "hf")
+    a = architecture_args("llama2", 7, 2, 64, 4, 2, 176, 96)
+    a.update(max_position_embeddings=64, seq_length=32)
+    src, mid, back, tp2 = (tmp_path / n for n in ("src", "mid", "back", "tp2"))
+    save_megatron(src, mw, a, torch.float32)
+    common = ["--model_type", "llama2", "--true_vocab_size", "96"]
+    checkpoint_util.main(common + ["--load_dir", str(src), "--save_dir", str(mid),
+                                   "--target_tensor_parallel_size", "2", "--target_pipeline_parallel_size", "2"])
+    assert sorted(os.listdir(mid / "release")) == ["mp_rank_00_000", "mp_rank_00_001", "mp_rank_01_000",
+                                                   "mp_rank_01_001"]
+    checkpoint_util.main(common + ["--load_dir", str(mid), "--save_dir", str(back),
+                                   "--target_tensor_parallel_size", "1", "--target_pipeline_parallel_size", "1"])
+    x = _flatten(torch.load(src / "release/mp_rank_00/model_optim_rng.pt", weights_only=False)["model"])
+    y = _flatten(torch.load(back / "release/mp_rank_00/model_optim_rng.pt", weights_only=False)["model"])
+    x = {k.replace("transformer.", "encoder.").replace(".attention.", ".self_attention.")
+         .replace("word_embeddings.weight", "word_embeddings.weight"): v for k, v in x.items()}
+    y = {k.replace("word_embeddings.weight", "word_embeddings.weight"): v for k, v in y.items()}
+    assert set(x) == set(y), set(x) ^ set(y)
+    for k in x:
+        assert torch.equal(x[k], y[k]), k
+    checkpoint_util.main(common + ["--load_dir", str(src), "--save_dir", str(tp2),
+                                   "--target_tensor_parallel_size", "2", "--target_pipeline_parallel_size", "1"])
+    tokens = torch.randint(0, 96, (2, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = hf(tokens).logits
+    run_distributed(_load_and_forward, 2, str(tp2), tokens, ref, backend="gloo")
