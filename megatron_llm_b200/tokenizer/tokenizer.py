@@ -118,10 +118,18 @@ class _NullTokenizer(AbstractTokenizer):
         return {i: str(i) for i in range(self._vocab_size)}
 
     def tokenize(self, text):
-        return [int(x) for x in text.split()]
+        """Integer words map to themselves; anything else to a stable hash bucket (so free text can be smoke-tested)."""
+        import zlib
+        out = []
+        for w in text.split():
+            try:
+                out.append(int(w) % self._vocab_size)
+            except ValueError:
+                out.append(zlib.crc32(w.encode()) % self._vocab_size)
+        return out
 
     def detokenize(self, ids):
-        return " ".join(str(i) for i in ids)
+        return " ".join(str(int(i)) for i in ids)
 
     @property
     def eod(self):
