@@ -113,3 +113,28 @@ def test_reshard_roundtrip_and_tp2_logits(tmp_path):
     with torch.no_grad():
         ref = hf(tokens).logits
     run_distributed(_load_and_forward, 2, str(tp2), tokens, ref, backend="gloo")
+
+
+def test_verify_correctness_script(tmp_path):
+    """verify_correctness.py end to end on CPU: converted tiny Llama vs its HF original on synthetic batches."""
+    import subprocess
+    from weights_conversion.hf_to_megatron import (architecture_args, hf_llama_state_to_meta_names,
+                                                   llama_like_to_megatron, save_megatron)
+    from tests.dist_utils import free_port
+    hf = _tiny_hf_llama(2)
+    hf.save_pretrained(tmp_path / "hf")
+    mw = llama_like_to_megatron(hf_llama_state_to_meta_names(dict(hf.state_dict())), 2, 64, 4, 2, "hf")
+    a = architecture_args("llama2", 7, 2, 64, 4, 2, 176, 96)
+    a.update(max_position_embeddings=64, seq_length=32)
+    save_megatron(tmp_path / "mega", mw, a, torch.float32)
+    env = dict(os.environ, MLB200_FORCE_CPU="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(free_port()), RANK="0",
+               WORLD_SIZE="1", CUDA_VISIBLE_DEVICES="")
+    cmd = [sys.executable, os.path.join(ROOT, "verify_correctness.py"), "--model_name", "llama2", "--load",
+           str(tmp_path / "mega"), "--huggingface_cache", str(tmp_path / "hf"), "--huggingface_device", "cpu",
+           "--data_type", "synthetic", "--tokenizer_type", "NullTokenizer", "--vocab_file", "96", "--no_load_optim",
+           "--no_load_rng", "--finetune", "--train_iters", "10", "--global_batch_size", "1"]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("Max absoulute error")]
+    assert len(lines) == 10
+    assert all(float(l.split("max=")[1].split(",")[0]) < 1e-3 for l in lines), lines
