@@ -20,4 +20,9 @@ def __getattr__(name):
     if name == "T5Model":
         from .t5_model import T5Model
         return T5Model
+    lazy = {"Classification": "classification", "MultipleChoice": "multiple_choice",
+            "BiEncoderModel": "biencoder_model", "PretrainedBertModel": "biencoder_model"}
+    if name in lazy:
+        import importlib
+        return getattr(importlib.import_module(f".{lazy[name]}", __name__), name)
     raise AttributeError(name)

@@ -456,7 +456,9 @@ def _get_num_layers(args, is_encoder_and_decoder_model, is_decoder=False):
             num_layers = (0 if args.standalone_embedding_stage and ps.get_pipeline_model_parallel_rank() == 0
                           else args.num_layers // args.transformer_pipeline_model_parallel_size)
     else:
-        num_layers = args.decoder_num_layers if is_decoder else args.encoder_num_layers
+        # (the reference leaves decoder_num_layers unset when only --num_layers is given; default it)
+        dec = args.decoder_num_layers if args.decoder_num_layers is not None else args.num_layers
+        num_layers = dec if is_decoder else args.encoder_num_layers
     return num_layers
 
 

@@ -1,5 +1,11 @@
 """GPU check of the tcgen05 attention kernels against the fp32 reference (+ timing vs the FA-2 library)."""
-import json, os, sys, torch
+import faulthandler, json, os, sys, time
+faulthandler.enable()
+_t0 = time.time()
+import torch
+def log(m):
+    print(f"[{time.time()-_t0:7.1f}s] {m}", file=sys.stderr, flush=True)
+log("torch imported")
 sys.path.insert(0, ".")
 from megatron_llm_b200.ops import attention_sm100 as A
 from megatron_llm_b200.ops.attention import attention_reference
@@ -11,15 +17,19 @@ def run(b, s, nq, nkv, window, timing):
     k = (torch.randn(b, s, nkv, 128, device=dev) * 0.5).to(torch.bfloat16).requires_grad_(True)
     v = (torch.randn(b, s, nkv, 128, device=dev) * 0.5).to(torch.bfloat16).requires_grad_(True)
     assert A.supported(q, k, v, True, window, 0.0), "kernel not available / shape unsupported"
+    log("inputs ready")
     out = A.attention(q, k, v, True, window, None)
+    torch.cuda.synchronize(); log("fwd done")
     res = {"b": b, "s": s, "nq": nq, "nkv": nkv, "window": window}
     if not timing:
         qr, kr, vr = (t.detach().float().requires_grad_(True) for t in (q, k, v))
         ref = attention_reference(qr, kr, vr, causal=True, window=window)
+        log("reference fwd done")
         res["fwd_err"] = (out.float() - ref).abs().max().item()
         res["fwd_ref_scale"] = ref.abs().max().item()
         do = torch.randn_like(out)
         out.backward(do)
+        torch.cuda.synchronize(); log("bwd done")
         ref.backward(do.float())
         for name, a, bb in (("dq", q.grad, qr.grad), ("dk", k.grad, kr.grad), ("dv", v.grad, vr.grad)):
             res[name + "_err"] = (a.float() - bb).abs().max().item()
