@@ -12,6 +12,9 @@
 // Every accumulator lives in TMEM; nothing is accumulated with atomics, so the result is deterministic.
 #include "attention_common.cuh"
 
+#include <stdio.h>
+#include <stdlib.h>
+
 namespace mlb {
 
 struct AttnBwdParams {
@@ -397,6 +400,9 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
                             cudaStream_t stream) {
   using namespace mlb;
   if (seq % AT_M != 0) return -2;
+  static const bool dbg = getenv("MLB200_ATTN_DEBUG") != nullptr;
+#define ATT_DBG(msg) do { if (dbg) { fprintf(stderr, "[attn_bwd] %s\n", msg); fflush(stderr); } } while (0)
+  ATT_DBG("enter");
   CUtensorMap tq, tk, tv, tdo;
   int r = make_tmap_heads(&tq, q, AT_D, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
   if (r) return 1000 + r;
@@ -406,6 +412,7 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
   if (r) return 3000 + r;
   r = make_tmap_heads(&tdo, dout, AT_D, heads, seq, batch, do_str[0], do_str[1], do_str[2], AT_M);
   if (r) return 4000 + r;
+  ATT_DBG("tensor maps built");
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.hm.q_group_stride = head_map[0]; p.hm.q_off = head_map[1]; p.hm.k_group_stride = head_map[2];
@@ -420,6 +427,7 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
   RowAddr rdo{const_cast<void*>(dout), do_str[0], do_str[1], do_str[2]};
   const long long rows = (long long)seq * batch * heads;
   attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ro, rdo, delta, seq, batch, heads);
+  ATT_DBG("delta launched");
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
@@ -430,7 +438,9 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
   }
   dim3 g1(seq / AT_N, heads / q_per_kv, batch);
   attn_bwd_dkdv_kernel<<<g1, AT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  ATT_DBG("dkdv launched");
   dim3 g2(seq / AT_M, heads, batch);
   attn_bwd_dq_kernel<<<g2, AT_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  ATT_DBG("dq launched");
   return (int)cudaGetLastError();
 }

@@ -79,3 +79,102 @@ def test_merge_datasets(tmp_path):
     ds = indexed_dataset.make_dataset(str(tmp_path / "merged"), "mmap")
     assert [x.tolist() for x in ds] == expect
     assert len(ds.doc_idx) == 13
+
+
+class _FakeBertTok:
+    """ids 0..4 special, 5..: words; odd ids in [21, 90) are '##' continuation pieces."""
+    cls, sep, mask, pad = 1, 2, 3, 0
+    bos_token_id, eos_token_id = 4, 2
+    additional_special_tokens_ids = list(range(90, 100))
+
+    @property
+    def inv_vocab(self):
+        v = {0: "[PAD]", 1: "[CLS]", 2: "[SEP]", 3: "[MASK]", 4: "[BOS]"}
+        for i in range(5, 100):
+            v[i] = ("##p%d" % i) if (21 <= i < 90 and i % 2 == 1) else "w%d" % i
+        return v
+
+
+def _sentence_corpus(tmp_path, name="sent", n_docs=30):
+    from megatron_llm_b200.data import indexed_dataset
+    rng = np.random.RandomState(0)
+    b = indexed_dataset.make_builder(str(tmp_path / f"{name}.bin"), "mmap", vocab_size=100)
+    for d in range(n_docs):
+        for s in range(rng.randint(2, 6)):
+            b.add_item(torch.IntTensor(rng.randint(5, 90, size=rng.randint(4, 12)).tolist()))
+        b.end_document()
+    b.finalize(str(tmp_path / f"{name}.idx"))
+    return str(tmp_path / name)
+
+
+def test_bert_and_t5_datasets(tmp_path):
+    from megatron_llm_b200.data import indexed_dataset
+    from megatron_llm_b200.data.bert_dataset import BertDataset
+    from megatron_llm_b200.data.t5_dataset import T5Dataset
+    prefix = _sentence_corpus(tmp_path)
+    ds = indexed_dataset.make_dataset(prefix, "mmap", True)
+    tok = _FakeBertTok()
+    bert = BertDataset("train", ds, prefix, None, 50, 0.15, 48, 0.1, 1234, True, tokenizer=tok)
+    assert len(bert) >= 50
+    n_masked = 0
+    for i in range(20):
+        s = bert[i]
+        assert s["text"].shape == (48,) and s["text"][0] == tok.cls
+        real = int(s["padding_mask"].sum())
+        assert (s["text"][real:] == tok.pad).all() and s["text"][real - 1] == tok.sep
+        pos = np.nonzero(s["loss_mask"])[0]
+        assert len(pos) >= 1 and (s["labels"][pos] >= 5).all() and (s["labels"][s["loss_mask"] == 0] == -1).all()
+        assert set(np.unique(s["types"][:real])) <= {0, 1}
+        n_masked += len(pos)
+        assert (bert[i]["text"] == s["text"]).all()          # deterministic per index
+    assert n_masked > 20
+    t5 = T5Dataset("train", ds, prefix, None, 50, 0.15, 48, 32, 0.1, 1234, tokenizer=tok)
+    for i in range(20):
+        s = t5[i]
+        assert s["text_enc"].shape == (48,) and s["text_dec"].shape == (32,) and s["labels"].shape == (32,)
+        assert s["text_dec"][0] == tok.bos_token_id
+        n_dec = int(s["loss_mask"].sum())
+        assert s["labels"][n_dec - 1] == tok.eos_token_id
+        sent_enc = [t for t in s["text_enc"] if t >= 90]
+        sent_dec = [t for t in s["text_dec"] if t >= 90]
+        assert sent_enc == sent_dec and len(sent_enc) >= 1
+        assert s["enc_mask"].shape == (48, 48) and s["dec_mask"].shape == (32, 32)
+        assert s["enc_dec_mask"].shape == (32, 48)
+        assert np.triu(s["dec_mask"], 1).sum() == 0
+        assert (s["text_dec"][1:n_dec] == s["labels"][:n_dec - 1]).all()
+
+
+def test_ict_dataset(tmp_path):
+    from megatron_llm_b200.data import indexed_dataset
+    from megatron_llm_b200.data.ict_dataset import ICTDataset
+    prefix = _sentence_corpus(tmp_path, "blocks", 20)
+    b = indexed_dataset.make_builder(str(tmp_path / "titles.bin"), "mmap", vocab_size=100)
+    for d in range(20):
+        b.add_item(torch.IntTensor([5 + d % 10, 6]))
+        b.end_document()
+    b.finalize(str(tmp_path / "titles.idx"))
+    blocks = indexed_dataset.make_dataset(prefix, "mmap", True)
+    titles = indexed_dataset.make_dataset(str(tmp_path / "titles"), "mmap", True)
+    tok = _FakeBertTok()
+    ict = ICTDataset("full", blocks, titles, prefix, 1, None, 64, 0.1, 1, tokenizer=tok)
+    assert len(ict) > 0
+    s = ict[0]
+    assert s["query_tokens"].shape == (64,) and s["context_tokens"].shape == (64,)
+    assert s["query_tokens"][0] == tok.cls and s["context_tokens"][0] == tok.cls
+    assert s["block_data"].shape == (4,)
+    toks, pad = ict.get_block(*s["block_data"][:3])
+    assert toks.shape == (64,) and pad.sum() > 3
+
+
+def test_mips_index():
+    from megatron_llm_b200.data.realm_index import FaissMIPSIndex, OpenRetreivalDataStore
+    store = OpenRetreivalDataStore("/tmp/_unused_embeds.pkl", load_from_path=False, rank=0)
+    rng = np.random.RandomState(0)
+    emb = rng.randn(200, 16).astype(np.float32)
+    store.add_block_data(np.arange(1000, 1200), emb)
+    index = FaissMIPSIndex(16, store, chunk=64)
+    q = rng.randn(5, 16).astype(np.float32)
+    scores, ids = index.search_mips_index(q, 4, reconstruct=False)
+    ref = np.argsort(-(q @ np.float32(np.float16(emb)).T), axis=1)[:, :4] + 1000
+    assert (ids == ref).all()
+    assert index.search_mips_index(q, 4, reconstruct=True).shape == (5, 4, 16)
