@@ -3,6 +3,9 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdio>
+#include <stdexcept>
+
 #include <cuda_runtime.h>
 
 extern "C" {
@@ -19,7 +22,15 @@ int mlb_attn_bwd(const void* q, const void* k, const void* v, const void* o, con
 }
 
 static cudaStream_t cur() { return at::cuda::getCurrentCUDAStream().stream(); }
-#define CHK(call) do { int _e = (call); TORCH_CHECK(_e == 0, #call " failed with code ", _e); } while (0)
+#define CHK(call)                                                                                     \
+  do {                                                                                                \
+    int _e = (call);                                                                                  \
+    if (_e != 0) {                                                                                    \
+      char _buf[256];                                                                                 \
+      snprintf(_buf, sizeof(_buf), "%s failed with code %d", #call, _e);                              \
+      throw std::runtime_error(_buf);                                                                 \
+    }                                                                                                 \
+  } while (0)
 
 // tensors are [b, s, n, hn] views (any strides, hn contiguous); strides passed as (head, seq, batch)
 static void strides_of(const torch::Tensor& t, long long* s) {
@@ -67,7 +78,47 @@ static std::vector<torch::Tensor> attn_bwd(const torch::Tensor& dout, const torc
   return {dq, dk, dv};
 }
 
+// Packed path: ``mixed`` is the QKV projection output [s, b, nkv * (g + 2) * 128] (per KV group: g query heads, k, v),
+// already rotated in place.  The kernels address Q/K/V inside it through the head map: no splits, no transposes, and
+// the backward writes dQ/dK/dV straight into one ``dmixed`` buffer of the same layout.
+static std::vector<torch::Tensor> attn_fwd_packed(const torch::Tensor& mixed, int64_t nkv, int64_t g, int64_t window,
+                                                  double scale) {
+  TORCH_CHECK(mixed.dim() == 3 && mixed.stride(2) == 1 && mixed.size(2) == nkv * (g + 2) * 128,
+              "attn_fwd_packed: expected [s, b, nkv * (g + 2) * 128]");
+  c10::cuda::CUDAGuard guard(mixed.device());
+  const int s = mixed.size(0), b = mixed.size(1), n = nkv * g, mh = nkv * (g + 2);
+  long long ms[3] = {128, (long long)mixed.stride(0), (long long)mixed.stride(1)};
+  auto out = torch::empty({s, b, (int64_t)n * 128}, mixed.options());
+  auto lse = torch::empty({b, n, s}, mixed.options().dtype(torch::kFloat32));
+  int head_map[6] = {(int)g + 2, 0, (int)g + 2, (int)g, (int)g + 2, (int)g + 1};
+  CHK(mlb_attn_fwd(mixed.data_ptr(), mixed.data_ptr(), mixed.data_ptr(), ms, ms, ms, mh, mh, mh, head_map, (int)g, s,
+                   b, n, (int)window, (float)scale, out.data_ptr(), (long long)b * n * 128, (long long)n * 128,
+                   lse.data_ptr<float>(), cur()));
+  return {out, lse};
+}
+
+static torch::Tensor attn_bwd_packed(const torch::Tensor& dout, const torch::Tensor& mixed, const torch::Tensor& out,
+                                     const torch::Tensor& lse, int64_t nkv, int64_t g, int64_t window, double scale) {
+  TORCH_CHECK(dout.dim() == 3 && dout.stride(2) == 1 && out.stride(2) == 1, "attn_bwd_packed: contiguous hn expected");
+  c10::cuda::CUDAGuard guard(mixed.device());
+  const int s = mixed.size(0), b = mixed.size(1), n = nkv * g, mh = nkv * (g + 2);
+  long long ms[3] = {128, (long long)mixed.stride(0), (long long)mixed.stride(1)};
+  long long os[3] = {128, (long long)out.stride(0), (long long)out.stride(1)};
+  long long ds[3] = {128, (long long)dout.stride(0), (long long)dout.stride(1)};
+  auto dmixed = torch::empty({s, b, mixed.size(2)}, mixed.options());
+  long long dms[3] = {128, (long long)dmixed.stride(0), (long long)dmixed.stride(1)};
+  auto delta = torch::empty({b, n, s}, mixed.options().dtype(torch::kFloat32));
+  int head_map[6] = {(int)g + 2, 0, (int)g + 2, (int)g, (int)g + 2, (int)g + 1};
+  CHK(mlb_attn_bwd(mixed.data_ptr(), mixed.data_ptr(), mixed.data_ptr(), out.data_ptr(), dout.data_ptr(), ms, ms, ms,
+                   os, ds, mh, mh, mh, head_map, (int)g, s, b, n, (int)window, (float)scale, lse.data_ptr<float>(),
+                   delta.data_ptr<float>(), dmixed.data_ptr(), dmixed.data_ptr(), dmixed.data_ptr(), dms, dms, dms,
+                   cur()));
+  return dmixed;
+}
+
 void register_attention(pybind11::module_& m) {
+  m.def("attn_fwd_packed", &attn_fwd_packed);
+  m.def("attn_bwd_packed", &attn_bwd_packed);
   m.def("attn_fwd", &attn_fwd);
   m.def("attn_bwd", &attn_bwd);
 }

@@ -200,10 +200,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
     mbar_wait(acc_done, 0);
     tc_fence_after();
     if (kv < p.seq) {
-      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh) - p.hm.v_off + 0);   // output tensors have their own layout:
-      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh) - p.hm.k_off + 0);   // head coordinate = group index
-      dvrow = p.dv.row(kv, b, kvh);
-      dkrow = p.dk.row(kv, b, kvh);
+      // gradients use the same head -> coordinate map as the inputs (separate tensors or one packed QKV buffer)
+      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh));
+      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh));
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t a[32], bb[32];
@@ -365,7 +364,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(acc_done, 0);
     tc_fence_after();
     if (row < p.seq) {
-      __nv_bfloat16* dqrow = p.dq.row(row, b, h);
+      __nv_bfloat16* dqrow = p.dq.row(row, b, p.hm.q(h));
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t a[32];

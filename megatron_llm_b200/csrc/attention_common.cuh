@@ -33,6 +33,7 @@ static inline int make_tmap_heads(CUtensorMap* tm, const void* base, int hn, int
                                   long long head_stride, long long seq_stride, long long batch_stride, int box_rows) {
   auto fn = at_encode_fn();
   if (!fn) return -1;
+  mlb_bind_context();
   cuuint64_t dims[4] = {(cuuint64_t)hn, (cuuint64_t)heads, (cuuint64_t)seq, (cuuint64_t)batch};
   cuuint64_t strides[3] = {(cuuint64_t)head_stride * 2, (cuuint64_t)seq_stride * 2, (cuuint64_t)batch_stride * 2};
   cuuint32_t box[4] = {64, 1, (cuuint32_t)box_rows, 1};

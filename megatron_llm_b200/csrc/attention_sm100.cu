@@ -16,6 +16,8 @@
 //   * dQ:    one CTA per query tile, recomputes S and dP and accumulates dQ += dS K.
 #include "attention_common.cuh"
 
+#include <stdlib.h>
+
 namespace mlb {
 
 // TMEM column map (forward)
@@ -259,6 +261,258 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
 constexpr int AT_FWD_SMEM = 5 * AT_TILE_BYTES + 256 + 1024;
 
+// =================================================================================================
+// forward, two query tiles per CTA (256 query rows)
+// =================================================================================================
+// The single-tile kernel above is bound by its one softmax warpgroup (one warp per SM sub-partition: no latency
+// hiding, and the tensor core idles while it works).  Here a CTA owns two adjacent query tiles `a` and `b`, each with
+// its own softmax warpgroup, and the MMA warp ping-pongs between them:
+//        S_a(t+1) / PV_b(t) run while softmax_b(t) / softmax_a(t+1) are busy.
+// TMEM: [0,128) S_a, [128,256) S_b, [256,384) O_a, [384,512) O_b; P_x (bf16) overwrites the first 64 columns of S_x in
+// place (a thread has consumed columns [0, 32c+32) of its row before it writes P columns [16c, 16c+16)).
+constexpr int AT2_THREADS = 384;
+constexpr uint32_t T2_S0 = 0, T2_S1 = 128, T2_O0 = 256, T2_O1 = 384;
+constexpr int AT_FWD2_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;
+
+__global__ void __launch_bounds__(AT2_THREADS, 1)
+attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                          // 2 query tiles
+  uint8_t* sK = smem + 2 * AT_TILE_BYTES;      // 2 stages
+  uint8_t* sV = smem + 4 * AT_TILE_BYTES;      // 2 stages
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 6 * AT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;    // [2]
+  uint64_t* k_empty = bars + 3;   // [2]
+  uint64_t* v_full = bars + 5;    // [2]
+  uint64_t* v_empty = bars + 7;   // [2]
+  uint64_t* s_full = bars + 9;    // [2] per query tile
+  uint64_t* p_full = bars + 11;   // [2] per query tile
+  uint64_t* o_done = bars + 13;   // [2] per query tile
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pair = (int)gridDim.x - 1 - (int)blockIdx.x;   // heavy (late) tiles first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int q0 = pair * 2 * AT_M;
+  const int kvh = h / p.q_per_kv;
+  const int q_coord = kvh * p.q_group_stride + (h % p.q_per_kv) + p.q_off;
+  const int k_coord = kvh * p.k_group_stride + p.k_off;
+  const int v_coord = kvh * p.v_group_stride + p.v_off;
+  // kv tiles [j_lo, j_hi]: tile b ends on its diagonal (2*pair+1), tile a one tile earlier
+  const int j_hi = 2 * pair + 1;
+  int j_lo = 0;
+  if (p.window > 0) j_lo = max(0, (q0 - p.window) / AT_N);
+  const int n_b = j_hi - j_lo + 1;
+  const int n_a = n_b - 1;          // >= 1
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ); tma_prefetch_desc(&tmK); tma_prefetch_desc(&tmV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&o_done[i], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc<1>(tmem_ptr_smem, 512);
+    tmem_relinquish<1>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr_smem;
+  constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, true);
+  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, AT_D, false, true, true);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
+      load_tile(sQ, &tmQ, q_full, q_coord, q0, b);
+      load_tile(sQ + AT_TILE_BYTES, &tmQ, q_full, q_coord, q0 + AT_M, b);
+      for (int t = 0; t < n_b; ++t) {
+        const int st = t & 1;
+        const uint32_t ph = (t >> 1) & 1;
+        const int kv0 = (j_lo + t) * AT_N;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
+        load_tile(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], k_coord, kv0, b);
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
+        load_tile(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], v_coord, kv0, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      auto issue_S = [&](int x, int t) {
+        const int st = t & 1;
+        mbar_wait(&k_full[st], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + x * AT_TILE_BYTES);
+        const uint32_t aK = smem_u32(sK + st * AT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < AT_D / 16; ++k)
+          umma_f16_ss<1>(tmem + (x ? T2_S1 : T2_S0), desc_kmajor(aQ, k), desc_kmajor(aK, k), IDESC_S, k != 0);
+        umma_commit<1>(&s_full[x]);
+      };
+      auto issue_PV = [&](int x, int t) {
+        const int st = t & 1;
+        mbar_wait(&p_full[x], t & 1);
+        mbar_wait(&v_full[st], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t aV = smem_u32(sV + st * AT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < AT_N / 16; ++k)
+          umma_f16_ts(tmem + (x ? T2_O1 : T2_O0), tmem + (x ? T2_S1 : T2_S0) + k * 8, desc_mnmajor(aV, k), IDESC_PV,
+                      (t | k) != 0 ? 1u : 0u);
+        umma_commit<1>(&o_done[x]);
+      };
+      mbar_wait(q_full, 0);
+      issue_S(0, 0);
+      issue_S(1, 0);
+      umma_commit<1>(&k_empty[0]);
+      for (int t = 0; t < n_b; ++t) {
+        if (t < n_a) {
+          issue_PV(0, t);
+          if (t + 1 < n_a) issue_S(0, t + 1);
+        }
+        issue_PV(1, t);
+        umma_commit<1>(&v_empty[t & 1]);
+        if (t + 1 < n_b) {
+          issue_S(1, t + 1);
+          umma_commit<1>(&k_empty[(t + 1) & 1]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------ softmax / correction / epilogue: one thread per query row ------------------
+    const int x = (warp - 4) >> 2;          // query tile of this warpgroup
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;
+    const int row = q0 + x * AT_M + r;
+    const int n_x = x ? n_b : n_a;
+    const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t s_addr = tmem + lane_addr + (x ? T2_S1 : T2_S0);
+    const uint32_t o_addr = tmem + lane_addr + (x ? T2_O1 : T2_O0);
+    const float sc = p.scale_log2;
+    float m_used = -INFINITY, l = 0.f;
+    for (int t = 0; t < n_x; ++t) {
+      const int kv0 = (j_lo + t) * AT_N;
+      mbar_wait(&s_full[x], t & 1);
+      tc_fence_after();
+      const bool need_mask = (kv0 + AT_N - 1 > row) || (p.window > 0 && kv0 < row - p.window);
+      // pass 1: row max (two chunks in flight)
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; c += 2) {
+        uint32_t v0[32], v1[32];
+        tmem_ld_32x32(s_addr + c * 32, v0);
+        tmem_ld_32x32(s_addr + c * 32 + 32, v1);
+        tmem_ld_wait();
+        if (need_mask) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int col0 = kv0 + c * 32 + i, col1 = col0 + 32;
+            if (col0 > row || (p.window > 0 && col0 < row - p.window)) v0[i] = 0xff800000u;
+            if (col1 > row || (p.window > 0 && col1 < row - p.window)) v1[i] = 0xff800000u;
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          mx0 = fmaxf(mx0, __uint_as_float(v0[i]));
+          mx1 = fmaxf(mx1, __uint_as_float(v1[i]));
+        }
+      }
+      const float m_new = fmaxf(m_used, fmaxf(mx0, mx1) * sc);
+      const bool grow = (m_new > m_used + 8.0f) || (m_used == -INFINITY && m_new != -INFINITY);
+      if (__any_sync(0xffffffffu, grow && t > 0)) {
+        mbar_wait(&o_done[x], (t - 1) & 1);    // PV_x(t-1) must have landed in O_x
+        tc_fence_after();
+        const float alpha = grow ? ((m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new)) : 1.f;
+        if (grow) { m_used = m_new; l *= alpha; }
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32(o_addr + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+          tmem_st_32x32(o_addr + c * 32, v);
+        }
+        tmem_st_wait();
+      } else if (grow) {
+        m_used = m_new;   // t == 0: nothing accumulated yet
+      }
+      // pass 2: p = exp2(s * c - m_used) packed to bf16 over the consumed part of S
+      const float moff = (m_used == -INFINITY) ? 0.f : m_used;
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(s_addr + c * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
+          if (need_mask) {
+            const int col = kv0 + c * 32 + 2 * i;
+            if (col > row || (p.window > 0 && col < row - p.window)) s0 = -INFINITY;
+            if (col + 1 > row || (p.window > 0 && col + 1 < row - p.window)) s1 = -INFINITY;
+          }
+          const float p0 = fast_exp2(fmaf(s0, sc, -moff)), p1 = fast_exp2(fmaf(s1, sc, -moff));
+          l0 += p0; l1 += p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st_32x16(s_addr + c * 16, pk);
+      }
+      l += l0 + l1;
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[x]);
+    }
+    // ------------------------------ epilogue ------------------------------------------------------------------
+    mbar_wait(&o_done[x], (n_x - 1) & 1);
+    tc_fence_after();
+    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    if (row < p.seq) {
+      __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.out_s_stride +
+                            (long long)b * p.out_b_stride + (long long)h * AT_D;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32(o_addr + c * 32, v);
+        tmem_ld_wait();
+        uint4* dst = reinterpret_cast<uint4*>(orow + c * 32);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          uint4 o;
+          o.x = pack_bf16x2(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+          o.y = pack_bf16x2(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+          o.z = pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+          o.w = pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+          dst[i] = o;
+        }
+      }
+      if (p.lse) p.lse[((long long)b * p.heads + h) * p.seq + row] = m_used * 0.6931471805599453f + logf(l);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem, 512);
+  }
+}
+
 }  // namespace mlb
 
 // q/k/v described by (base pointer, head stride, seq stride, batch stride) in elements + number of heads in the map;
@@ -288,9 +542,17 @@ extern "C" int mlb_attn_fwd(const void* q, const void* k, const void* v, const l
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
     if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD2_SMEM);
+    if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid(seq / AT_M, heads, batch);
-  attn_fwd_kernel<<<grid, AT_THREADS, AT_FWD_SMEM, stream>>>(tq, tk, tv, p);
+  static const int force_single = getenv("MLB200_ATTN_FWD1") != nullptr;
+  if (seq % (2 * AT_M) == 0 && !force_single) {
+    dim3 grid(seq / (2 * AT_M), heads, batch);
+    attn_fwd2_kernel<<<grid, AT2_THREADS, AT_FWD2_SMEM, stream>>>(tq, tk, tv, p);
+  } else {
+    dim3 grid(seq / AT_M, heads, batch);
+    attn_fwd_kernel<<<grid, AT_THREADS, AT_FWD_SMEM, stream>>>(tq, tk, tv, p);
+  }
   return (int)cudaGetLastError();
 }

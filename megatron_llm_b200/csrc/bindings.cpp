@@ -3,6 +3,9 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdio>
+#include <stdexcept>
+
 #include <cuda_runtime.h>
 
 namespace mlb { struct GemmComm; }
@@ -65,7 +68,15 @@ static int dt(const torch::Tensor& t) {
 }
 static cudaStream_t cur() { return at::cuda::getCurrentCUDAStream().stream(); }
 static const void* optp(const c10::optional<torch::Tensor>& t) { return t.has_value() ? t->data_ptr() : nullptr; }
-#define CHK(call) do { int _e = (call); TORCH_CHECK(_e == 0, #call " failed with code ", _e); } while (0)
+#define CHK(call)                                                                                     \
+  do {                                                                                                \
+    int _e = (call);                                                                                  \
+    if (_e != 0) {                                                                                    \
+      char _buf[256];                                                                                 \
+      snprintf(_buf, sizeof(_buf), "%s failed with code %d", #call, _e);                              \
+      throw std::runtime_error(_buf);                                                                 \
+    }                                                                                                 \
+  } while (0)
 
 static int g_num_sms = 0;
 static int num_sms() {

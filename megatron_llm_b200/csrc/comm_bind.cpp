@@ -4,6 +4,9 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdio>
+#include <stdexcept>
+
 #include <cuda_runtime.h>
 #include <string.h>
 
@@ -18,7 +21,15 @@ int mlb_dp_reduce(int reduce_scatter, float* local, const long long* peer_ptrs, 
 }
 
 static cudaStream_t cur() { return at::cuda::getCurrentCUDAStream().stream(); }
-#define CHK(call) do { int _e = (call); TORCH_CHECK(_e == 0, #call " failed with code ", _e); } while (0)
+#define CHK(call)                                                                                     \
+  do {                                                                                                \
+    int _e = (call);                                                                                  \
+    if (_e != 0) {                                                                                    \
+      char _buf[256];                                                                                 \
+      snprintf(_buf, sizeof(_buf), "%s failed with code %d", #call, _e);                              \
+      throw std::runtime_error(_buf);                                                                 \
+    }                                                                                                 \
+  } while (0)
 
 static int sm_count() {
   static int n = 0;

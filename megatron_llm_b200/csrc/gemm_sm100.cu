@@ -25,6 +25,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                       uint32_t box_inner, uint32_t box_outer) {
   auto fn = get_encode_fn();
+  mlb_bind_context();
   if (!fn) return -1;
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {ld * 2};

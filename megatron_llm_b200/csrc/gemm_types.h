@@ -59,3 +59,13 @@ struct GemmParams {
 };
 
 }  // namespace mlb
+
+// cuTensorMapEncodeTiled (driver API) needs a CUDA context current on the calling thread.  PyTorch's autograd worker
+// threads only get one once a runtime call that needs it runs there (a CUDAGuard for device 0 is a no-op), so every
+// tensor-map builder binds the primary context of the thread's current device first (one runtime call per thread).
+#if defined(__CUDACC__) || defined(__CUDA_RUNTIME_H__) || defined(CUDART_VERSION)
+static inline void mlb_bind_context() {
+  static thread_local bool bound = false;
+  if (!bound) { cudaFree(nullptr); bound = true; }
+}
+#endif

@@ -27,6 +27,7 @@ import torch
 import torch.nn.functional as F
 
 from .. import ops
+from ..ops import attention_sm100
 from ..parallel import layers as tp_layers
 from ..parallel import state as ps
 from ..parallel.random import checkpoint as tp_checkpoint, get_cuda_rng_tracker
@@ -251,6 +252,18 @@ class ParallelAttention(MegatronModule):
                 pid = position_ids if inference_params is None else None
                 mixed = ops.rope_qkv_(mixed, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn,
                                       _shared_rope_table(self._rope_cfg, mixed.device), pid, pos_offset)
+            # fast path: the tcgen05 attention kernels read Q/K/V in place from the packed projection output and the
+            # backward writes one packed gradient (no splits / transposes / view-gradient accumulation)
+            p_drop = self.attention_dropout_p if self.training else 0.0
+            if (inference_params is None and self.use_flash_attn
+                    and attention_sm100.packed_supported(mixed, self.num_kv_heads_per_partition, self.q_per_kv, hn,
+                                                         p_drop)):
+                window = None
+                if self.sliding_window_size is not None and sq > self.sliding_window_size:
+                    window = self.sliding_window_size
+                context_layer = attention_sm100.packed_attention(mixed, self.num_kv_heads_per_partition,
+                                                                 self.q_per_kv, window, None)
+                return self.dense(context_layer)
             qkv = mixed.view(sq, b, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn)
             if self.q_per_kv == 1:
                 query_layer = qkv[:, :, :, 0]                                     # view [sq,b,np,hn]

@@ -38,7 +38,7 @@ class _AttnFn(torch.autograd.Function):
         mod = _ext.load()
         dq, dk, dv = mod.attn_bwd(dout if dout.stride(-1) == 1 else dout.contiguous(), q, k, v, out, lse, ctx.causal,
                                   -1 if ctx.window is None else int(ctx.window), float(ctx.scale))
-        _ext.count(2)
+        _ext.count(3)
         return dq, dk, dv, None, None, None
 
 
@@ -46,3 +46,45 @@ def attention(q, k, v, causal, window, scale):
     import math
     scale = scale if scale is not None else 1.0 / math.sqrt(q.size(-1))
     return _AttnFn.apply(q, k, v, causal, window, scale)
+
+
+# ------------------------------------------------------------------------------------------------ packed QKV path
+def packed_supported(mixed, nkv, g, hn, dropout_p) -> bool:
+    """``mixed`` = QKV projection output [s, b, nkv * (g + 2) * hn] (per KV group: g query heads, then k, then v)."""
+    if os.environ.get("MLB200_ATTN", "1") == "0" or os.environ.get("MLB200_ATTN_PACKED", "1") == "0":
+        return False
+    if not (mixed.is_cuda and mixed.dtype == torch.bfloat16 and hn == 128 and dropout_p == 0.0
+            and mixed.dim() == 3 and mixed.stride(2) == 1 and mixed.size(0) % 128 == 0):
+        return False
+    try:
+        return hasattr(_ext.load(), "attn_fwd_packed")
+    except Exception:
+        return False
+
+
+class _PackedAttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mixed, nkv, g, window, scale):
+        mod = _ext.load()
+        out, lse = mod.attn_fwd_packed(mixed, nkv, g, -1 if window is None else int(window), float(scale))
+        _ext.count()
+        ctx.save_for_backward(mixed, out, lse)
+        ctx.cfg = (nkv, g, window, scale)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        mixed, out, lse = ctx.saved_tensors
+        nkv, g, window, scale = ctx.cfg
+        mod = _ext.load()
+        d = dout if dout.stride(-1) == 1 else dout.contiguous()
+        dmixed = mod.attn_bwd_packed(d, mixed, out, lse, nkv, g, -1 if window is None else int(window), float(scale))
+        _ext.count(3)
+        return dmixed, None, None, None, None
+
+
+def packed_attention(mixed, nkv, g, window=None, scale=None):
+    """Causal attention straight from the packed (already rotated) QKV buffer -> context [s, b, nkv * g * 128]."""
+    import math
+    scale = scale if scale is not None else 1.0 / math.sqrt(128)
+    return _PackedAttnFn.apply(mixed, nkv, g, window, scale)

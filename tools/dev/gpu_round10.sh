@@ -1,0 +1,9 @@
+#!/bin/bash
+mkdir -p gpurun_out; out=gpurun_out/attn_checks4.jsonl; : > $out
+for c in "1 128 1 1 none c" "1 256 2 2 none c" "1 1024 2 2 256 c" "2 1024 4 1 none c" "1 2048 8 2 512 c" "1 4096 32 32 none t"; do
+  timeout 120 python tools/dev/attn_check.py $c >> $out 2> gpurun_out/attn4_err_$(echo $c | tr ' ' '_').txt || echo "{\"case\": \"$c\", \"failed\": $?}" >> $out
+done
+cat $out
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_r10.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_gpu_r10.log
+timeout 600 python bench.py --steps 3 --warmup 3 --no_e2e > gpurun_out/bench_7b_r10_ownattn.json 2> gpurun_out/bench_7b_r10_ownattn.err; tail -1 gpurun_out/bench_7b_r10_ownattn.json | cut -c1-600
+MLB200_ATTN=0 timeout 600 python bench.py --steps 3 --warmup 3 --no_e2e > gpurun_out/bench_7b_r10_fa2.json 2> gpurun_out/bench_7b_r10_fa2.err; tail -1 gpurun_out/bench_7b_r10_fa2.json | cut -c1-600
