@@ -228,6 +228,8 @@ _GROUPS = {
         ("--biencoder_shared_query_context_model", _S()),
         ("--ict_load", dict(type=str, default=None)),
         ("--bert_load", dict(type=str, default=None)),
+        # (missing from the reference's parser although pretrain_bert.py reads it; restored from upstream Megatron-LM)
+        ("--bert_no_binary_head", dict(action="store_false", dest="bert_binary_head")),
         ("--titles_data_path", dict(type=str, default=None)),
         ("--query_in_block_prob", dict(type=float, default=0.1)),
         ("--use_one_sent_docs", _S()),
