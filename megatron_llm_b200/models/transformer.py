@@ -483,7 +483,9 @@ class ParallelTransformer(MegatronModule):
                  drop_path_rate=0.0, args=None, model_type=None):
         super().__init__()
         world_size = ps.get_tensor_model_parallel_world_size()
-        assert args is not None and model_type is not None
+        assert args is not None
+        if model_type is None:       # the reference reads args.model_type (set by get_model); default = decoder-only
+            model_type = getattr(args, "model_type", None) or ModelType.encoder_or_decoder
         self.layer_type = layer_type
         self.model_type = model_type
         self.bf16 = args.bf16
