@@ -47,11 +47,19 @@ __global__ void attn_delta_kernel(RowAddr o, RowAddr dout, float* __restrict__ d
   if (lane == 0) delta[((long long)b * heads + h) * seq + s] = v;
 }
 
-// TMEM column map (dK/dV kernel): the bf16 P^T / dS^T tiles alias the first 64 columns of the fp32 tiles
+// Both backward kernels split every 128-wide score tile into two 64-column halves.  Each half has its own
+// elementwise warpgroup (the math is purely elementwise: P = exp2(S c - lse), dS = P o (dP - D) c) and its own
+// barriers, and the MMA warp ping-pongs between them:
+//        [S,dP]_hi(t) and acc_lo(t) run while the warpgroups work on lo(t) / hi(t); [S,dP]_lo(t+1) follows acc_lo(t).
+// The bf16 P / dS tiles overwrite the first half of the fp32 columns of their own 64-column half in place.
+constexpr int BW_THREADS = 384;
+constexpr int AT_ROWS64 = 64 * 128;   // byte offset of tile row 64 inside a 64-column swizzle box
+
+// TMEM column map (dK/dV kernel)
 constexpr uint32_t KV_ST = 0, KV_DPT = 128, KV_DV = 256, KV_DK = 384;
 constexpr int BWD_SMEM = 6 * AT_TILE_BYTES + 2 * 2 * 128 * 4 + 256 + 1024;   // K, V, 2 x (Q, dO), 2 x (lse, D)
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                      const AttnBwdParams p) {
@@ -67,10 +75,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* kv_full = bars;        // K and V landed
   uint64_t* in_full = bars + 1;    // [2] Q + dO of stage s landed
   uint64_t* in_empty = bars + 3;   // [2] dV/dK MMAs of the tile finished reading stage s
-  uint64_t* sdp_full = bars + 5;   // S^T and dP^T computed
-  uint64_t* pds_full = bars + 6;   // P^T and dS^T written (4 warps)
-  uint64_t* acc_done = bars + 7;   // all MMAs retired (epilogue)
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_full = bars + 5;   // [2] S^T and dP^T of half x computed
+  uint64_t* pds_full = bars + 7;   // [2] P^T and dS^T of half x written (4 warps)
+  uint64_t* acc_done = bars + 9;   // all MMAs retired (epilogue)
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -87,9 +95,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   }
   if (warp == 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
-    mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1);
+      mbar_init(&sdp_full[s], 1); mbar_init(&pds_full[s], 4);
+    }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -98,7 +107,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
-  constexpr uint32_t ID_KK = make_idesc_f16(AT_N, AT_M, false, false, true);   // A K-major smem, B K-major smem
+  constexpr uint32_t ID_KK = make_idesc_f16(AT_N, 64, false, false, true);     // [128 kv] x [64 q], both K-major smem
   constexpr uint32_t ID_TS = make_idesc_f16(AT_N, AT_D, false, true, true);    // A from TMEM, B MN-major smem
 
   if (warp == 0) {
@@ -119,56 +128,78 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t aK = smem_u32(sK), aV = smem_u32(sV);
-      mbar_wait(kv_full, 0);
-      for (int it = 0; it < n_iter; ++it) {
+      // S^T_x = K Q_x^T ; dP^T_x = V dO_x^T          (x = query-column half)
+      auto issue_sdp = [&](int x, int it) {
         const int st = it & 1;
-        const uint32_t aQ = smem_u32(sQ + st * AT_TILE_BYTES), aDO = smem_u32(sDO + st * AT_TILE_BYTES);
+        const uint32_t aQ = smem_u32(sQ + st * AT_TILE_BYTES) + x * AT_ROWS64;
+        const uint32_t aDO = smem_u32(sDO + st * AT_TILE_BYTES) + x * AT_ROWS64;
         mbar_wait(&in_full[st], (it >> 1) & 1);
         tc_fence_after();
-        // S^T = K Q^T ; dP^T = V dO^T      (the previous tile's dV/dK MMAs precede these in the tensor pipe, so the
-        //                                   aliased P^T/dS^T columns are free by the time they are overwritten)
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_f16_ss<1>(tmem + KV_ST, desc_kmajor(aK, k), desc_kmajor(aQ, k), ID_KK, k != 0);
+          umma_f16_ss<1>(tmem + KV_ST + x * 64, desc_kmajor(aK, k), desc_kmajor(aQ, k), ID_KK, k != 0);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_f16_ss<1>(tmem + KV_DPT, desc_kmajor(aV, k), desc_kmajor(aDO, k), ID_KK, k != 0);
-        umma_commit<1>(sdp_full);
-        mbar_wait(pds_full, it & 1);
+          umma_f16_ss<1>(tmem + KV_DPT + x * 64, desc_kmajor(aV, k), desc_kmajor(aDO, k), ID_KK, k != 0);
+        umma_commit<1>(&sdp_full[x]);
+      };
+      // dV += P^T_x dO_x ; dK += dS^T_x Q_x
+      auto issue_acc = [&](int x, int it) {
+        const int st = it & 1;
+        const uint32_t aQ = smem_u32(sQ + st * AT_TILE_BYTES), aDO = smem_u32(sDO + st * AT_TILE_BYTES);
+        mbar_wait(&pds_full[x], it & 1);
         tc_fence_after();
-        // dV += P^T dO ; dK += dS^T Q
 #pragma unroll
-        for (int k = 0; k < AT_M / 16; ++k)
-          umma_f16_ts(tmem + KV_DV, tmem + KV_ST + k * 8, desc_mnmajor(aDO, k), ID_TS, (it | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(tmem + KV_DV, tmem + KV_ST + x * 64 + k * 8, desc_mnmajor(aDO, x * 4 + k), ID_TS,
+                      (it | x | k) != 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < AT_M / 16; ++k)
-          umma_f16_ts(tmem + KV_DK, tmem + KV_DPT + k * 8, desc_mnmajor(aQ, k), ID_TS, (it | k) != 0 ? 1u : 0u);
-        umma_commit<1>(&in_empty[st]);
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(tmem + KV_DK, tmem + KV_DPT + x * 64 + k * 8, desc_mnmajor(aQ, x * 4 + k), ID_TS,
+                      (it | x | k) != 0 ? 1u : 0u);
+      };
+      mbar_wait(kv_full, 0);
+      issue_sdp(0, 0);
+      issue_sdp(1, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        issue_acc(0, it);
+        if (it + 1 < n_iter) issue_sdp(0, it + 1);
+        issue_acc(1, it);
+        umma_commit<1>(&in_empty[it & 1]);
+        if (it + 1 < n_iter) issue_sdp(1, it + 1);
       }
       umma_commit<1>(acc_done);
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    const int x = (warp - 4) >> 2;        // query-column half of this warpgroup
+    const int q = warp & 3;               // TMEM lane quarter
     const int r = q * 32 + lane;          // kv row inside the tile (TMEM lane)
     const int kv = kv0 + r;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t st_addr = tmem + lane_addr + KV_ST + x * 64, dp_addr = tmem + lane_addr + KV_DPT + x * 64;
     for (int it = 0; it < n_iter; ++it) {
       const int st = it & 1;
       const int hq = kvh * g + it / tiles_per_head;
       const int q0 = (j + it % tiles_per_head) * AT_M;
-      // per-query statistics of this tile -> smem (one value per thread), visible to the 128 softmax threads
-      const long long stat = ((long long)b * p.heads + hq) * p.seq + q0 + r;
-      sLse[st * 128 + r] = p.lse[stat] * 1.4426950408889634f;
-      sD[st * 128 + r] = p.delta[stat];
-      asm volatile("bar.sync 2, 128;" ::: "memory");
-      mbar_wait(sdp_full, it & 1);
+      // per-query statistics of this half -> smem: threads 0..63 fetch lse, 64..127 fetch D
+      {
+        const int c = r & 63;
+        const long long stat = ((long long)b * p.heads + hq) * p.seq + q0 + x * 64 + c;
+        if (r < 64) sLse[st * 128 + x * 64 + c] = p.lse[stat] * 1.4426950408889634f;
+        else sD[st * 128 + x * 64 + c] = p.delta[stat];
+      }
+      if (x == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
+      else asm volatile("bar.sync 3, 128;" ::: "memory");
+      mbar_wait(&sdp_full[x], it & 1);
       tc_fence_after();
       const bool need_mask = (q0 < kv0 + AT_N - 1) || (p.window > 0 && q0 + AT_M - 1 > kv0 + p.window);
+      const float* lse_s = sLse + st * 128 + x * 64;
+      const float* d_s = sD + st * 128 + x * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32];
-        tmem_ld_32x32(tmem + lane_addr + KV_ST + c * 32, s);
-        tmem_ld_32x32(tmem + lane_addr + KV_DPT + c * 32, dp);
+        tmem_ld_32x32(st_addr + c * 32, s);
+        tmem_ld_32x32(dp_addr + c * 32, dp);
         tmem_ld_wait();
         uint32_t pk[16], dk[16];
 #pragma unroll
@@ -176,38 +207,38 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           float pv[2], dv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int col = c * 32 + 2 * i + e;     // query index inside the tile
-            float pe = fast_exp2(__uint_as_float(s[2 * i + e]) * p.scale_log2 - sLse[st * 128 + col]);
+            const int col = c * 32 + 2 * i + e;     // query index inside the half
+            float pe = fast_exp2(fmaf(__uint_as_float(s[2 * i + e]), p.scale_log2, -lse_s[col]));
             if (need_mask) {
-              const int qrow = q0 + col;
+              const int qrow = q0 + x * 64 + col;
               if (kv > qrow || (p.window > 0 && kv < qrow - p.window)) pe = 0.f;
             }
             pv[e] = pe;
-            dv[e] = pe * (__uint_as_float(dp[2 * i + e]) - sD[st * 128 + col]) * p.scale;
+            dv[e] = pe * (__uint_as_float(dp[2 * i + e]) - d_s[col]) * p.scale;
           }
           pk[i] = pack_bf16x2(pv[0], pv[1]);
           dk[i] = pack_bf16x2(dv[0], dv[1]);
         }
-        tmem_st_32x16(tmem + lane_addr + KV_ST + c * 16, pk);     // in place: only already-consumed columns
-        tmem_st_32x16(tmem + lane_addr + KV_DPT + c * 16, dk);
+        tmem_st_32x16(st_addr + c * 16, pk);     // in place: only already-consumed columns of this half
+        tmem_st_32x16(dp_addr + c * 16, dk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
+      if (lane == 0) mbar_arrive(&pds_full[x]);
     }
-    // epilogue: dV, dK -> bf16
+    // epilogue: dV, dK -> bf16 (each warpgroup writes 64 of the 128 head-dim columns)
     mbar_wait(acc_done, 0);
     tc_fence_after();
     if (kv < p.seq) {
       // gradients use the same head -> coordinate map as the inputs (separate tensors or one packed QKV buffer)
-      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh));
-      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh));
+      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh)) + x * 64;
+      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh)) + x * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t a[32], bb[32];
-        tmem_ld_32x32(tmem + lane_addr + KV_DV + c * 32, a);
-        tmem_ld_32x32(tmem + lane_addr + KV_DK + c * 32, bb);
+        tmem_ld_32x32(tmem + lane_addr + KV_DV + x * 64 + c * 32, a);
+        tmem_ld_32x32(tmem + lane_addr + KV_DK + x * 64 + c * 32, bb);
         tmem_ld_wait();
         uint4* d0 = reinterpret_cast<uint4*>(dvrow + c * 32);
         uint4* d1 = reinterpret_cast<uint4*>(dkrow + c * 32);
@@ -237,7 +268,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 constexpr uint32_t Q_S = 0, Q_DP = 128, Q_DQ = 256;
 constexpr int BWD_DQ_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;   // Q, dO, 2 x (K, V)
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
                    const AttnBwdParams p) {
@@ -251,10 +282,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   uint64_t* q_full = bars;
   uint64_t* in_full = bars + 1;    // [2]
   uint64_t* in_empty = bars + 3;   // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* ds_full = bars + 6;
-  uint64_t* acc_done = bars + 7;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_full = bars + 5;   // [2] per kv-column half
+  uint64_t* ds_full = bars + 7;    // [2] per kv-column half
+  uint64_t* acc_done = bars + 9;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int i = (int)gridDim.x - 1 - (int)blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -269,9 +300,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) { mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1); }
-    mbar_init(sdp_full, 1);
-    mbar_init(ds_full, 4);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&in_full[s], 1); mbar_init(&in_empty[s], 1);
+      mbar_init(&sdp_full[s], 1); mbar_init(&ds_full[s], 4);
+    }
     mbar_init(acc_done, 1);
     fence_barrier_init();
   }
@@ -280,7 +312,7 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
-  constexpr uint32_t ID_KK = make_idesc_f16(AT_M, AT_N, false, false, true);
+  constexpr uint32_t ID_KK = make_idesc_f16(AT_M, 64, false, false, true);
   constexpr uint32_t ID_TS = make_idesc_f16(AT_M, AT_D, false, true, true);
 
   if (warp == 0) {
@@ -300,46 +332,61 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t aQ = smem_u32(sQ), aDO = smem_u32(sDO);
-      mbar_wait(q_full, 0);
-      for (int it = 0; it < n_iter; ++it) {
+      auto issue_sdp = [&](int x, int it) {      // S_x = Q K_x^T ; dP_x = dO V_x^T
         const int st = it & 1;
-        const uint32_t aK = smem_u32(sK + st * AT_TILE_BYTES), aV = smem_u32(sV + st * AT_TILE_BYTES);
+        const uint32_t aK = smem_u32(sK + st * AT_TILE_BYTES) + x * AT_ROWS64;
+        const uint32_t aV = smem_u32(sV + st * AT_TILE_BYTES) + x * AT_ROWS64;
         mbar_wait(&in_full[st], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_f16_ss<1>(tmem + Q_S, desc_kmajor(aQ, k), desc_kmajor(aK, k), ID_KK, k != 0);
+          umma_f16_ss<1>(tmem + Q_S + x * 64, desc_kmajor(aQ, k), desc_kmajor(aK, k), ID_KK, k != 0);
 #pragma unroll
         for (int k = 0; k < AT_D / 16; ++k)
-          umma_f16_ss<1>(tmem + Q_DP, desc_kmajor(aDO, k), desc_kmajor(aV, k), ID_KK, k != 0);
-        umma_commit<1>(sdp_full);
-        mbar_wait(ds_full, it & 1);
+          umma_f16_ss<1>(tmem + Q_DP + x * 64, desc_kmajor(aDO, k), desc_kmajor(aV, k), ID_KK, k != 0);
+        umma_commit<1>(&sdp_full[x]);
+      };
+      auto issue_acc = [&](int x, int it) {      // dQ += dS_x K_x
+        const uint32_t aK = smem_u32(sK + (it & 1) * AT_TILE_BYTES);
+        mbar_wait(&ds_full[x], it & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AT_N / 16; ++k)
-          umma_f16_ts(tmem + Q_DQ, tmem + Q_DP + k * 8, desc_mnmajor(aK, k), ID_TS, (it | k) != 0 ? 1u : 0u);
-        umma_commit<1>(&in_empty[st]);
+        for (int k = 0; k < 4; ++k)
+          umma_f16_ts(tmem + Q_DQ, tmem + Q_DP + x * 64 + k * 8, desc_mnmajor(aK, x * 4 + k), ID_TS,
+                      (it | x | k) != 0 ? 1u : 0u);
+      };
+      mbar_wait(q_full, 0);
+      issue_sdp(0, 0);
+      issue_sdp(1, 0);
+      for (int it = 0; it < n_iter; ++it) {
+        issue_acc(0, it);
+        if (it + 1 < n_iter) issue_sdp(0, it + 1);
+        issue_acc(1, it);
+        umma_commit<1>(&in_empty[it & 1]);
+        if (it + 1 < n_iter) issue_sdp(1, it + 1);
       }
       umma_commit<1>(acc_done);
     }
   } else if (warp >= 4) {
-    const int q = warp - 4;
+    const int x = (warp - 4) >> 2;        // kv-column half of this warpgroup
+    const int q = warp & 3;
     const int r = q * 32 + lane;
     const int row = q0 + r;
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
+    const uint32_t s_addr = tmem + lane_addr + Q_S + x * 64, dp_addr = tmem + lane_addr + Q_DP + x * 64;
     const long long stat = ((long long)b * p.heads + h) * p.seq + row;
     const float lse2 = p.lse[stat] * 1.4426950408889634f;
     const float dlt = p.delta[stat];
     for (int it = 0; it < n_iter; ++it) {
-      const int kv0 = (j_lo + it) * AT_N;
-      mbar_wait(sdp_full, it & 1);
+      const int kv0 = (j_lo + it) * AT_N + x * 64;
+      mbar_wait(&sdp_full[x], it & 1);
       tc_fence_after();
-      const bool need_mask = (kv0 + AT_N - 1 > row) || (p.window > 0 && kv0 < row - p.window);
+      const bool need_mask = (kv0 + 63 > row) || (p.window > 0 && kv0 < row - p.window);
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32];
-        tmem_ld_32x32(tmem + lane_addr + Q_S + c * 32, s);
-        tmem_ld_32x32(tmem + lane_addr + Q_DP + c * 32, dp);
+        tmem_ld_32x32(s_addr + c * 32, s);
+        tmem_ld_32x32(dp_addr + c * 32, dp);
         tmem_ld_wait();
         uint32_t dk[16];
 #pragma unroll
@@ -348,27 +395,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int col = kv0 + c * 32 + 2 * e2 + e;
-            float pe = fast_exp2(__uint_as_float(s[2 * e2 + e]) * p.scale_log2 - lse2);
+            float pe = fast_exp2(fmaf(__uint_as_float(s[2 * e2 + e]), p.scale_log2, -lse2));
             if (need_mask && (col > row || (p.window > 0 && col < row - p.window))) pe = 0.f;
             dv[e] = pe * (__uint_as_float(dp[2 * e2 + e]) - dlt) * p.scale;
           }
           dk[e2] = pack_bf16x2(dv[0], dv[1]);
         }
-        tmem_st_32x16(tmem + lane_addr + Q_DP + c * 16, dk);
+        tmem_st_32x16(dp_addr + c * 16, dk);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(ds_full);
+      if (lane == 0) mbar_arrive(&ds_full[x]);
     }
     mbar_wait(acc_done, 0);
     tc_fence_after();
     if (row < p.seq) {
-      __nv_bfloat16* dqrow = p.dq.row(row, b, p.hm.q(h));
+      __nv_bfloat16* dqrow = p.dq.row(row, b, p.hm.q(h)) + x * 64;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t a[32];
-        tmem_ld_32x32(tmem + lane_addr + Q_DQ + c * 32, a);
+        tmem_ld_32x32(tmem + lane_addr + Q_DQ + x * 64 + c * 32, a);
         tmem_ld_wait();
         uint4* d0 = reinterpret_cast<uint4*>(dqrow + c * 32);
 #pragma unroll
@@ -436,10 +483,10 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
     configured = true;
   }
   dim3 g1(seq / AT_N, heads / q_per_kv, batch);
-  attn_bwd_dkdv_kernel<<<g1, AT_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dkdv_kernel<<<g1, BW_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
   ATT_DBG("dkdv launched");
   dim3 g2(seq / AT_M, heads, batch);
-  attn_bwd_dq_kernel<<<g2, AT_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dq_kernel<<<g2, BW_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
   ATT_DBG("dq launched");
   return (int)cudaGetLastError();
 }
