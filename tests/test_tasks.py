@@ -79,3 +79,55 @@ def test_zeroshot_gpt(tmp_path):
     assert "validation results on WIKITEXT103" in out and "adjusted ppl" in out
     out = _run(common + ["--task", "LAMBADA", "--valid_data", str(tmp_path / "lambada.jsonl")])
     assert "validation results on LAMBADA" in out and "total examples: 6" in out
+
+
+def test_qa_match_utils():
+    from tasks.orqa.unsupervised.qa_utils import calculate_matches, exact_match_score, has_answer
+    from tasks.orqa.unsupervised.tokenizers import SimpleTokenizer
+    tok = SimpleTokenizer()
+    assert tok.tokenize("Hello, World! 42").words(uncased=True) == ["hello", ",", "world", "!", "42"]
+    assert has_answer(["new york"], "He moved to New York in 1999.", tok, "string")
+    assert not has_answer(["york new"], "He moved to New York in 1999.", tok, "string")
+    assert has_answer([r"19\d\d"], "He moved to New York in 1999.", tok, "regex")
+    assert exact_match_score("The Eiffel Tower!", "eiffel tower")
+    docs = {1: ("paris is the capital of france", "France"), 2: ("berlin is in germany", "Germany")}
+    stats = calculate_matches(docs, [["paris"], ["rome"]], [([2, 1], [0.9, 0.8]), ([1, 2], [0.5, 0.4])], 1, "string")
+    assert stats.top_k_hits == [0, 1] and stats.questions_doc_hits == [[False, True], [False, False]]
+
+
+def _ctx(rnd):
+    return {"title": _sent(rnd, 2), "text": _sent(rnd, 12)}
+
+
+def test_retriever_finetune_and_eval(tmp_path):
+    """RET-FINETUNE-NQ for one epoch (with hard negatives), then RETRIEVER-EVAL on the saved bi-encoder."""
+    rnd = random.Random(3)
+    rows = [{"question": _sent(rnd, 5) + "?", "answers": [rnd.choice(WORDS[:21])], "positive_ctxs": [_ctx(rnd)],
+             "negative_ctxs": [_ctx(rnd) for _ in range(3)], "hard_negative_ctxs": [_ctx(rnd) for _ in range(2)]}
+            for _ in range(8)]
+    (tmp_path / "nq-train.json").write_text(json.dumps(rows))
+    (tmp_path / "nq-dev.json").write_text(json.dumps(rows[:4]))
+    ckpt = tmp_path / "ckpt"
+    base = [a for a in MODEL] + ["--tokenizer_type", "BertWordPieceLowerCase", "--vocab_file", _vocab(tmp_path),
+                                 "--retriever_seq_length", "48", "--biencoder_projection_dim", "16",
+                                 "--retriever_report_topk_accuracies", "1", "2", "--bert_load", "none_given"]
+    base = base[:-2]
+    out = _run(base + ["--task", "RET-FINETUNE-NQ", "--epochs", "1", "--train_data", str(tmp_path / "nq-train.json"),
+                       "--valid_data", str(tmp_path / "nq-dev.json"), "--train_with_neg", "--train_hard_neg", "2",
+                       "--val_av_rank_hard_neg", "2", "--val_av_rank_other_neg", "2", "--eval_micro_batch_size", "2",
+                       "--save", str(ckpt), "--save_interval", "1000"])
+    assert "epoch:0|rank = " in out and "top1_acc" in out
+    # evidence + questions for the zero-shot style evaluation of the fine-tuned retriever
+    with open(tmp_path / "evidence.tsv", "w") as f:
+        f.write("id\ttext\ttitle\n")
+        for i in range(12):
+            f.write("{}\t{}\t{}\n".format(i + 1, _sent(rnd, 14), _sent(rnd, 2)))
+    with open(tmp_path / "nq-dev.tsv", "w") as f:
+        for i in range(3):
+            f.write("{}\t{}\n".format(_sent(rnd, 5), repr([rnd.choice(WORDS[:21])])))
+    out = _run(base + ["--task", "RETRIEVER-EVAL", "--load", str(ckpt), "--evidence_data_path",
+                       str(tmp_path / "evidence.tsv"), "--embedding_path", str(tmp_path / "evidence_embeds.pkl"),
+                       "--qa_data_dev", str(tmp_path / "nq-dev.tsv"), "--faiss_topk_retrievals", "5",
+                       "--indexer_batch_size", "4", "--indexer_log_interval", "1", "--no_load_optim", "--no_load_rng"])
+    assert "DEV SET RESULTS" in out and "top-1:" in out
+    assert os.path.exists(tmp_path / "evidence_embeds.pkl")
