@@ -131,3 +131,35 @@ def test_retriever_finetune_and_eval(tmp_path):
                        "--indexer_batch_size", "4", "--indexer_log_interval", "1", "--no_load_optim", "--no_load_rng"])
     assert "DEV SET RESULTS" in out and "top-1:" in out
     assert os.path.exists(tmp_path / "evidence_embeds.pkl")
+
+
+def test_msdp_metrics_and_preprocessing(tmp_path):
+    from tasks.msdp.metrics import F1Metric, normalize_answer
+    from tasks.msdp import preprocessing as pp
+    assert normalize_answer("The cat, an animal!") == "cat animal"
+    p, r, f = F1Metric.compute_all_pairs(["the cat sat", "anything", ""], ["a cat sat down", "", "dog"])
+    assert abs(p - 0.5) < 1e-6 and abs(r - 1 / 3) < 1e-6 and f > 0
+    wow = [{"chosen_topic": "Cats", "dialog": [
+        {"speaker": "0_Apprentice", "text": "I love cats"},
+        {"speaker": "1_Wizard", "text": "Cats are small felines", "checked_sentence": {"k": "The cat is a feline."},
+         "checked_passage": {"p": "Cat"}},
+        {"speaker": "0_Apprentice", "text": "Really?"},
+        {"speaker": "1_Wizard", "text": "Yes!", "checked_sentence": {}, "checked_passage": {}}]}]
+    (tmp_path / "wow.json").write_text(json.dumps(wow))
+    pp.process_wow_dataset(str(tmp_path / "wow.json"), str(tmp_path / "proc.txt"), str(tmp_path / "k.txt"),
+                           str(tmp_path / "r.txt"))
+    rows = (tmp_path / "proc.txt").read_text().strip().split("\n")
+    assert rows[0].split("\t") == ["Cat", "I love cats.", "The cat is a feline.", "Cats are small felines."]
+    assert rows[1].split("\t") == ["Cats", "I love cats. [SEP] Cats are small felines. [SEP] Really?",
+                                   "no_passages_used", "Yes!"]
+    (tmp_path / "gen.txt").write_text("generated one<|endoftext|>\nsecond\n")
+    pp.prepare_input_for_response_generation(str(tmp_path / "proc.txt"), str(tmp_path / "gen.txt"),
+                                             str(tmp_path / "inp.txt"))
+    assert (tmp_path / "inp.txt").read_text().split("\n")[0].split("\t")[2] == "generated one"
+    by_topic, dialogs, examples = pp.get_database(str(tmp_path / "proc.txt"), str(tmp_path / "proc.txt"), "wow_seen")
+    assert list(by_topic) == ["Cat"] and len(examples) == 1
+    from tasks.msdp.evaluate import evaluate_f1
+    import megatron_llm_b200.utils as u
+    (tmp_path / "guess.txt").write_text("the cat is a feline\nwhatever\n")
+    p, r, f = evaluate_f1(str(tmp_path / "guess.txt"), str(tmp_path / "k.txt"))
+    assert f > 0.9
