@@ -270,6 +270,12 @@ def _load_base_checkpoint(load_dir, use_distributed_optimizer, rank0=False, iter
         else:
             print_rank_0(f" loading checkpoint from {load_dir} at iteration {iteration}")
     model_name, optim_name = names
+    if use_distributed_optimizer and not os.path.isfile(model_name):
+        # a checkpoint written without the distributed optimizer (e.g. converted HF weights or a resharded checkpoint)
+        # keeps everything in model_optim_rng.pt; the model part of it is loadable (relaxes the reference, which fails)
+        alt = os.path.join(os.path.dirname(model_name), "model_optim_rng.pt")
+        if os.path.isfile(alt):
+            model_name = alt
     try:
         model_state = _torch_load(model_name)
         optim_state = _torch_load(optim_name) if (use_distributed_optimizer and os.path.isfile(optim_name)) \

@@ -112,15 +112,21 @@ def _communicate(tensor_send_next: Optional[torch.Tensor], tensor_send_prev: Opt
         if tensor_send_prev is not None:
             tensor_send_prev = split_tensor_into_1d_equal_chunks(tensor_send_prev)
 
+    def send_alias(t):
+        """A separate tensor object over the same storage: the schedule shrinks ``out.data`` of a sent activation
+        right after the send is *posted* (deallocate_output_tensor); the in-flight isend must keep the real storage."""
+        c = t.contiguous()
+        return c.detach() if c is t else c
+
     ops, kinds = [], []
     if tensor_send_prev is not None:
-        ops.append(dist.P2POp(dist.isend, tensor_send_prev.contiguous(), ps.get_pipeline_model_parallel_prev_rank()))
+        ops.append(dist.P2POp(dist.isend, send_alias(tensor_send_prev), ps.get_pipeline_model_parallel_prev_rank()))
         kinds.append("s")
     if tensor_recv_prev is not None:
         ops.append(dist.P2POp(dist.irecv, tensor_recv_prev, ps.get_pipeline_model_parallel_prev_rank()))
         kinds.append("r")
     if tensor_send_next is not None:
-        ops.append(dist.P2POp(dist.isend, tensor_send_next.contiguous(), ps.get_pipeline_model_parallel_next_rank()))
+        ops.append(dist.P2POp(dist.isend, send_alias(tensor_send_next), ps.get_pipeline_model_parallel_next_rank()))
         kinds.append("s")
     if tensor_recv_next is not None:
         ops.append(dist.P2POp(dist.irecv, tensor_recv_next, ps.get_pipeline_model_parallel_next_rank()))

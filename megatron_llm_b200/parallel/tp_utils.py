@@ -38,7 +38,8 @@ def gather_split_1d_tensor(tensor: torch.Tensor) -> torch.Tensor:
     world = ps.get_tensor_model_parallel_world_size()
     out = torch.empty(world * tensor.numel(), dtype=tensor.dtype, device=tensor.device,
                       requires_grad=False)
-    dist.all_gather_into_tensor(out, tensor.contiguous(), group=ps.get_tensor_model_parallel_group())
+    with torch.no_grad():      # pure data movement (the received chunk may carry requires_grad)
+        dist.all_gather_into_tensor(out, tensor.detach().contiguous(), group=ps.get_tensor_model_parallel_group())
     return out
 
 
