@@ -1,0 +1,6 @@
+#!/bin/bash
+# Stage 1: knowledge generation by few-shot prompting (parity: examples/msdp/prompt_knwl_gen.sh).
+source "$(dirname "$0")/../_common.sh"; DIR=${DIR:-data/msdp}
+launch $REPO/tasks/msdp/main.py --tensor_model_parallel_size 1 --num_layers 24 --hidden_size 1024 --num_attention_heads 16 --seq_length 2048 --max_position_embeddings 2048 --micro_batch_size 1 --vocab_file ${VOCAB_FILE:-gpt2-vocab.json} --merge_file ${MERGE_FILE:-gpt2-merges.txt} --tokenizer_type GPT2BPETokenizer --bf16 --load ${CHECKPOINT_PATH:-checkpoints/gpt2_345m} --task MSDP-PROMPT --prompt_type knowledge \
+  --sample_input_file $DIR/wow/test_seen_processed.txt --sample_output_file $DIR/wow/knwl_gen_seen.txt \
+  --prompt_file $DIR/wow/knwl_prompts_seen.jsonl --out_seq_length 100 --num_prompt_examples 10

@@ -1,0 +1,9 @@
+#!/bin/bash
+# 8-GPU data-parallel GPT-2 345M (parity: examples/pretrain_gpt_distributed.sh).  Gradients are reduced by the
+# peer-memory bucket kernel overlapped with the backward pass.
+source "$(dirname "$0")/_common.sh"
+CHECKPOINT_PATH=${CHECKPOINT_PATH:-checkpoints/gpt2_345m}; DATA_PATH=${DATA_PATH:-my-gpt2_text_document}
+launch $REPO/finetune.py --model_name gpt --micro_batch_size 8 --global_batch_size 64 --num_layers 24 --hidden_size 1024 --num_attention_heads 16 --seq_length 1024 --max_position_embeddings 1024
+  --vocab_file ${VOCAB_FILE:-gpt2-vocab.json} --merge_file ${MERGE_FILE:-gpt2-merges.txt} --tokenizer_type GPT2BPETokenizer \
+  --train_iters 500000 --lr_decay_iters 320000 --lr 0.00015 --min_lr 1.0e-5 --lr_decay_style cosine --lr_warmup_fraction .01
+  --weight_decay 1e-2 --clip_grad 1.0 --log_interval 100 --save_interval 10000 --eval_interval 1000 --eval_iters 10 --split 949,50,1 --save $CHECKPOINT_PATH --load $CHECKPOINT_PATH --data_path $DATA_PATH --bf16 --use_distributed_optimizer

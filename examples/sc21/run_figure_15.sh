@@ -1,0 +1,8 @@
+#!/bin/bash
+# Tensor vs data parallelism on 64 GPUs.
+cd "$(dirname "$0")"
+TP=${TP:-2}; GBS=${GBS:-32}; DP=$((64/TP)); PP=1; MBS=1; NLS=32; HS=3840; NAH=32; DDP=local; NNODES=8
+MEGATRON_EXTRA_PARAMS="--recompute_granularity full --recompute_method uniform "
+export JOB_NAME=results_figure_15_tensor_parallel_size_${TP}_data_parallel_size_${DP}_batch_size_${GBS}
+. ./CONFIG.sh
+. ./SBATCH.sh

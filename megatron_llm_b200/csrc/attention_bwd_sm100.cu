@@ -192,7 +192,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       else asm volatile("bar.sync 3, 128;" ::: "memory");
       mbar_wait(&sdp_full[x], it & 1);
       tc_fence_after();
+      // warp-uniform boundary-tile test; the masked path uses selects against per-chunk column limits
       const bool need_mask = (q0 < kv0 + AT_N - 1) || (p.window > 0 && q0 + AT_M - 1 > kv0 + p.window);
+      const int qlo = kv - q0 - x * 64;                                       // query columns < qlo precede this key
+      const int qhi = (p.window > 0) ? kv + p.window - q0 - x * 64 : (1 << 30);   // columns > qhi lost it from the window
       const float* lse_s = sLse + st * 128 + x * 64;
       const float* d_s = sD + st * 128 + x * 64;
 #pragma unroll 1
@@ -209,10 +212,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
           for (int e = 0; e < 2; ++e) {
             const int col = c * 32 + 2 * i + e;     // query index inside the half
             float pe = fast_exp2(fmaf(__uint_as_float(s[2 * i + e]), p.scale_log2, -lse_s[col]));
-            if (need_mask) {
-              const int qrow = q0 + x * 64 + col;
-              if (kv > qrow || (p.window > 0 && kv < qrow - p.window)) pe = 0.f;
-            }
+            if (need_mask) pe = (col < qlo || col > qhi) ? 0.f : pe;
             pv[e] = pe;
             dv[e] = pe * (__uint_as_float(dp[2 * i + e]) - d_s[col]) * p.scale;
           }
@@ -381,7 +381,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
       const int kv0 = (j_lo + it) * AT_N + x * 64;
       mbar_wait(&sdp_full[x], it & 1);
       tc_fence_after();
-      const bool need_mask = (kv0 + 63 > row) || (p.window > 0 && kv0 < row - p.window);
+      const bool need_mask = __any_sync(0xffffffffu, (kv0 + 63 > row) || (p.window > 0 && kv0 < row - p.window));
+      const int hi = row - kv0;                                             // columns > hi are in the future
+      const int lo = (p.window > 0) ? row - p.window - kv0 : -(1 << 30);    // columns < lo fell out of the window
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32];
@@ -394,9 +396,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
           float dv[2];
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const int col = kv0 + c * 32 + 2 * e2 + e;
+            const int col = c * 32 + 2 * e2 + e;
             float pe = fast_exp2(fmaf(__uint_as_float(s[2 * e2 + e]), p.scale_log2, -lse2));
-            if (need_mask && (col > row || (p.window > 0 && col < row - p.window))) pe = 0.f;
+            if (need_mask) pe = (col > hi || col < lo) ? 0.f : pe;
             dv[e] = pe * (__uint_as_float(dp[2 * e2 + e]) - dlt) * p.scale;
           }
           dk[e2] = pack_bf16x2(dv[0], dv[1]);

@@ -406,7 +406,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
       const int kv0 = (j_lo + t) * AT_N;
       mbar_wait(&s_full[x], t & 1);
       tc_fence_after();
-      const bool need_mask = (kv0 + AT_N - 1 > row) || (p.window > 0 && kv0 < row - p.window);
+      // masking only touches the boundary tiles; the decision is made warp-uniform so the common path carries no
+      // per-element branches, and the masked path uses selects against per-chunk column limits
+      const bool need_mask = __any_sync(0xffffffffu, (kv0 + AT_N - 1 > row) || (p.window > 0 && kv0 < row - p.window));
+      const int hi = row - kv0;                                        // columns  > hi are in the future
+      const int lo = (p.window > 0) ? row - p.window - kv0 : -(1 << 30);   // columns < lo fell out of the window
       // pass 1: row max (two chunks in flight)
       float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll 1
@@ -416,11 +420,11 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         tmem_ld_32x32(s_addr + c * 32 + 32, v1);
         tmem_ld_wait();
         if (need_mask) {
+          const int h0 = hi - c * 32, l0 = lo - c * 32;
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            const int col0 = kv0 + c * 32 + i, col1 = col0 + 32;
-            if (col0 > row || (p.window > 0 && col0 < row - p.window)) v0[i] = 0xff800000u;
-            if (col1 > row || (p.window > 0 && col1 < row - p.window)) v1[i] = 0xff800000u;
+            v0[i] = (i > h0 || i < l0) ? 0xff800000u : v0[i];
+            v1[i] = (i + 32 > h0 || i + 32 < l0) ? 0xff800000u : v1[i];
           }
         }
 #pragma unroll
@@ -457,16 +461,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t v[32];
         tmem_ld_32x32(s_addr + c * 32, v);
         tmem_ld_wait();
+        if (need_mask) {
+          const int h0 = hi - c * 32, l0c = lo - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[i] = (i > h0 || i < l0c) ? 0xff800000u : v[i];
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float s0 = __uint_as_float(v[2 * i]), s1 = __uint_as_float(v[2 * i + 1]);
-          if (need_mask) {
-            const int col = kv0 + c * 32 + 2 * i;
-            if (col > row || (p.window > 0 && col < row - p.window)) s0 = -INFINITY;
-            if (col + 1 > row || (p.window > 0 && col + 1 < row - p.window)) s1 = -INFINITY;
-          }
-          const float p0 = fast_exp2(fmaf(s0, sc, -moff)), p1 = fast_exp2(fmaf(s1, sc, -moff));
+          const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, -moff));
+          const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, -moff));
           l0 += p0; l1 += p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
