@@ -14,6 +14,7 @@ extern "C" {
 int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                   int a_mn_major, int b_mn_major, int epilogue, int block_n, const void* comm, int num_sms,
                   cudaStream_t stream);
+int mlb_gemm2_debug_read(unsigned long long* host, int n);
 int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                        int a_mn_major, int b_mn_major, int epilogue, int num_sms, cudaStream_t stream);
 int mlb_norm_fwd(int dtype, const void* x, const void* res_in, const void* w, const void* b, void* y, void* res_out,
@@ -253,8 +254,15 @@ static void softmax_bwd(torch::Tensor& dy, const torch::Tensor& y, double scale,
 void register_attention(pybind11::module_& m);
 void register_comm(pybind11::module_& m);
 
+static torch::Tensor gemm2_debug() {
+  auto t = torch::zeros({512, 8}, torch::dtype(torch::kInt64));
+  CHK(mlb_gemm2_debug_read(reinterpret_cast<unsigned long long*>(t.data_ptr<int64_t>()), 512 * 8));
+  return t;
+}
+
 PYBIND11_MODULE(_C_b200, m) {
   m.def("gemm", &gemm);
+  m.def("gemm2_debug", &gemm2_debug);
   m.def("norm_fwd", &norm_fwd);
   m.def("norm_bwd", &norm_bwd);
   m.def("rope_qkv", &rope_qkv);

@@ -7,6 +7,7 @@
 #include "ptx.cuh"
 
 #include <cudaTypedefs.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace mlb {
@@ -24,10 +25,21 @@ constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB per CTA per st
 constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
 constexpr int G2_SMEM_TOTAL = G2_BAR_OFFSET + 256 + 1024;
 
+// Optional timeline counters (MLB200_GEMM2_DEBUG=1): per CTA 8 x u64 =
+// [0] MMA cycles waiting on full_bar   [1] MMA cycles waiting on tmem_empty   [2] MMA total cycles
+// [3] producer cycles waiting on empty_bar   [4] producer total cycles
+// [5] epilogue(warp 4) cycles waiting on tmem_full   [6] epilogue total cycles   [7] tiles
+__device__ unsigned long long g2_dbg[512 * 8];
+__device__ __forceinline__ unsigned long long g2_clock() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+  return t;
+}
+
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const GemmParams p) {
+                      const GemmParams p, const int dbg) {
   constexpr uint32_t TMEM_COLS = 2 * G2_BLOCK_N;  // two accumulator stages
   constexpr uint32_t IDESC = make_idesc_f16(G2_BLOCK_M, G2_BLOCK_N, A_MN, B_MN, true);
   constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
@@ -92,13 +104,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      unsigned long long w_empty = 0, t_begin = dbg ? g2_clock() : 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
         for (int kb = 0; kb < num_k; ++kb) {
+          const unsigned long long t0 = dbg ? g2_clock() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (dbg) w_empty += g2_clock() - t0;
           uint8_t* sA = smem + stage * G2_STAGE_BYTES;
           uint8_t* sB = sA + G2_A_BYTES;
           if (leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * G2_STAGE_BYTES);
@@ -121,6 +136,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (++stage == G2_STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      if (dbg) { g2_dbg[blockIdx.x * 8 + 3] = w_empty; g2_dbg[blockIdx.x * 8 + 4] = g2_clock() - t_begin; }
     }
   } else if (warp == 1 && leader) {
     // ================================ MMA issuer (leader CTA only) ================================
@@ -129,12 +145,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
+      unsigned long long w_full = 0, w_tmem = 0, n_tiles = 0, t_begin = dbg ? g2_clock() : 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
+        unsigned long long t0 = dbg ? g2_clock() : 0;
         mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (dbg) { w_tmem += g2_clock() - t0; ++n_tiles; }
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * G2_BLOCK_N;
         for (int kb = 0; kb < num_k; ++kb) {
+          t0 = dbg ? g2_clock() : 0;
           mbar_wait(&full_bar[stage], phase);
+          if (dbg) w_full += g2_clock() - t0;
           tc_fence_after();
           const uint32_t sA = smem_u32(smem + stage * G2_STAGE_BYTES);
           const uint32_t sB = sA + G2_A_BYTES;
@@ -152,17 +173,24 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         umma_commit<2>(&tmem_full_bar[acc]);     // accumulators ready in BOTH CTAs
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (dbg) {
+        g2_dbg[blockIdx.x * 8 + 0] = w_full; g2_dbg[blockIdx.x * 8 + 1] = w_tmem;
+        g2_dbg[blockIdx.x * 8 + 2] = g2_clock() - t_begin; g2_dbg[blockIdx.x * 8 + 7] = n_tiles;
+      }
     }
   } else if (warp >= 4) {
     // ================================ epilogue (both CTAs) ================================
     const int q = warp - 4;
     int acc = 0;
     uint32_t acc_phase = 0;
+    unsigned long long w_tf = 0, t_begin = dbg ? g2_clock() : 0;
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
       const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF, n0 = n_blk * G2_BLOCK_N;
+      const unsigned long long t0 = dbg ? g2_clock() : 0;
       mbar_wait(&tmem_full_bar[acc], acc_phase);
+      if (dbg) w_tf += g2_clock() - t0;
       tc_fence_after();
       const int row = m0 + q * 32 + lane;
       const bool row_ok = row < p.M;
@@ -225,6 +253,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread is the only waiter
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (dbg && warp == 4 && lane == 0) {
+      g2_dbg[blockIdx.x * 8 + 5] = w_tf; g2_dbg[blockIdx.x * 8 + 6] = g2_clock() - t_begin;
+    }
   }
 
   tc_fence_before();
@@ -248,7 +279,8 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPar
   const int tiles = ((p.M + G2_BLOCK_M - 1) / G2_BLOCK_M) * ((p.N + G2_BLOCK_N - 1) / G2_BLOCK_N);
   int pairs = num_sms / 2;
   if (pairs > tiles) pairs = tiles;
-  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, p);
+  static const int dbg = getenv("MLB200_GEMM2_DEBUG") != nullptr;
+  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, p, dbg);
   return (int)cudaGetLastError();
 }
 
@@ -265,6 +297,10 @@ static int dispatch2_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, co
 }
 
 }  // namespace mlb
+
+extern "C" int mlb_gemm2_debug_read(unsigned long long* host, int n) {
+  return (int)cudaMemcpyFromSymbol(host, mlb::g2_dbg, sizeof(unsigned long long) * n);
+}
 
 extern "C" int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
                                   int ldc, int a_mn_major, int b_mn_major, int epilogue, int num_sms,
