@@ -48,6 +48,9 @@ def parse():
     p.add_argument("--micro_batch", type=int, default=1)
     p.add_argument("--layers", type=int, default=None, help="DEV ONLY: override layer count (invalidates the number)")
     p.add_argument("--no_e2e", action="store_true")
+    p.add_argument("--graph", type=int, default=-1,
+                   help="1/0: replay each micro-batch from a CUDA graph (default: on when TP > 1, where the step is "
+                        "launch-bound; see host_enqueue_ms_per_step)")
     return p.parse_args()
 
 
@@ -121,6 +124,9 @@ def megatron_argv(a, n_gpus):
         argv.append("--sequence_parallel")
     if a.model.startswith("mistral"):
         argv += ["--sliding_window_size", "4096"]
+    use_graph = a.graph == 1 or (a.graph == -1 and n_gpus > 1 and os.environ.get("MLB200_BENCH_GRAPH", "1") == "1")
+    if use_graph:
+        argv += ["--cuda_graph_microbatch"]
     return argv, vocab
 
 
@@ -191,15 +197,18 @@ def run_ours(a):
         n0 = ops.launches()
         s.record()
         last = None
+        t_host = time.perf_counter()
         for _ in range(k):
             loss = step(it)
             if read_loss and loss:
                 last = loss["lm loss"].item()          # D2H read of the step's result, every step
         e.record()
+        host_ms = (time.perf_counter() - t_host) * 1e3   # time the host needed to enqueue the work (no sync inside)
         torch.cuda.synchronize()
         dist.barrier()
         ms = torch.tensor([s.elapsed_time(e)], device=dev)
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        timed.host_enqueue_ms = host_ms / k
         return ms.item(), ops.launches() - n0, last
 
     for _ in range(a.warmup):
@@ -208,6 +217,7 @@ def run_ours(a):
     if rank == 0:
         sampler.start()
     ms_dev, launches, _ = timed(it_dev, a.steps, read_loss=False)
+    host_enqueue_ms = timed.host_enqueue_ms
     clocks = sampler.stop() if rank == 0 else None
     e2e = None
     if not a.no_e2e:
@@ -228,9 +238,11 @@ def run_ours(a):
                "config": {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
                           "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
                           "parallelism": f"tp{a.gpus}" + ("+sp" if a.gpus > 1 else ""),
+                          "cuda_graph_microbatch": bool(getattr(args, "cuda_graph_microbatch", False)),
                           "optimizer": "AdamW fp32 master (in timed region), clip 1.0",
                           "l2": "no flush needed: each step streams >100 GB of weights/grads/optimizer state (>> 126 MB L2)"},
-               "clocks": clocks, "e2e": e2e, "gpu_launches": launches}
+               "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
+               "host_enqueue_ms_per_step": host_enqueue_ms}
         print(json.dumps(out), flush=True)
     dist.barrier()
     dist.destroy_process_group()

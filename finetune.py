@@ -131,14 +131,23 @@ def loss_func(is_training, batch, outputs):
     return loss, out_dict
 
 
+def run_from_batch(batch, model):
+    tokens, labels, loss_mask, attention_mask, position_ids = batch
+    output_tensor = model(tokens, position_ids, attention_mask, labels=labels)
+    return output_tensor, partial(loss_func, model.training, batch)
+
+
 def forward_step(data_iterator, model):
     timers = get_timers()
     timers("batch-generator", log_level=2).start()
     batch = get_batch(data_iterator)
-    tokens, labels, loss_mask, attention_mask, position_ids = batch
     timers("batch-generator").stop()
-    output_tensor = model(tokens, position_ids, attention_mask, labels=labels)
-    return output_tensor, partial(loss_func, model.training, batch)
+    return run_from_batch(batch, model)
+
+
+# the two halves, for schedules that capture the device work of a micro-batch in a CUDA graph (--cuda_graph_microbatch)
+forward_step.get_batch = get_batch
+forward_step.run = run_from_batch
 
 
 def extra_args(parser):

@@ -227,6 +227,7 @@ _GROUPS = {
         ("--biencoder_projection_dim", dict(type=int, default=0)),
         ("--biencoder_shared_query_context_model", _S()),
         ("--ict_load", dict(type=str, default=None)),
+        ("--cuda_graph_microbatch", dict(action="store_true")),
         ("--bert_load", dict(type=str, default=None)),
         # (missing from the reference's parser although pretrain_bert.py reads it; restored from upstream Megatron-LM)
         ("--bert_no_binary_head", dict(action="store_false", dest="bert_binary_head")),

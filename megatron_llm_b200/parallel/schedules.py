@@ -149,12 +149,94 @@ def _enable_grad_sync(model, flag=True):
             fn(flag)
 
 
+class GraphedMicrobatch:
+    """One micro-batch (forward + loss + backward) captured in a CUDA graph and replayed.
+
+    With tensor parallelism the per-GPU kernels shrink by 1/TP while the host still issues the same ~2.7k launches per
+    micro-batch, so the step becomes launch-bound (``host_enqueue_ms_per_step`` in bench.py).  Replaying a graph
+    removes the host from the loop.  Requirements (checked by :func:`_graph_runner`): no pipeline parallelism, DP = 1
+    (gradient-bucket hooks are Python), no dropout / activation recompute (host-side RNG bookkeeping), static shapes,
+    and a forward_step_func that exposes its two halves as ``.get_batch(data_iterator)`` and ``.run(batch, model)``.
+    Gradients accumulate into the static fp32 ``main_grad`` buffers exactly as in eager mode (the accumulation hooks'
+    kernels are part of the graph)."""
+
+    WARMUP = 2
+
+    def __init__(self, parts, model, optimizer):
+        self.parts, self.model, self.optimizer = parts, model, optimizer
+        self.graph = None
+        self.calls = 0
+        self.static_batch = None
+        self.static_reduced = None
+        self.launches = 0
+
+    def _eager(self, batch, n_microbatches):
+        output, loss_func = self.parts.run(batch, self.model)
+        loss, reduced = loss_func(output)
+        scaled = loss / n_microbatches
+        if self.optimizer is not None:
+            scaled = self.optimizer.scale_loss(scaled)
+        torch.autograd.backward(scaled)
+        return reduced
+
+    def run(self, batch, n_microbatches):
+        from ..ops import _ext
+        self.calls += 1
+        if self.graph is None and self.calls <= self.WARMUP:
+            return self._eager(batch, n_microbatches)
+        if self.graph is None:
+            torch.cuda.synchronize()
+            self.static_batch = [b.clone() if torch.is_tensor(b) else b for b in batch]
+            self.graph = torch.cuda.CUDAGraph()
+            before = _ext.LAUNCHES
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.static_reduced = self._eager(self.static_batch, n_microbatches)
+            self.launches = _ext.LAUNCHES - before
+            torch.cuda.synchronize()
+            # the capture pass itself does not execute: fall through and replay for this micro-batch
+        for dst, src in zip(self.static_batch, batch):
+            if torch.is_tensor(dst):
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        _ext.count(self.launches)
+        return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.static_reduced.items()}
+
+
+_GRAPH_RUNNERS = {}
+
+
+def _graph_runner(forward_step_func, model, optimizer, forward_only):
+    get_args, _, _ = _glob()
+    args = get_args()
+    if forward_only or not getattr(args, "cuda_graph_microbatch", False) or not torch.cuda.is_available():
+        return None
+    if not (hasattr(forward_step_func, "get_batch") and hasattr(forward_step_func, "run")):
+        return None
+    ok = (ps.get_data_parallel_world_size() == 1 and args.hidden_dropout == 0.0 and args.attention_dropout == 0.0
+          and args.recompute_granularity is None and not args.variable_seq_lengths and not args.fp16)
+    if not ok:
+        if not getattr(_graph_runner, "warned", False):
+            print("WARNING: --cuda_graph_microbatch ignored (needs DP=1, no dropout, no recompute, bf16/fp32, fixed "
+                  "sequence length)", flush=True)
+            _graph_runner.warned = True
+        return None
+    key = id(model)
+    if key not in _GRAPH_RUNNERS:
+        _GRAPH_RUNNERS[key] = GraphedMicrobatch(forward_step_func, model, optimizer)
+    return _GRAPH_RUNNERS[key]
+
+
 def forward_backward_no_pipelining(forward_step_func, data_iterator, model, optimizer, timers, forward_only,
                                    collect_non_loss_data=False):
     """All micro-batches forward+backward on one stage; DP grad reduction overlaps the last backward."""
     _, get_num_microbatches, _ = _glob()
     assert len(model) == 1
     model = model[0]
+    runner = _graph_runner(forward_step_func, model, optimizer, forward_only) if not collect_non_loss_data else None
+    if runner is not None:
+        n = get_num_microbatches()
+        _enable_grad_sync(model, True)
+        return [runner.run(forward_step_func.get_batch(data_iterator), n) for _ in range(n)]
     from torch.nn.parallel.distributed import DistributedDataParallel as torchDDP
     context_handler = model.no_sync if isinstance(model, torchDDP) else dummy_handler
     forward_data_store = []
