@@ -65,6 +65,11 @@ def _initialize_distributed():
             else:
                 args.local_rank = device
             torch.cuda.set_device(device)
+            if getattr(args, "cuda_graph_microbatch", False):
+                # CUDA-graph capture cannot touch the legacy default stream, and autograd's AccumulateGrad nodes run
+                # on the stream that was current when they were created (model construction): do everything on one
+                # ordinary side stream from the very beginning and capture on that same stream
+                torch.cuda.set_stream(torch.cuda.Stream())
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         kwargs = {}

@@ -44,7 +44,10 @@ def _tile_cfg(M: int, N: int) -> int:
         return 0
     if mode == "1":
         return 512
-    return 0  # TODO(perf): switch to 512 once the 2-CTA kernel is validated on hardware
+    # auto: the 2-CTA kernel halves the B-operand shared-memory / L2 traffic per SM and wins whenever there are enough
+    # 256x256 tiles to keep the 74 SM pairs busy (measured: profiles/gemm_shapes_v2.jsonl)
+    tiles = ((M + 255) // 256) * ((N + 255) // 256)
+    return 512 if (M >= 256 and N >= 256 and tiles >= 48) else 0
 
 
 def _gemm_ok(*ts) -> bool:

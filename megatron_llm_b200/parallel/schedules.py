@@ -189,7 +189,7 @@ class GraphedMicrobatch:
             self.static_batch = [b.clone() if torch.is_tensor(b) else b for b in batch]
             self.graph = torch.cuda.CUDAGraph()
             before = _ext.LAUNCHES
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream(), capture_error_mode="thread_local"):
                 self.static_reduced = self._eager(self.static_batch, n_microbatches)
             self.launches = _ext.LAUNCHES - before
             torch.cuda.synchronize()
