@@ -100,11 +100,14 @@ static void gemm(const torch::Tensor& A, const torch::Tensor& B, torch::Tensor& 
   TORCH_CHECK(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && N % 8 == 0, "gemm: leading dims / N must be multiples of 8");
   c10::cuda::CUDAGuard guard(A.device());
   const void* cp = comm.has_value() ? comm->data_ptr() : nullptr;
-  if (block_n == 512) {  // 2-CTA (cta_group::2) 256x256 tiles
+  // 2-CTA (cta_group::2) 256x256 tiles; its TMA-store epilogue needs 16-byte multiples of the output row pitch
+  const int64_t out_bytes = (epilogue == 0 || epilogue == 3) ? 2 : 4;
+  if (block_n == 512 && (ldc * out_bytes) % 16 == 0) {
     CHK(mlb_gemm_bf16_2cta(A.data_ptr(), B.data_ptr(), C.data_ptr(), (int)M, (int)N, (int)K, (int)lda, (int)ldb,
                            (int)ldc, a_mn, b_mn, (int)epilogue, sms > 0 ? (int)sms : num_sms(), cur()));
     return;
   }
+  if (block_n == 512) block_n = 0;
   CHK(mlb_gemm_bf16(A.data_ptr(), B.data_ptr(), C.data_ptr(), (int)M, (int)N, (int)K, (int)lda, (int)ldb, (int)ldc,
                     a_mn, b_mn, (int)epilogue, (int)block_n, cp, sms > 0 ? (int)sms : num_sms(), cur()));
 }

@@ -14,6 +14,8 @@ namespace mlb {
 
 int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer, uint64_t ld,
                       uint32_t box_inner, uint32_t box_outer);
+int make_tmap_2d_out(CUtensorMap* tm, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_outer);
 
 constexpr int G2_BLOCK_M = 256;      // per pair
 constexpr int G2_BLOCK_N = 256;
@@ -22,7 +24,10 @@ constexpr int G2_STAGES = 6;
 constexpr int G2_A_BYTES = G2_HALF * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int G2_B_BYTES = G2_HALF * GEMM_BLOCK_K * 2;   // 16 KB
 constexpr int G2_STAGE_BYTES = G2_A_BYTES + G2_B_BYTES;  // 32 KB per CTA per stage
-constexpr int G2_BAR_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+// epilogue staging for the TMA stores: per warp 2 buffers of [32 rows][128 B] (128B-swizzled), 32 KB per CTA
+constexpr int G2_EPI_OFFSET = G2_STAGES * G2_STAGE_BYTES;
+constexpr int G2_EPI_BYTES = 4 * 2 * 4096;
+constexpr int G2_BAR_OFFSET = G2_EPI_OFFSET + G2_EPI_BYTES;
 constexpr int G2_SMEM_TOTAL = G2_BAR_OFFSET + 256 + 1024;
 
 // Optional timeline counters (MLB200_GEMM2_DEBUG=1): per CTA 8 x u64 =
@@ -39,7 +44,7 @@ __device__ __forceinline__ unsigned long long g2_clock() {
 template <bool A_MN, bool B_MN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const GemmParams p, const int dbg) {
+                      const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int dbg) {
   constexpr uint32_t TMEM_COLS = 2 * G2_BLOCK_N;  // two accumulator stages
   constexpr uint32_t IDESC = make_idesc_f16(G2_BLOCK_M, G2_BLOCK_N, A_MN, B_MN, true);
   constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
@@ -197,6 +202,49 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool row_ok = row < p.M;
       uint8_t* crow = reinterpret_cast<uint8_t*>(p.C) + (size_t)(row_ok ? row : 0) * p.ldc * OUT_ELEM;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * G2_BLOCK_N;
+      if constexpr (EPI != EPI_BF16_ACCUM) {
+        // TMEM -> registers -> swizzled smem rows of 128 B -> one TMA store (or fp32 reduce-add) per 32-row x 128-B
+        // box: full-line global writes, no read-modify-write traffic through the SM for the wgrad accumulation,
+        // out-of-range rows / columns clipped by the tensor map
+        uint8_t* ebase = smem + G2_EPI_OFFSET + q * 8192;
+        constexpr int COLS = 128 / OUT_ELEM;                 // columns per box: 32 fp32 or 64 bf16
+#pragma unroll 1
+        for (int c = 0; c < G2_BLOCK_N / COLS; ++c) {
+          uint32_t w[32];                                    // this row's 128 bytes
+          if constexpr (OUT_ELEM == 4) {
+            tmem_ld_32x32(taddr + c * 32, w);
+            tmem_ld_wait();
+          } else {
+            uint32_t r0[32], r1[32];
+            tmem_ld_32x32(taddr + c * 64, r0);
+            tmem_ld_32x32(taddr + c * 64 + 32, r1);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              w[i] = pack_bf16x2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+              w[16 + i] = pack_bf16x2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+            }
+          }
+          uint8_t* buf = ebase + (c & 1) * 4096;
+          if (lane == 0) tma_store_wait_read<1>();           // the store from two chunks ago has drained this buffer
+          __syncwarp();
+          uint8_t* rowp = buf + lane * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(rowp + ((j ^ (lane & 7)) << 4)) =
+                make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const int c0 = n0 + c * COLS, c1 = m0 + q * 32;
+            if (c0 < p.N && c1 < p.M) {
+              if constexpr (EPI == EPI_F32_ACCUM) tma_reduce_add_2d(&tmC, buf, c0, c1);
+              else tma_store_2d(&tmC, buf, c0, c1);
+            }
+            tma_store_commit();
+          }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < G2_BLOCK_N / 64; ++c) {
         uint32_t r0[32], r1[32];
@@ -254,6 +302,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread is the only waiter
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();     // all epilogue stores of this warp have completed
     if (dbg && warp == 4 && lane == 0) {
       g2_dbg[blockIdx.x * 8 + 5] = w_tf; g2_dbg[blockIdx.x * 8 + 6] = g2_clock() - t_begin;
     }
@@ -268,8 +317,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 template <bool A_MN, bool B_MN, int EPI>
-static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
-                   cudaStream_t stream) {
+static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
+                   int num_sms, cudaStream_t stream) {
   auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -281,18 +330,18 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPar
   int pairs = num_sms / 2;
   if (pairs > tiles) pairs = tiles;
   static const int dbg = getenv("MLB200_GEMM2_DEBUG") != nullptr;
-  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, p, dbg);
+  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, tmC, p, dbg);
   return (int)cudaGetLastError();
 }
 
 template <bool A_MN, bool B_MN>
-static int dispatch2_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, const GemmParams& p, int sms,
-                         cudaStream_t st) {
+static int dispatch2_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                         const GemmParams& p, int sms, cudaStream_t st) {
   switch (epi) {
-    case EPI_BF16: return launch2<A_MN, B_MN, EPI_BF16>(a, b, p, sms, st);
-    case EPI_F32_ACCUM: return launch2<A_MN, B_MN, EPI_F32_ACCUM>(a, b, p, sms, st);
-    case EPI_F32: return launch2<A_MN, B_MN, EPI_F32>(a, b, p, sms, st);
-    case EPI_BF16_ACCUM: return launch2<A_MN, B_MN, EPI_BF16_ACCUM>(a, b, p, sms, st);
+    case EPI_BF16: return launch2<A_MN, B_MN, EPI_BF16>(a, b, c, p, sms, st);
+    case EPI_F32_ACCUM: return launch2<A_MN, B_MN, EPI_F32_ACCUM>(a, b, c, p, sms, st);
+    case EPI_F32: return launch2<A_MN, B_MN, EPI_F32>(a, b, c, p, sms, st);
+    case EPI_BF16_ACCUM: return launch2<A_MN, B_MN, EPI_BF16_ACCUM>(a, b, c, p, sms, st);
   }
   return -2;
 }
@@ -316,11 +365,15 @@ extern "C" int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, 
   if (!b_mn_major) r = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, G2_HALF);
   else r = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BLOCK_K);
   if (r) return 2000 + r;
+  CUtensorMap tmC;
+  const int out_bytes = (epilogue == EPI_BF16 || epilogue == EPI_BF16_ACCUM) ? 2 : 4;
+  r = make_tmap_2d_out(&tmC, C, out_bytes, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32);
+  if (r) return 3000 + r;
   GemmParams p;
   memset(&p, 0, sizeof(p));
   p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
-  if (!a_mn_major && !b_mn_major) return dispatch2_epi<false, false>(epilogue, tmA, tmB, p, num_sms, stream);
-  if (!a_mn_major && b_mn_major) return dispatch2_epi<false, true>(epilogue, tmA, tmB, p, num_sms, stream);
-  if (a_mn_major && b_mn_major) return dispatch2_epi<true, true>(epilogue, tmA, tmB, p, num_sms, stream);
-  return dispatch2_epi<true, false>(epilogue, tmA, tmB, p, num_sms, stream);
+  if (!a_mn_major && !b_mn_major) return dispatch2_epi<false, false>(epilogue, tmA, tmB, tmC, p, num_sms, stream);
+  if (!a_mn_major && b_mn_major) return dispatch2_epi<false, true>(epilogue, tmA, tmB, tmC, p, num_sms, stream);
+  if (a_mn_major && b_mn_major) return dispatch2_epi<true, true>(epilogue, tmA, tmB, tmC, p, num_sms, stream);
+  return dispatch2_epi<true, false>(epilogue, tmA, tmB, tmC, p, num_sms, stream);
 }

@@ -37,6 +37,22 @@ int make_tmap_2d_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
+// 2-D output map (fp32 or bf16), 128-byte inner box (32 fp32 / 64 bf16 columns), 128B swizzle: epilogue TMA stores
+int make_tmap_2d_out(CUtensorMap* tm, const void* base, int elem_bytes, uint64_t inner, uint64_t outer, uint64_t ld,
+                     uint32_t box_outer) {
+  auto fn = get_encode_fn();
+  mlb_bind_context();
+  if (!fn) return -1;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * (uint64_t)elem_bytes};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / elem_bytes), box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
 template <int BLOCK_N, bool A_MN, bool B_MN, int EPI, int MODE = MODE_PLAIN>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int num_sms,
                   cudaStream_t stream) {

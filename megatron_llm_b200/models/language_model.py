@@ -147,11 +147,13 @@ class Embedding(MegatronModule):
         embeddings = embeddings.transpose(0, 1).contiguous()  # [b,s,h] -> [s,b,h]
         if self.fp32_residual_connection:
             embeddings = embeddings.float()
+        drop = self.training and self.embedding_dropout.p > 0.0      # p = 0: no RNG use (and CUDA-graph capturable)
         if self.sequence_parallel:
             embeddings = mappings.scatter_to_sequence_parallel_region(embeddings)
-            with get_cuda_rng_tracker().fork():
-                embeddings = self.embedding_dropout(embeddings)
-        else:
+            if drop:
+                with get_cuda_rng_tracker().fork():
+                    embeddings = self.embedding_dropout(embeddings)
+        elif drop:
             embeddings = self.embedding_dropout(embeddings)
         return embeddings
 

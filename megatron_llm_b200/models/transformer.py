@@ -500,6 +500,7 @@ class ParallelTransformer(MegatronModule):
         self.recompute_num_layers = args.recompute_num_layers
         self.distribute_saved_activations = args.distribute_saved_activations and not args.sequence_parallel
         self.sequence_parallel = args.sequence_parallel
+        self._any_dropout = args.hidden_dropout > 0.0 or args.attention_dropout > 0.0 or drop_path_rate > 0.0
         assert args.transformer_impl == "local", \
             "transformer_engine fp8 layers are not part of this build (fp8 is never on a Llama/Falcon/Mistral path)"
         self.num_microbatches_in_previous_step = -1
@@ -598,7 +599,9 @@ class ParallelTransformer(MegatronModule):
         if not self.pre_process:
             hidden_states = self.input_tensor
         hidden_states = make_viewless_tensor(hidden_states, requires_grad=True, keep_graph=True)
-        rng_context = get_cuda_rng_tracker().fork() if self.sequence_parallel else nullcontext()
+        # the forked (per-TP-rank) RNG stream only matters if something draws random numbers
+        rng_context = get_cuda_rng_tracker().fork() if (self.sequence_parallel and self.training and self._any_dropout) \
+            else nullcontext()
         deferred = None
         with rng_context:
             if self.recompute_granularity == "full":
