@@ -244,7 +244,13 @@ def run_ours(a):
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                "host_enqueue_ms_per_step": host_enqueue_ms}
         print(json.dumps(out), flush=True)
+    torch.cuda.synchronize()
     dist.barrier()
+    if getattr(args, "cuda_graph_microbatch", False):
+        # tearing down NCCL communicators that are referenced by live CUDA graphs can block: leave without it
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
     dist.destroy_process_group()
 
 

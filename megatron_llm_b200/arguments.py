@@ -116,6 +116,9 @@ _GROUPS = {
         ("--sequence_parallel", _S()),
         ("--no_gradient_accumulation_fusion", _SF("gradient_accumulation_fusion")),
         # B200-native switches (not in the reference)
+        # fused GEMM+collective kernels over NVLink peer memory (all-gather->GEMM, GEMM->reduce-scatter).  Opt-in: as
+        # measured (profiles/README.md) the NCCL path + CUDA-graph micro-batches is currently faster at TP=2..8.
+        ("--fused_tp_comm", dict(action="store_true", default=False)),
         ("--no_fused_tp_comm", _SF("fused_tp_comm")),
         ("--no_fused_dp_comm", _SF("fused_dp_comm")),
         ("--ddp_bucket_size_mb", dict(type=int, default=256)),

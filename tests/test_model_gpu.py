@@ -66,3 +66,23 @@ def test_kernels_match_torch_path(name):
         assert abs(la - lb) < 3e-2 * max(1.0, abs(lb)), (a, b)
         assert abs(ga - gb) < 0.15 * max(1e-3, abs(gb)), (a, b)
     assert a[-1][0] < a[0][0] + 1e-3   # loss does not blow up over 3 steps
+
+
+def test_cuda_graph_microbatch_matches_eager():
+    """Replaying the micro-batch from a CUDA graph (--cuda_graph_microbatch) trains exactly like the eager schedule:
+    same kernels, same order -> identical loss / grad-norm trajectory (first steps are eager warm-up + capture)."""
+    argv = CONFIGS["llama"].replace("--train_iters 10", "--train_iters 20")
+    script = SCRIPT.replace("for step in range(3):", "for step in range(6):")
+    def run(extra, port):
+        env = dict(os.environ, MLB200_DISABLE_KERNELS="0")
+        code = script % {"root": ROOT, "port": str(port), "argv": argv + extra, "seq": 256}
+        r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        import json
+        line = [l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1]
+        return json.loads(line[len("RESULT "):])
+    eager = run("", 29612)
+    graph = run(" --cuda_graph_microbatch", 29613)
+    for (la, ga), (lb, gb) in zip(eager, graph):
+        assert abs(la - lb) < 2e-3 * max(1.0, abs(la)), (eager, graph)
+        assert abs(ga - gb) < 2e-2 * max(1e-3, abs(ga)), (eager, graph)

@@ -25,6 +25,9 @@ data = it()
 for _ in range(2):
     train_step(finetune.forward_step, data, model, opt, sched)
 torch.cuda.synchronize()
+_s, _e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+_s.record(); train_step(finetune.forward_step, data, model, opt, sched); _e.record(); torch.cuda.synchronize()
+step_ms = _s.elapsed_time(_e)
 from torch.profiler import profile, ProfilerActivity
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     train_step(finetune.forward_step, data, model, opt, sched)
@@ -37,7 +40,8 @@ for e in prof.key_averages():
 rows.sort(reverse=True)
 tot = sum(r[0] for r in rows)
 with open(out, "w") as f:
-    f.write(f"layers={layers} global_batch=2 total_device_us={tot:.0f}\n")
+    f.write(f"layers={layers} global_batch=2 total_device_us={tot:.0f} unprofiled_step_ms={step_ms:.1f} "
+            f"(device busy {tot / 10 / step_ms:.1f}% of the step)\n")
     for dt, n, k in rows[:45]:
         f.write(f"{dt/tot*100:6.2f}%  {dt:10.0f}us  n={n:5d}  {k[:110]}\n")
 print(open(out).read())
