@@ -1,0 +1,118 @@
+"""Small unit tests mirroring the reference's tests/test_basic.py, test_utils.py, test_activations.py, test_wandb.py
+and test_layernorm_order.py (CPU)."""
+import os
+import sys
+
+import pytest
+import torch
+from torch.nn import functional as F
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), os.pardir))
+sys.path.insert(0, ROOT)
+
+
+def test_import_and_compat_alias():
+    import megatron_llm_b200  # noqa: F401
+    import megatron
+    from megatron.core import tensor_parallel, parallel_state  # noqa: F401
+    from megatron.model import GPTModel, LlamaModel  # noqa: F401
+    from megatron.core.tensor_parallel import ColumnParallelLinear, RowParallelLinear, vocab_parallel_cross_entropy  # noqa
+    assert megatron.get_args is megatron_llm_b200.get_args
+
+
+def test_divide_and_viewless_helpers():
+    from megatron_llm_b200.utils import core_utils as util
+    assert util.divide(4, 2) == 2
+    with pytest.raises(AssertionError):
+        util.divide(4, 5)
+    inp = torch.rand(3, 4)
+    assert torch.equal(inp, util.make_viewless_tensor(inp, True, True))
+    assert torch.equal(inp, util.make_viewless_tensor(inp, True, False))
+    view = inp.view(4, 3)
+    out = util.make_viewless_tensor(view, False, False)
+    assert out._base is None and torch.equal(out, view)
+    t = torch.zeros(3, 4)
+    new = torch.rand(3, 4)
+    util.safely_set_viewless_tensor_data(t, new)
+    assert torch.equal(t, new)
+    assert torch.equal(util.assert_viewless_tensor(inp), inp)
+    assert all(torch.equal(a, inp) for a in util.assert_viewless_tensor([inp, inp]))
+
+
+@pytest.mark.parametrize("name,act", [("liglu", lambda x: x), ("geglu", F.gelu), ("reglu", F.relu), ("swiglu", F.silu)])
+def test_glu_activations(name, act):
+    from megatron_llm_b200.models.activations import GLU_ACTIVATIONS
+    torch.manual_seed(11)
+    x = torch.randn(3, 257, 2 * 38)
+    x1, x2 = x.chunk(2, dim=-1)
+    out = GLU_ACTIVATIONS[name](x)
+    assert list(out.shape) == [3, 257, 38]
+    assert torch.allclose(out, x1 * act(x2), atol=1e-6)
+
+
+def test_wandb_shim_without_wandb(tmp_path, monkeypatch):
+    """The TensorBoard-compatible shim must work (mirror to TB, drop 'vs samples' duplicates) with wandb offline or
+    absent."""
+    from megatron_llm_b200 import wandb_logger
+    monkeypatch.setenv("WANDB_MODE", "offline")
+    monkeypatch.setenv("WANDB_DIR", str(tmp_path))
+    cfg = wandb_logger.WandBConfig.default("test-logger")
+    cfg.logdir = str(tmp_path / "tb")
+    cfg.with_tensorboard = True
+    w = wandb_logger.WandbTBShim(cfg)
+    for step in range(3):
+        w.add_scalar("lm loss", 1.0 / (step + 1), step)
+        w.add_scalar("lm loss vs samples", 1.0, step * 8)
+    w.add_text("args", "x=1")
+    w.flush_all()
+    assert w._pending == {}
+
+
+def _layer(rank, world, extra):
+    from megatron_llm_b200.initialize import initialize_megatron
+    from megatron_llm_b200.global_vars import get_args
+    initialize_megatron(args_list=["--num_layers", "2", "--hidden_size", "16", "--num_attention_heads", "4",
+                                   "--seq_length", "8", "--max_position_embeddings", "8", "--micro_batch_size", "2",
+                                   "--tokenizer_type", "NullTokenizer", "--vocab_file", "32", "--train_iters", "1",
+                                   "--lr", "1e-3", "--hidden_dropout", "0.0", "--attention_dropout", "0.0",
+                                   "--use_bias"] + extra)
+    args = get_args()
+    from megatron_llm_b200.models.activations import init_method_normal, scaled_init_method_normal
+    from megatron_llm_b200.models.enums import LayerType
+    from megatron_llm_b200.models.transformer import ParallelTransformerLayer
+    torch.manual_seed(0)
+    layer = ParallelTransformerLayer(init_method_normal(0.02), scaled_init_method_normal(0.02, 2), 1,
+                                     layer_type=LayerType.encoder, args=args, world_size=1)
+    x = torch.randn(8, 2, 16)
+    mask = torch.zeros(2, 1, 8, 8, dtype=torch.bool)
+    out = layer(x, mask)
+    return layer, x, out
+
+
+def _layernorm_order(rank, world):
+    """pre-LN: out = x' + mlp(LN2(x')), x' = x + attn(LN1(x));  post-LN: out = LN(x' + mlp(x')), x' = x + attn(x)."""
+    layer, x, out = _layer(rank, world, [])
+    mask = torch.zeros(2, 1, 8, 8, dtype=torch.bool)
+    a, ab = layer.self_attention(layer.input_layernorm(x), mask)
+    x1 = x + a + (ab if ab is not None else 0)
+    m, mb = layer.mlp(layer.post_attention_layernorm(x1))
+    ref = x1 + m + (mb if mb is not None else 0)
+    assert torch.allclose(out, ref, atol=1e-5), (out - ref).abs().max()
+    assert isinstance(layer.output_layernorm, torch.nn.Identity)
+
+
+def _post_ln(rank, world):
+    layer, x, out = _layer(rank, world, ["--use_post_ln"])
+    assert isinstance(layer.input_layernorm, torch.nn.Identity)
+    mask = torch.zeros(2, 1, 8, 8, dtype=torch.bool)
+    a, ab = layer.self_attention(x, mask)
+    x1 = x + a + (ab if ab is not None else 0)
+    m, mb = layer.mlp(layer.post_attention_layernorm(x1))
+    ref = layer.output_layernorm(x1 + m + (mb if mb is not None else 0))
+    assert torch.allclose(out, ref, atol=1e-5), (out - ref).abs().max()
+
+
+def test_layernorm_order():
+    from tests.dist_utils import run_distributed
+    run_distributed(_layernorm_order, 1)
+    run_distributed(_post_ln, 1)
