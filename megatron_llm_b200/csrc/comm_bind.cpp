@@ -4,6 +4,8 @@
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
 
+#include <cstdlib>
+
 #include <cstdio>
 #include <stdexcept>
 
@@ -13,6 +15,10 @@
 #include "gemm_types.h"
 
 extern "C" {
+int mlb_gemm_bf16_2cta_ag(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                          int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int b_mn_major,
+                          mlb::GemmComm* comm, int prev_total, int num_sms, cudaStream_t stream);
 int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
                         int ldc, int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
 int mlb_dp_reduce(int reduce_scatter, float* local, const long long* peer_ptrs, int* pad_local,
@@ -70,16 +76,26 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
   c.ag_chunk_flags = chunk_flags.data_ptr<int>();
   c.ag_read_counters = read_counters.data_ptr<int>();
   fill_pads(c, pad_local, pad_peers);
+  // the 2-CTA (256x256-tile, TMA-store epilogue) kernel when the shard is a whole number of its row blocks
+  static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;
+  if (!force_1cta && rows_per_rank % 256 == 0 && num_comm_ctas % 2 == 0 && N >= 256 && (out.stride(0) * 2) % 16 == 0) {
+    CHK(mlb_gemm_bf16_2cta_ag(gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
+                              (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(),
+                              cur()));
+    return;
+  }
   CHK(mlb_gemm_bf16_fused(mlb::MODE_AG_GEMM, gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
                           (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
 }
 
 // rs_out[M/world, N] = reduce_scatter(x[M, K] @ W^T or @ W) over the group; tiles travel through rs_dst[] (peer slots).
-static void fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight, torch::Tensor& rs_out, bool b_mn,
-                          const std::vector<int64_t>& rs_dst, int64_t rs_slots, int64_t rows_per_rank,
-                          int64_t expected_total, torch::Tensor& reduce_counter, int64_t pad_local,
-                          const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world, int64_t epoch,
-                          int64_t sms) {
+// ``prev_total``: cumulative arrivals every source had delivered per destination before this call; returns the new
+// cumulative count (the tile granularity depends on the kernel variant that is chosen here).
+static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight, torch::Tensor& rs_out, bool b_mn,
+                             const std::vector<int64_t>& rs_dst, int64_t rs_slots, int64_t rows_per_rank,
+                             int64_t prev_total, int64_t tiles_1cta, torch::Tensor& reduce_counter, int64_t pad_local,
+                             const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world, int64_t epoch,
+                             int64_t sms) {
   c10::cuda::CUDAGuard guard(x.device());
   const int M = x.size(0), K = x.size(1);
   const int N = b_mn ? weight.size(1) : weight.size(0);
@@ -94,11 +110,20 @@ static void fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight, t
   c.rs_slots = reinterpret_cast<const void*>(rs_slots);
   c.rs_out = rs_out.data_ptr();
   c.rs_rows_per_rank = rows_per_rank;
-  c.rs_expected_total = expected_total;
   c.rs_reduce_counter = reduce_counter.data_ptr<int>();
   fill_pads(c, pad_local, pad_peers);
+  static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;
+  if (!force_1cta && rows_per_rank % 256 == 0 && N >= 256) {
+    const int got = mlb_gemm_bf16_2cta_rs(x.data_ptr(), weight.data_ptr(), M, N, K, (int)x.stride(0),
+                                          (int)weight.stride(0), b_mn, &c, (int)prev_total,
+                                          sms > 0 ? (int)sms : sm_count(), cur());
+    if (got > 0) return prev_total + got;
+    TORCH_CHECK(got == -3, "fused_gemm_rs (2-CTA) failed with code ", got);
+  }
+  c.rs_expected_total = (int)(prev_total + tiles_1cta);
   CHK(mlb_gemm_bf16_fused(mlb::MODE_GEMM_RS, x.data_ptr(), weight.data_ptr(), nullptr, M, N, K, (int)x.stride(0),
                           (int)weight.stride(0), N, b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
+  return prev_total + tiles_1cta;
 }
 
 // Data-parallel gradient reduction over peer memory: every rank's fp32 bucket lives in symmetric memory.

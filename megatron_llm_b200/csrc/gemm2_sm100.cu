@@ -3,8 +3,7 @@
 // halved and the smem ring is 6 stages deep instead of 4), the leader CTA's single MMA thread issues
 // tcgen05.mma.cta_group::2 (UMMA 256x256x16), accumulators live in both CTAs' TMEM (128 lanes x 256 columns each,
 // double buffered), and each CTA's four epilogue warps drain their own half.
-#include "gemm_types.h"
-#include "ptx.cuh"
+#include "gemm_sm100.cuh"   // GemmParams, ptx helpers, spin_until_ge, ag_puller (shared with the 1-CTA kernel)
 
 #include <cudaTypedefs.h>
 #include <stdlib.h>
@@ -41,16 +40,33 @@ __device__ __forceinline__ unsigned long long g2_clock() {
   return t;
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+// MODE_GEMM_RS: one bf16 output map per destination rank (this rank's receive slot [rows_per_rank, N] on that rank,
+// NVLink-mapped): the epilogue's TMA stores go straight into peer memory in 32-row x 128-byte boxes
+struct RsMaps {
+  CUtensorMap m[GEMM_MAX_PEERS];
+};
+
+template <bool A_MN, bool B_MN, int EPI, int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      const __grid_constant__ CUtensorMap tmC, const GemmParams p, const int dbg) {
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ RsMaps rsm,
+                      const GemmParams p, const int dbg) {
   constexpr uint32_t TMEM_COLS = 2 * G2_BLOCK_N;  // two accumulator stages
   constexpr uint32_t IDESC = make_idesc_f16(G2_BLOCK_M, G2_BLOCK_N, A_MN, B_MN, true);
   constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // MODE_AG_GEMM: the trailing clusters of the grid are puller CTAs (all-gather of the peer shards into the local
+  // gathered buffer with bulk async copies over NVLink, one flag per 128-row chunk); they never join the GEMM
+  int num_pairs = gridDim.x >> 1;
+  if constexpr (MODE == MODE_AG_GEMM) {
+    num_pairs = ((int)gridDim.x - p.comm.num_comm_ctas) >> 1;
+    if ((int)blockIdx.x >= 2 * num_pairs) {
+      ag_puller(p.comm, smem, (int)blockIdx.x - 2 * num_pairs);
+      return;
+    }
+  }
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + G2_BAR_OFFSET);
   uint64_t* empty_bar = full_bar + G2_STAGES;
   uint64_t* tmem_full_bar = empty_bar + G2_STAGES;
@@ -93,10 +109,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int num_k = (p.K + GEMM_BLOCK_K - 1) / GEMM_BLOCK_K;
   const int total_tiles = num_m * num_n;
   const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
   constexpr int GROUP_M = 8;
 
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
+    if constexpr (MODE != MODE_PLAIN) {
+      // fused modes: one 256-row block at a time, starting with the rows that are available first (own shard)
+      m_blk = tile / num_n + (p.comm.m_rotate_blocks >> 1);
+      if (m_blk >= num_m) m_blk -= num_m;
+      n_blk = tile % num_n;
+      return;
+    }
     const int per_group = GROUP_M * num_n;
     const int group = tile / per_group;
     const int first_m = group * GROUP_M;
@@ -117,6 +139,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
+        if constexpr (MODE == MODE_AG_GEMM) {
+          spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), p.comm.epoch, p.comm.pad_local);
+          fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
+        }
         for (int kb = 0; kb < num_k; ++kb) {
           const unsigned long long t0 = dbg ? g2_clock() : 0;
           mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -190,6 +216,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     int acc = 0;
     uint32_t acc_phase = 0;
     unsigned long long w_tf = 0, t_begin = dbg ? g2_clock() : 0;
+    uint32_t free_checked = 0;   // RS: destinations whose receive slot is known to be reusable
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
@@ -202,6 +229,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const bool row_ok = row < p.M;
       uint8_t* crow = reinterpret_cast<uint8_t*>(p.C) + (size_t)(row_ok ? row : 0) * p.ldc * OUT_ELEM;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + acc * G2_BLOCK_N;
+      int rs_dst = 0;
+      if constexpr (MODE == MODE_GEMM_RS) {
+        rs_dst = (m_blk * G2_BLOCK_M) / p.comm.rs_rows_per_rank;
+        if (!((free_checked >> rs_dst) & 1u)) {
+          // the receive slot of this parity on `rs_dst` was last used two calls ago: wait until it was reduced there
+          if (rs_dst != p.comm.rank)
+            spin_until_ge(p.comm.pad_local + PAD_RS_FREE + rs_dst, p.comm.epoch - 2, p.comm.pad_local);
+          free_checked |= (1u << rs_dst);
+        }
+      }
       if constexpr (EPI != EPI_BF16_ACCUM) {
         // TMEM -> registers -> swizzled smem rows of 128 B -> one TMA store (or fp32 reduce-add) per 32-row x 128-B
         // box: full-line global writes, no read-modify-write traffic through the SM for the wgrad accumulation,
@@ -238,7 +275,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (lane == 0) {
             const int c0 = n0 + c * COLS, c1 = m0 + q * 32;
             if (c0 < p.N && c1 < p.M) {
-              if constexpr (EPI == EPI_F32_ACCUM) tma_reduce_add_2d(&tmC, buf, c0, c1);
+              if constexpr (MODE == MODE_GEMM_RS) tma_store_2d(&rsm.m[rs_dst], buf, c0, c1 - rs_dst * p.comm.rs_rows_per_rank);
+              else if constexpr (EPI == EPI_F32_ACCUM) tma_reduce_add_2d(&tmC, buf, c0, c1);
               else tma_store_2d(&tmC, buf, c0, c1);
             }
             tma_store_commit();
@@ -300,6 +338,21 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread is the only waiter
+      if constexpr (MODE == MODE_GEMM_RS) {
+        // (after the accumulator was handed back) this CTA's half tile is delivered once all four warps' stores have
+        // completed at the destination
+        if (lane == 0) {
+          tma_store_wait<0>();
+          fence_proxy_async_global();
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (q == 0 && lane == 0) {
+          __threadfence_system();
+          int* counter = (rs_dst == p.comm.rank ? p.comm.pad_local : p.comm.pad_peer[rs_dst]) + PAD_RS_ARRIVED +
+                         p.comm.rank;
+          red_add_release_sys(counter, 1);
+        }
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();     // all epilogue stores of this warp have completed
@@ -314,12 +367,58 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tc_fence_after();
     tmem_dealloc<2>(tmem_base, TMEM_COLS);
   }
+
+  if constexpr (MODE == MODE_GEMM_RS) {
+    // ================================ reduce the local chunk (fp32) ================================
+    const GemmComm& c = p.comm;
+    __shared__ int s_last;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < c.world; ++s)
+        spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, c.rs_expected_total, c.pad_local);
+    }
+    __syncthreads();
+    const int vec_per_row = p.N / 8;
+    const long long total_vec = (long long)c.rs_rows_per_rank * vec_per_row;
+    const size_t slot_elems = (size_t)c.rs_rows_per_rank * p.ldc;
+    const __nv_bfloat16* slots = reinterpret_cast<const __nv_bfloat16*>(c.rs_slots);
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c.rs_out);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
+         i += (long long)gridDim.x * blockDim.x) {
+      const long long r = i / vec_per_row;
+      const int v = (int)(i - r * vec_per_row);
+      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int s = 0; s < c.world; ++s) {
+        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(slots + s * slot_elems + r * p.ldc + v * 8));
+        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
+        acc8[0] += f0.x; acc8[1] += f0.y; acc8[2] += f1.x; acc8[3] += f1.y;
+        acc8[4] += f2.x; acc8[5] += f2.y; acc8[6] += f3.x; acc8[7] += f3.y;
+      }
+      uint4 o;
+      o.x = pack_bf16x2(acc8[0], acc8[1]); o.y = pack_bf16x2(acc8[2], acc8[3]);
+      o.z = pack_bf16x2(acc8[4], acc8[5]); o.w = pack_bf16x2(acc8[6], acc8[7]);
+      *reinterpret_cast<uint4*>(out + r * p.ldc + v * 8) = o;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      s_last = (atomicAdd(c.rs_reduce_counter, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+      *c.rs_reduce_counter = 0;
+      __threadfence_system();
+      for (int d = 0; d < c.world; ++d)
+        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, c.epoch);
+    }
+  }
 }
 
-template <bool A_MN, bool B_MN, int EPI>
+template <bool A_MN, bool B_MN, int EPI, int MODE = MODE_PLAIN>
 static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC, const GemmParams& p,
-                   int num_sms, cudaStream_t stream) {
-  auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN, EPI>;
+                   int num_sms, cudaStream_t stream, const RsMaps* rsm = nullptr) {
+  static RsMaps no_maps;
+  if (!rsm) rsm = &no_maps;
+  auto kern = gemm_bf16_2cta_kernel<A_MN, B_MN, EPI, MODE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, G2_SMEM_TOTAL);
@@ -328,9 +427,14 @@ static int launch2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtenso
   }
   const int tiles = ((p.M + G2_BLOCK_M - 1) / G2_BLOCK_M) * ((p.N + G2_BLOCK_N - 1) / G2_BLOCK_N);
   int pairs = num_sms / 2;
+  int extra = 0;
+  if constexpr (MODE == MODE_AG_GEMM) {
+    extra = p.comm.num_comm_ctas;                  // even: whole clusters of pullers
+    pairs = (num_sms - extra) / 2;
+  }
   if (pairs > tiles) pairs = tiles;
   static const int dbg = getenv("MLB200_GEMM2_DEBUG") != nullptr;
-  kern<<<2 * pairs, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, tmC, p, dbg);
+  kern<<<2 * pairs + extra, GEMM_THREADS, G2_SMEM_TOTAL, stream>>>(tmA, tmB, tmC, *rsm, p, dbg);
   return (int)cudaGetLastError();
 }
 
@@ -347,6 +451,63 @@ static int dispatch2_epi(int epi, const CUtensorMap& a, const CUtensorMap& b, co
 }
 
 }  // namespace mlb
+
+// all-gather -> GEMM with the 2-CTA kernel: A = local gathered buffer [world * rows_per_rank, K] (filled by the puller
+// CTAs while the tiles of already-arrived row blocks are computed), C[M, N] = A @ B^T (or A @ B), bf16 out
+extern "C" int mlb_gemm_bf16_2cta_ag(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
+                                     int ldc, int b_mn_major, const mlb::GemmComm* comm, int num_sms,
+                                     cudaStream_t stream) {
+  using namespace mlb;
+  if ((comm->ag_rows_per_rank % G2_BLOCK_M) != 0 || (comm->num_comm_ctas & 1)) return -3;
+  CUtensorMap tmA, tmB, tmC;
+  int r = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, G2_HALF);
+  if (r) return 1000 + r;
+  if (!b_mn_major) r = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, G2_HALF);
+  else r = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BLOCK_K);
+  if (r) return 2000 + r;
+  r = make_tmap_2d_out(&tmC, C, 2, (uint64_t)N, (uint64_t)M, (uint64_t)ldc, 32);
+  if (r) return 3000 + r;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.comm = *comm;
+  if (!b_mn_major) return launch2<false, false, EPI_BF16, MODE_AG_GEMM>(tmA, tmB, tmC, p, num_sms, stream);
+  return launch2<false, true, EPI_BF16, MODE_AG_GEMM>(tmA, tmB, tmC, p, num_sms, stream);
+}
+
+// GEMM -> reduce-scatter with the 2-CTA kernel: partial C[M, N] = A @ B^T (or A @ B); the 256-row blocks that belong
+// to rank d are TMA-stored into this rank's receive slot on d, every rank then reduces its world slots in fp32.
+// Returns the number of half-tile arrivals every source contributes per destination (so the caller can keep the
+// cumulative expected-arrivals counter), or a negative / >= 1000 error code.
+extern "C" int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int lda, int ldb,
+                                     int b_mn_major, mlb::GemmComm* comm, int prev_total, int num_sms,
+                                     cudaStream_t stream) {
+  using namespace mlb;
+  const int m = comm->rs_rows_per_rank;
+  if (m % G2_BLOCK_M != 0 || M != m * comm->world || (N * 2) % 16 != 0) return -3;
+  CUtensorMap tmA, tmB, tmC;
+  int r = make_tmap_2d_bf16(&tmA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, G2_HALF);
+  if (r) return -(1000 + r);
+  if (!b_mn_major) r = make_tmap_2d_bf16(&tmB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, G2_HALF);
+  else r = make_tmap_2d_bf16(&tmB, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, GEMM_BLOCK_K);
+  if (r) return -(2000 + r);
+  RsMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  for (int d = 0; d < comm->world; ++d) {
+    r = make_tmap_2d_out(&maps.m[d], comm->rs_dst[d], 2, (uint64_t)N, (uint64_t)m, (uint64_t)N, 32);
+    if (r) return -(3000 + r);
+  }
+  tmC = maps.m[comm->rank];
+  const int arrivals = (m / G2_HALF) * ((N + G2_BLOCK_N - 1) / G2_BLOCK_N);   // one per CTA per tile
+  comm->rs_expected_total = prev_total + arrivals;
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.C = nullptr; p.M = M; p.N = N; p.K = K; p.ldc = N;
+  p.comm = *comm;
+  int e = b_mn_major ? launch2<false, true, EPI_BF16, MODE_GEMM_RS>(tmA, tmB, tmC, p, num_sms, stream, &maps)
+                     : launch2<false, false, EPI_BF16, MODE_GEMM_RS>(tmA, tmB, tmC, p, num_sms, stream, &maps);
+  return e ? -(4000 + e) : arrivals;
+}
 
 extern "C" int mlb_gemm2_debug_read(unsigned long long* host, int n) {
   return (int)cudaMemcpyFromSymbol(host, mlb::g2_dbg, sizeof(unsigned long long) * n);

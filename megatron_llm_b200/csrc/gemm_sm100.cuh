@@ -67,7 +67,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 constexpr int AG_PIECE_BYTES = 32 * 1024;
 constexpr int AG_STAGES = 6;  // 192 KB of smem in flight per puller CTA
 
-__device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
+static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
   // one thread drives the whole copy pipeline (bulk copies are issued by a single thread anyway)
   if (threadIdx.x != 0) return;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);

@@ -119,13 +119,12 @@ class TPCommunicator:
         rs_slots = self.rs_ptrs[self.rank] + 2 * base
         num_n_256 = None  # tile count is computed with the same heuristic as the kernel launcher
         out = torch.empty((m, N), dtype=torch.bfloat16, device=self.device)
-        tiles_per_dst = (m // 128) * self._num_n_tiles(M, N)
-        self.rs_arrived_total += tiles_per_dst
+        tiles_per_dst = (m // 128) * self._num_n_tiles(M, N)      # arrivals if the 1-CTA kernel is chosen
         x = x2d if (x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0) else x2d.contiguous()
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
-        self.mod.fused_gemm_rs(x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total,
-                               self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
-                               self.rs_epoch, 0)
+        self.rs_arrived_total = self.mod.fused_gemm_rs(
+            x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total, tiles_per_dst,
+            self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch, 0)
         _ext.count()
         return out
 

@@ -16,11 +16,13 @@ def _tp_kernels(rank, world):
     ps.initialize_model_parallel(world, 1)
     dev = torch.device("cuda", rank)
     torch.manual_seed(100 + rank)
-    m, K, N = 256, 512, 768
+    K, N = 512, 768
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), max_rows_per_rank=512, max_k=2048, max_n=2048,
                           num_comm_ctas=4)
     group = ps.get_tensor_model_parallel_group()
-    for it in range(4):
+    # m = 256 takes the 2-CTA (cta_group::2) kernels, m = 128 the 1-CTA ones; alternating them on one communicator
+    # also checks that the arrival / epoch accounting is shared correctly between the two variants
+    for it, m in enumerate((256, 256, 128, 256, 128, 128)):
         # ---- all-gather -> GEMM (W [N,K]) and the transposed-weight form (W [K,N])
         x = torch.randn(m, K, device=dev, dtype=torch.bfloat16)
         torch.manual_seed(7 + it)
