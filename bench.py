@@ -130,6 +130,12 @@ def megatron_argv(a, n_gpus):
     return argv, vocab
 
 
+def _fused_tp_active():
+    from megatron_llm_b200.parallel import fused_tp
+    c = fused_tp.communicator()
+    return c is not None and c.enabled
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -239,6 +245,8 @@ def run_ours(a):
                           "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
                           "parallelism": f"tp{a.gpus}" + ("+sp" if a.gpus > 1 else ""),
                           "cuda_graph_microbatch": bool(getattr(args, "cuda_graph_microbatch", False)),
+                          "tp_comm": ("n/a" if a.gpus == 1 else "fused GEMM+collective kernels over peer memory"
+                                      if _fused_tp_active() else "nccl"),
                           "optimizer": "AdamW fp32 master (in timed region), clip 1.0",
                           "l2": "no flush needed: each step streams >100 GB of weights/grads/optimizer state (>> 126 MB L2)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

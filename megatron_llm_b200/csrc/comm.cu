@@ -98,6 +98,15 @@ __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
 
 }  // namespace mlb
 
+__global__ void set_ints3_kernel(int* dst, int a, int b, int c) {
+  dst[0] = a; dst[1] = b; dst[2] = c;
+}
+
+extern "C" int mlb_set_ints3(int* dst, int a, int b, int c, cudaStream_t stream) {
+  set_ints3_kernel<<<1, 1, 0, stream>>>(dst, a, b, c);
+  return (int)cudaGetLastError();
+}
+
 extern "C" int mlb_dp_reduce(int reduce_scatter, float* local, const long long* peer_ptrs, int* pad_local,
                              const long long* pad_peer_ptrs, long long n, int rank, int world, int epoch,
                              float scale, int num_ctas, cudaStream_t st) {

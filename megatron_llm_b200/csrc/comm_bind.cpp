@@ -17,6 +17,7 @@
 extern "C" {
 int mlb_gemm_bf16_2cta_ag(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                           int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+int mlb_set_ints3(int* dst, int a, int b, int c, cudaStream_t stream);
 int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int b_mn_major,
                           mlb::GemmComm* comm, int prev_total, int num_sms, cudaStream_t stream);
 int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
@@ -58,7 +59,8 @@ static void fill_pads(mlb::GemmComm& c, int64_t pad_local, const std::vector<int
 static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, torch::Tensor& out, bool b_mn,
                           const std::vector<int64_t>& ag_src, int64_t rows_per_rank, torch::Tensor& chunk_flags,
                           torch::Tensor& read_counters, int64_t pad_local, const std::vector<int64_t>& pad_peers,
-                          int64_t rank, int64_t world, int64_t epoch, int64_t num_comm_ctas, int64_t sms) {
+                          int64_t rank, int64_t world, int64_t epoch, int64_t num_comm_ctas, int64_t sms,
+                          int64_t state_ptr) {
   c10::cuda::CUDAGuard guard(gathered.device());
   const int M = gathered.size(0), K = gathered.size(1);
   const int N = b_mn ? weight.size(1) : weight.size(0);
@@ -68,6 +70,7 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
   mlb::GemmComm c;
   memset(&c, 0, sizeof(c));
   c.rank = rank; c.world = world; c.epoch = epoch; c.num_comm_ctas = num_comm_ctas;
+  c.state = reinterpret_cast<const int*>(state_ptr);
   c.m_rotate_blocks = (int)(rank * rows_per_rank / mlb::GEMM_BLOCK_M);
   for (int i = 0; i < world; ++i) c.ag_src[i] = reinterpret_cast<const void*>(ag_src[i]);
   c.ag_dst = gathered.data_ptr();
@@ -95,7 +98,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
                              const std::vector<int64_t>& rs_dst, int64_t rs_slots, int64_t rows_per_rank,
                              int64_t prev_total, int64_t tiles_1cta, torch::Tensor& reduce_counter, int64_t pad_local,
                              const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world, int64_t epoch,
-                             int64_t sms) {
+                             int64_t sms, int64_t state_ptr) {
   c10::cuda::CUDAGuard guard(x.device());
   const int M = x.size(0), K = x.size(1);
   const int N = b_mn ? weight.size(1) : weight.size(0);
@@ -105,6 +108,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
   mlb::GemmComm c;
   memset(&c, 0, sizeof(c));
   c.rank = rank; c.world = world; c.epoch = epoch;
+  c.state = reinterpret_cast<const int*>(state_ptr);
   c.m_rotate_blocks = (int)(((rank + 1) % world) * rows_per_rank / mlb::GEMM_BLOCK_M);  // remote chunks first
   for (int i = 0; i < world; ++i) c.rs_dst[i] = reinterpret_cast<void*>(rs_dst[i]);
   c.rs_slots = reinterpret_cast<const void*>(rs_slots);
@@ -141,7 +145,15 @@ static void dp_reduce(torch::Tensor& local, const std::vector<int64_t>& peer_ptr
                     local.numel(), (int)rank, (int)world, (int)epoch, (float)scale, (int)num_ctas, cur()));
 }
 
+// state[0..2] = {a, b, c} on the current stream (the offsets a replayed graph's fused kernels add to their epochs)
+static void comm_set_state(torch::Tensor& state, int64_t a, int64_t b, int64_t c) {
+  c10::cuda::CUDAGuard guard(state.device());
+  TORCH_CHECK(state.scalar_type() == torch::kInt32 && state.numel() >= 3);
+  CHK(mlb_set_ints3(state.data_ptr<int>(), (int)a, (int)b, (int)c, cur()));
+}
+
 void register_comm(pybind11::module_& m) {
+  m.def("comm_set_state", &comm_set_state);
   m.def("fused_ag_gemm", &fused_ag_gemm);
   m.def("fused_gemm_rs", &fused_gemm_rs);
   m.def("dp_reduce", &dp_reduce);

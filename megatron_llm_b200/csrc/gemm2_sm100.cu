@@ -140,7 +140,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
         if constexpr (MODE == MODE_AG_GEMM) {
-          spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), p.comm.epoch, p.comm.pad_local);
+          spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
           fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
         }
         for (int kb = 0; kb < num_k; ++kb) {
@@ -235,7 +235,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         if (!((free_checked >> rs_dst) & 1u)) {
           // the receive slot of this parity on `rs_dst` was last used two calls ago: wait until it was reduced there
           if (rs_dst != p.comm.rank)
-            spin_until_ge(p.comm.pad_local + PAD_RS_FREE + rs_dst, p.comm.epoch - 2, p.comm.pad_local);
+            spin_until_ge(p.comm.pad_local + PAD_RS_FREE + rs_dst, comm_epoch(p.comm, STATE_RS_EPOCH) - 2, p.comm.pad_local);
           free_checked |= (1u << rs_dst);
         }
       }
@@ -374,7 +374,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     __shared__ int s_last;
     if (threadIdx.x == 0) {
       for (int s = 0; s < c.world; ++s)
-        spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, c.rs_expected_total, c.pad_local);
+        spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, comm_rs_expected(c), c.pad_local);
     }
     __syncthreads();
     const int vec_per_row = p.N / 8;
@@ -408,7 +408,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       *c.rs_reduce_counter = 0;
       __threadfence_system();
       for (int d = 0; d < c.world; ++d)
-        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, c.epoch);
+        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, comm_epoch(c, STATE_RS_EPOCH));
     }
   }
 }

@@ -67,6 +67,15 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 constexpr int AG_PIECE_BYTES = 32 * 1024;
 constexpr int AG_STAGES = 6;  // 192 KB of smem in flight per puller CTA
 
+// live epoch / arrival target of this call = launch argument + device-resident offset (see GemmComm::state)
+enum CommStateSlot : int { STATE_AG_EPOCH = 0, STATE_RS_EPOCH = 1, STATE_RS_TOTAL = 2 };
+__device__ __forceinline__ int comm_epoch(const GemmComm& c, int slot) {
+  return c.epoch + (c.state ? *reinterpret_cast<const volatile int*>(c.state + slot) : 0);
+}
+__device__ __forceinline__ int comm_rs_expected(const GemmComm& c) {
+  return c.rs_expected_total + (c.state ? *reinterpret_cast<const volatile int*>(c.state + STATE_RS_TOTAL) : 0);
+}
+
 static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
   // one thread drives the whole copy pipeline (bulk copies are issued by a single thread anyway)
   if (threadIdx.x != 0) return;
@@ -85,7 +94,7 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
     // my shard was written by earlier stream-ordered work: publish it to every peer
     __threadfence_system();
     for (int p = 0; p < c.world; ++p)
-      if (p != c.rank) st_release_sys(c.pad_peer[p] + PAD_AG_READY + c.rank, c.epoch);
+      if (p != c.rank) st_release_sys(c.pad_peer[p] + PAD_AG_READY + c.rank, comm_epoch(c, STATE_AG_EPOCH));
   }
 
   for (int i = 0; i < c.world; ++i) {
@@ -95,7 +104,7 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
       const int g = i * chunks_per_rank + j;
       if (g % c.num_comm_ctas != comm_id) continue;
       if (!waited && p != c.rank) {
-        spin_until_ge(c.pad_local + PAD_AG_READY + p, c.epoch, c.pad_local);
+        spin_until_ge(c.pad_local + PAD_AG_READY + p, comm_epoch(c, STATE_AG_EPOCH), c.pad_local);
         fence_proxy_async_global();
         waited = true;
       }
@@ -130,7 +139,7 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
       tma_store_wait<0>();          // all bytes of the chunk are in local HBM
       fence_proxy_async_global();
       __threadfence();
-      st_release_sys(c.ag_chunk_flags + p * chunks_per_rank + j, c.epoch);
+      st_release_sys(c.ag_chunk_flags + p * chunks_per_rank + j, comm_epoch(c, STATE_AG_EPOCH));
     }
     if (p != c.rank) {
       // tell the owner when ALL of this rank's pullers are done with its shard
@@ -139,14 +148,14 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
       if (done == c.num_comm_ctas) {
         c.ag_read_counters[p] = 0;
         __threadfence_system();
-        st_release_sys(c.pad_peer[p] + PAD_AG_ACK + c.rank, c.epoch);
+        st_release_sys(c.pad_peer[p] + PAD_AG_ACK + c.rank, comm_epoch(c, STATE_AG_EPOCH));
       }
     }
   }
   if (comm_id == 0) {
     // my published shard may be overwritten by the next call only once every peer has read it
     for (int p = 0; p < c.world; ++p)
-      if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, c.epoch, c.pad_local);
+      if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, comm_epoch(c, STATE_AG_EPOCH), c.pad_local);
   }
 }
 
@@ -240,7 +249,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
         if constexpr (MODE == MODE_AG_GEMM) {
-          spin_until_ge(p.comm.ag_chunk_flags + m_blk, p.comm.epoch, p.comm.pad_local);
+          spin_until_ge(p.comm.ag_chunk_flags + m_blk, comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
           fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
         }
         for (int kb = 0; kb < num_k; ++kb) {
@@ -321,7 +330,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         dst = m0 / p.comm.rs_rows_per_rank;
         if (!((free_checked >> dst) & 1u)) {
           // the receive slot of this parity on `dst` was last used two calls ago: wait until dst reduced it
-          if (dst != p.comm.rank) spin_until_ge(p.comm.pad_local + PAD_RS_FREE + dst, p.comm.epoch - 2, p.comm.pad_local);
+          if (dst != p.comm.rank) spin_until_ge(p.comm.pad_local + PAD_RS_FREE + dst, comm_epoch(p.comm, STATE_RS_EPOCH) - 2, p.comm.pad_local);
           free_checked |= (1u << dst);
         }
         const int lr = (row_ok ? row : m0) - dst * p.comm.rs_rows_per_rank;
@@ -406,7 +415,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const GemmComm& c = p.comm;
     __shared__ int s_last;
     if (threadIdx.x == 0) {
-      for (int s = 0; s < c.world; ++s) spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, c.rs_expected_total, c.pad_local);
+      for (int s = 0; s < c.world; ++s) spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, comm_rs_expected(c), c.pad_local);
     }
     __syncthreads();
     const int vec_per_row = p.N / 8;
@@ -441,7 +450,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       *c.rs_reduce_counter = 0;
       __threadfence_system();
       for (int d = 0; d < c.world; ++d)
-        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, c.epoch);
+        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, comm_epoch(c, STATE_RS_EPOCH));
     }
   }
 }

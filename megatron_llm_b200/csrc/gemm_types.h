@@ -46,6 +46,10 @@ struct GemmComm {
   int rs_rows_per_rank;
   int rs_expected_total;               // cumulative tiles every source will have delivered after this call
   int* rs_reduce_counter;              // local: CTAs that finished the reduction (last one frees the slot)
+  // ---- device-resident offsets added to `epoch` / `rs_expected_total` (nullptr = 0).  A kernel node of a replayed
+  //      CUDA graph keeps the arguments of its capture; the host writes {ag epoch, rs epoch, rs arrivals} deltas here
+  //      before every replay so the captured calls continue the live sequence.
+  const int* state;
   // ---- signal pads
   int* pad_local;
   int* pad_peer[GEMM_MAX_PEERS];

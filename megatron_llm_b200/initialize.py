@@ -95,10 +95,8 @@ def _bind_symmetric_communicators():
         return
     try:
         from .parallel import symm
-        # (the fused kernels take per-call epoch arguments from the host, which a replayed CUDA graph cannot update)
         want = os.environ.get("MLB200_FUSED_TP", "1" if getattr(args, "fused_tp_comm", False) else "0") == "1"
-        if want and ps.get_tensor_model_parallel_world_size() > 1 \
-                and not getattr(args, "cuda_graph_microbatch", False):
+        if want and ps.get_tensor_model_parallel_world_size() > 1:
             symm.bind_tp_communicator(args)
     except Exception as e:  # never fatal: the NCCL path is the checked fallback
         if args.rank == 0:

@@ -169,6 +169,7 @@ class GraphedMicrobatch:
         self.static_batch = None
         self.static_reduced = None
         self.launches = 0
+        self.comm = None
 
     def _eager(self, batch, n_microbatches):
         output, loss_func = self.parts.run(batch, self.model)
@@ -189,14 +190,22 @@ class GraphedMicrobatch:
             self.static_batch = [b.clone() if torch.is_tensor(b) else b for b in batch]
             self.graph = torch.cuda.CUDAGraph()
             before = _ext.LAUNCHES
+            from . import fused_tp
+            self.comm = fused_tp.communicator()
+            if self.comm is not None:
+                self.comm_before = self.comm.counters()
             with torch.cuda.graph(self.graph, stream=torch.cuda.current_stream(), capture_error_mode="thread_local"):
                 self.static_reduced = self._eager(self.static_batch, n_microbatches)
+            if self.comm is not None:
+                self.comm_advance = self.comm.end_capture(self.comm_before)
             self.launches = _ext.LAUNCHES - before
             torch.cuda.synchronize()
             # the capture pass itself does not execute: fall through and replay for this micro-batch
         for dst, src in zip(self.static_batch, batch):
             if torch.is_tensor(dst):
                 dst.copy_(src, non_blocking=True)
+        if self.comm is not None:   # fused TP kernels: re-base the captured epochs onto the live sequence
+            self.comm.begin_replay(self.comm_before, self.comm_advance)
         self.graph.replay()
         _ext.count(self.launches)
         return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self.static_reduced.items()}

@@ -73,6 +73,8 @@ class TPCommunicator:
         self.ag_epoch = 0
         self.rs_epoch = 0
         self.rs_arrived_total = 0
+        # offsets that calls captured in a CUDA graph add to their (frozen) epoch arguments -- see replay_offsets()
+        self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
         dist.barrier(group=group)
         self.enabled = True
@@ -100,7 +102,7 @@ class TPCommunicator:
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
         self.mod.fused_ag_gemm(gathered, w, out, transposed_weight, self.xs_ptrs, m, self.chunk_flags,
                                self.read_counters, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
-                               self.ag_epoch, self.num_comm_ctas, 0)
+                               self.ag_epoch, self.num_comm_ctas, 0, self._state_ptr())
         _ext.count()
         return out, gathered.view(self.world * lead[0], *lead[1:], K)
 
@@ -124,9 +126,40 @@ class TPCommunicator:
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
         self.rs_arrived_total = self.mod.fused_gemm_rs(
             x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total, tiles_per_dst,
-            self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch, 0)
+            self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch, 0,
+            self._state_ptr())
         _ext.count()
         return out
+
+    # ------------------------------------------------------------------- CUDA-graph support
+    # Epochs / arrival targets are host-side counters passed as kernel arguments.  Calls issued while a stream is
+    # capturing keep the values of the capture pass forever, so they additionally read an offset from ``self.state``
+    # (device memory); eager calls pass no state pointer and use their arguments as they are.
+    def _state_ptr(self) -> int:
+        return self.state.data_ptr() if torch.cuda.is_current_stream_capturing() else 0
+
+    def counters(self):
+        return (self.ag_epoch, self.rs_epoch, self.rs_arrived_total)
+
+    def end_capture(self, before):
+        """Called right after a capture pass that started at ``counters() == before``: the captured calls did not
+        run, so rewind, and return what one replay advances the counters by."""
+        adv = tuple(now - b for now, b in zip(self.counters(), before))
+        self.ag_epoch, self.rs_epoch, self.rs_arrived_total = before
+        return adv
+
+    def begin_replay(self, before, advance):
+        """Enqueue the offset update that makes a replay of a graph captured at ``before`` continue the live
+        sequence, and advance the host counters past it.  (The receive-slot parity of a captured reduce-scatter is
+        frozen too, so the rs epoch offset is kept even by skipping one epoch number when needed -- the slot-free
+        handshake only needs monotonic epochs.)"""
+        if (self.rs_epoch - before[1]) % 2:
+            self.rs_epoch += 1
+        self.mod.comm_set_state(self.state, self.ag_epoch - before[0], self.rs_epoch - before[1],
+                                self.rs_arrived_total - before[2])
+        self.ag_epoch += advance[0]
+        self.rs_epoch += advance[1]
+        self.rs_arrived_total += advance[2]
 
     def _num_n_tiles(self, M: int, N: int) -> int:
         """Mirror of ``pick_block_n`` in csrc/gemm_sm100.cu (the arrival counters count output tiles)."""

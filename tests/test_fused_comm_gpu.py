@@ -59,6 +59,61 @@ def test_fused_tp_kernels_match_nccl():
     run_distributed(_tp_kernels, 2, backend="nccl")
 
 
+def _tp_kernels_in_graph(rank, world):
+    """The fused kernels captured in a CUDA graph: every replay must continue the live epoch sequence, also when eager
+    calls run in between (which flips the receive-slot parity the captured reduce-scatter was recorded with)."""
+    from megatron_llm_b200.parallel import state as ps
+    from megatron_llm_b200.parallel.symm import TPCommunicator
+    ps.initialize_model_parallel(world, 1)
+    dev = torch.device("cuda", rank)
+    group = ps.get_tensor_model_parallel_group()
+    m, K, N = 256, 512, 768
+    comm = TPCommunicator(group, max_rows_per_rank=512, max_k=2048, max_n=2048, num_comm_ctas=4)
+    torch.manual_seed(5)
+    w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.05
+    x = torch.randn(m, K, device=dev, dtype=torch.bfloat16)
+    a = torch.randn(world * m, K, device=dev, dtype=torch.bfloat16)
+    stream = torch.cuda.Stream()
+    stream.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(stream):
+        for _ in range(3):                      # eager calls first: the capture starts from non-zero counters
+            comm.ag_gemm(x, w, False)
+            comm.gemm_rs(a, w, False)
+        torch.cuda.synchronize()
+        before = comm.counters()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+            out, gathered = comm.ag_gemm(x, w, False)
+            got = comm.gemm_rs(a, w, False)     # one reduce-scatter per replay: odd epoch advance
+        advance = comm.end_capture(before)
+        assert advance[0] == 1 and advance[1] == 1 and advance[2] > 0
+        for it in range(6):
+            torch.manual_seed(1000 * it + rank)
+            x.copy_(torch.randn(m, K, device=dev, dtype=torch.bfloat16))
+            a.copy_(torch.randn(world * m, K, device=dev, dtype=torch.bfloat16))
+            comm.begin_replay(before, advance)
+            graph.replay()
+            torch.cuda.synchronize()
+            full = torch.empty(world * m, K, device=dev, dtype=torch.bfloat16)
+            dist.all_gather_into_tensor(full, x, group=group)
+            assert torch.equal(gathered, full), f"replay {it}: gathered mismatch"
+            ref = full.float() @ w.float().t()
+            assert (out.float() - ref).abs().max() <= 2e-2 * ref.abs().max(), f"replay {it}: ag_gemm"
+            refs = torch.empty(m, N, device=dev, dtype=torch.float32)
+            dist.reduce_scatter_tensor(refs, a.float() @ w.float().t(), group=group)
+            assert (got.float() - refs).abs().max() <= 3e-2 * refs.abs().max(), f"replay {it}: gemm_rs"
+            if it % 3 == 1:                     # an eager call between two replays
+                e = comm.gemm_rs(a, w, False)
+                torch.cuda.synchronize()
+                assert (e.float() - refs).abs().max() <= 3e-2 * refs.abs().max(), f"eager after replay {it}"
+    assert comm.error_flag() == 0, "a spin-wait timed out"
+    ps.destroy_model_parallel()
+
+
+def test_fused_tp_kernels_replay_in_cuda_graph():
+    run_distributed(_tp_kernels_in_graph, 2, backend="nccl")
+
+
 def _dp_reduce(rank, world):
     from megatron_llm_b200.parallel import state as ps
     from megatron_llm_b200.parallel.symm import DPCommunicator
