@@ -98,6 +98,35 @@ __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
 
 }  // namespace mlb
 
+// dst1[i] = dst2[i] = src[i] (16-byte vectors): publishes a shard to the symmetric buffer and places it into the local
+// gathered buffer with one read
+__global__ void __launch_bounds__(256) copy2_kernel(const uint4* __restrict__ src, uint4* __restrict__ d1,
+                                                    uint4* __restrict__ d2, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < n; i0 += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n) v[u] = __ldcs(src + i);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < n) { d1[i] = v[u]; d2[i] = v[u]; }
+    }
+  }
+}
+
+extern "C" int mlb_copy2(const void* src, void* d1, void* d2, long long bytes, int num_sms, cudaStream_t stream) {
+  const long long n = bytes / 16;
+  long long want = (n + 256 * 4 - 1) / (256 * 4);
+  int grid = (int)(want < 1 ? 1 : (want > 4LL * num_sms ? 4LL * num_sms : want));
+  copy2_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(d1),
+                                         reinterpret_cast<uint4*>(d2), n);
+  return (int)cudaGetLastError();
+}
+
 __global__ void set_ints3_kernel(int* dst, int a, int b, int c) {
   dst[0] = a; dst[1] = b; dst[2] = c;
 }

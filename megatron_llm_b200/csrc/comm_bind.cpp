@@ -1,5 +1,6 @@
 // Bindings for the fused GEMM + collective kernels (gemm_sm100.cuh MODE_AG_GEMM / MODE_GEMM_RS) and the
 // peer-memory data-parallel gradient reduction (comm.cu).
+#include <algorithm>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 #include <torch/extension.h>
@@ -17,6 +18,7 @@
 extern "C" {
 int mlb_gemm_bf16_2cta_ag(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                           int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+int mlb_copy2(const void* src, void* d1, void* d2, long long bytes, int num_sms, cudaStream_t stream);
 int mlb_set_ints3(int* dst, int a, int b, int c, cudaStream_t stream);
 int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int b_mn_major,
                           mlb::GemmComm* comm, int prev_total, int num_sms, cudaStream_t stream);
@@ -54,6 +56,36 @@ static void fill_pads(mlb::GemmComm& c, int64_t pad_local, const std::vector<int
     c.pad_peer[i] = reinterpret_cast<int*>(pad_peers[i]);
 }
 
+// Tile-group height of the 2-CTA fused kernels (256-row blocks).  A group shares every B panel, so a tall group cuts
+// the B traffic; but its first tiles need all of its rows, so it should not reach past the rows that are available
+// first (one rank's shard) unless B is too large to be re-read from L2 for every shard.
+static int pick_group_blocks(int64_t rows_per_rank, int64_t b_bytes) {
+  const int per_rank = (int)(rows_per_rank / 256);
+  if (b_bytes > (24LL << 20) || per_rank >= 4) return 4;
+  return per_rank >= 2 ? 2 : 1;
+}
+
+// Number of puller CTAs for all-gather -> GEMM.  Every puller moves ~PULL_GBPS (one thread, 5 x 32 KB bulk copies in
+// flight over an NVLink round trip) and costs the GEMM one SM, so small GEMMs behind a big gather want many pullers
+// and big GEMMs few: minimise  max(gemm(c), pull(c) + one tile group of gemm(c))  over even c <= max_ctas.
+static int pick_comm_ctas(int64_t M, int64_t N, int64_t K, int64_t rows_per_rank, int world, int max_ctas, int sms) {
+  static const char* fixed = getenv("MLB200_AG_CTAS_FIXED");
+  if (fixed) return std::min(max_ctas, atoi(fixed));
+  constexpr double PULL_GBPS = 37.0, GEMM_TFLOPS = 1350.0;
+  const double chunk_us = 128.0 * K * 2 / (PULL_GBPS * 1e3);
+  const int remote_chunks = (int)((world - 1) * rows_per_rank / 128);
+  const int groups = std::max<int>(1, (int)(M / 256 / pick_group_blocks(rows_per_rank, N * K * 2)));
+  int best = 2;
+  double best_t = 1e30;
+  for (int c = 2; c <= max_ctas; c += 2) {
+    const double gemm_us = 2.0 * M * N * K / (GEMM_TFLOPS * 1e6) * sms / (double)(sms - c) + 4.0;
+    const double pull_us = ((remote_chunks + c - 1) / c) * chunk_us;
+    const double t = std::max(gemm_us, pull_us + gemm_us / groups);
+    if (t < best_t * 0.995) { best_t = t; best = c; }
+  }
+  return best;
+}
+
 // out[M, N] = all_gather(shards)[M, K] @ W^T (b_mn=false, W [N, K]) or @ W (b_mn=true, W [K, N]).
 // `gathered` is the local [M, K] buffer the puller CTAs fill from the peers' published shards `ag_src`.
 static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, torch::Tensor& out, bool b_mn,
@@ -69,7 +101,10 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
   TORCH_CHECK(K % 8 == 0 && N % 8 == 0);
   mlb::GemmComm c;
   memset(&c, 0, sizeof(c));
-  c.rank = rank; c.world = world; c.epoch = epoch; c.num_comm_ctas = num_comm_ctas;
+  c.rank = rank; c.world = world; c.epoch = epoch;
+  c.num_comm_ctas = pick_comm_ctas(M, N, K, rows_per_rank, (int)world, (int)num_comm_ctas, sms > 0 ? (int)sms : sm_count());
+  num_comm_ctas = c.num_comm_ctas;
+  c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
   c.state = reinterpret_cast<const int*>(state_ptr);
   c.m_rotate_blocks = (int)(rank * rows_per_rank / mlb::GEMM_BLOCK_M);
   for (int i = 0; i < world; ++i) c.ag_src[i] = reinterpret_cast<const void*>(ag_src[i]);
@@ -110,6 +145,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
   c.rank = rank; c.world = world; c.epoch = epoch;
   c.state = reinterpret_cast<const int*>(state_ptr);
   c.m_rotate_blocks = (int)(((rank + 1) % world) * rows_per_rank / mlb::GEMM_BLOCK_M);  // remote chunks first
+  c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
   for (int i = 0; i < world; ++i) c.rs_dst[i] = reinterpret_cast<void*>(rs_dst[i]);
   c.rs_slots = reinterpret_cast<const void*>(rs_slots);
   c.rs_out = rs_out.data_ptr();
@@ -152,7 +188,19 @@ static void comm_set_state(torch::Tensor& state, int64_t a, int64_t b, int64_t c
   CHK(mlb_set_ints3(state.data_ptr<int>(), (int)a, (int)b, (int)c, cur()));
 }
 
+// d1[:] = d2[:] = src[:] (contiguous, same byte size, a multiple of 16 bytes)
+static void comm_copy2(const torch::Tensor& src, torch::Tensor& d1, torch::Tensor& d2) {
+  c10::cuda::CUDAGuard guard(src.device());
+  const long long bytes = (long long)src.numel() * src.element_size();
+  TORCH_CHECK(src.is_contiguous() && d1.is_contiguous() && d2.is_contiguous());
+  TORCH_CHECK((long long)d1.numel() * d1.element_size() == bytes && (long long)d2.numel() * d2.element_size() == bytes);
+  TORCH_CHECK(bytes % 16 == 0 && (uintptr_t)src.data_ptr() % 16 == 0 && (uintptr_t)d1.data_ptr() % 16 == 0 &&
+              (uintptr_t)d2.data_ptr() % 16 == 0);
+  CHK(mlb_copy2(src.data_ptr(), d1.data_ptr(), d2.data_ptr(), bytes, sm_count(), cur()));
+}
+
 void register_comm(pybind11::module_& m) {
+  m.def("comm_copy2", &comm_copy2);
   m.def("comm_set_state", &comm_set_state);
   m.def("fused_ag_gemm", &fused_ag_gemm);
   m.def("fused_gemm_rs", &fused_gemm_rs);

@@ -113,10 +113,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 
   auto tile_coords = [&](int tile, int& m_blk, int& n_blk) {
     if constexpr (MODE != MODE_PLAIN) {
-      // fused modes: one 256-row block at a time, starting with the rows that are available first (own shard)
-      m_blk = tile / num_n + (p.comm.m_rotate_blocks >> 1);
+      // fused modes: groups of (up to) 4 row blocks in the order their data becomes available -- all-gather: own shard
+      // first; reduce-scatter: the next rank's rows first, own rows last -- n-major inside a group so that a B
+      // panel is reused by the whole group while it is hot in L2
+      int G = p.comm.m_group_blocks;
+      if (G <= 0 || num_m % G != 0) G = (num_m % 4 == 0) ? 4 : ((num_m % 2 == 0) ? 2 : 1);
+      const int per_group = G * num_n;
+      const int group = tile / per_group, in_group = tile - group * per_group;
+      m_blk = group * G + in_group % G + (p.comm.m_rotate_blocks >> 1);
       if (m_blk >= num_m) m_blk -= num_m;
-      n_blk = tile % num_n;
+      n_blk = in_group / G;
       return;
     }
     const int per_group = GROUP_M * num_n;
@@ -140,8 +146,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
         if constexpr (MODE == MODE_AG_GEMM) {
-          spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
-          fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
+          if (m0 / p.comm.ag_rows_per_rank != p.comm.rank) {   // (the own shard was placed before the launch)
+            spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
+            fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
+          }
         }
         for (int kb = 0; kb < num_k; ++kb) {
           const unsigned long long t0 = dbg ? g2_clock() : 0;
@@ -368,49 +376,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     tmem_dealloc<2>(tmem_base, TMEM_COLS);
   }
 
-  if constexpr (MODE == MODE_GEMM_RS) {
-    // ================================ reduce the local chunk (fp32) ================================
-    const GemmComm& c = p.comm;
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-      for (int s = 0; s < c.world; ++s)
-        spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, comm_rs_expected(c), c.pad_local);
-    }
-    __syncthreads();
-    const int vec_per_row = p.N / 8;
-    const long long total_vec = (long long)c.rs_rows_per_rank * vec_per_row;
-    const size_t slot_elems = (size_t)c.rs_rows_per_rank * p.ldc;
-    const __nv_bfloat16* slots = reinterpret_cast<const __nv_bfloat16*>(c.rs_slots);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c.rs_out);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-         i += (long long)gridDim.x * blockDim.x) {
-      const long long r = i / vec_per_row;
-      const int v = (int)(i - r * vec_per_row);
-      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int s = 0; s < c.world; ++s) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(slots + s * slot_elems + r * p.ldc + v * 8));
-        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-        acc8[0] += f0.x; acc8[1] += f0.y; acc8[2] += f1.x; acc8[3] += f1.y;
-        acc8[4] += f2.x; acc8[5] += f2.y; acc8[6] += f3.x; acc8[7] += f3.y;
-      }
-      uint4 o;
-      o.x = pack_bf16x2(acc8[0], acc8[1]); o.y = pack_bf16x2(acc8[2], acc8[3]);
-      o.z = pack_bf16x2(acc8[4], acc8[5]); o.w = pack_bf16x2(acc8[6], acc8[7]);
-      *reinterpret_cast<uint4*>(out + r * p.ldc + v * 8) = o;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      s_last = (atomicAdd(c.rs_reduce_counter, 1) == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-      *c.rs_reduce_counter = 0;
-      __threadfence_system();
-      for (int d = 0; d < c.world; ++d)
-        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, comm_epoch(c, STATE_RS_EPOCH));
-    }
-  }
+  if constexpr (MODE == MODE_GEMM_RS) rs_reduce_phase(p);
 }
 
 template <bool A_MN, bool B_MN, int EPI, int MODE = MODE_PLAIN>

@@ -97,11 +97,12 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
       if (p != c.rank) st_release_sys(c.pad_peer[p] + PAD_AG_READY + c.rank, comm_epoch(c, STATE_AG_EPOCH));
   }
 
-  for (int i = 0; i < c.world; ++i) {
+  // (the own shard is placed into ag_dst by the host-side copy that also publishes it)
+  for (int i = 1; i < c.world; ++i) {
     const int p = (c.rank + i) % c.world;
     bool waited = false;
     for (int j = 0; j < chunks_per_rank; ++j) {
-      const int g = i * chunks_per_rank + j;
+      const int g = (i - 1) * chunks_per_rank + j;
       if (g % c.num_comm_ctas != comm_id) continue;
       if (!waited && p != c.rank) {
         spin_until_ge(c.pad_local + PAD_AG_READY + p, comm_epoch(c, STATE_AG_EPOCH), c.pad_local);
@@ -156,6 +157,79 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
     // my published shard may be overwritten by the next call only once every peer has read it
     for (int p = 0; p < c.world; ++p)
       if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, comm_epoch(c, STATE_AG_EPOCH), c.pad_local);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// reduce-scatter tail (all CTAs of the grid, after the GEMM part): wait until every source delivered its tiles, sum the
+// world receive slots in fp32 into the output rows, and hand the slot back to the senders
+// ------------------------------------------------------------------------------------------------
+static __device__ void rs_reduce_phase(const GemmParams& p) {
+  const GemmComm& c = p.comm;
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    const int expected = comm_rs_expected(c);
+    for (int s = 0; s < c.world; ++s) spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, expected, c.pad_local);
+  }
+  __syncthreads();
+  // rows are contiguous (ldc == N): treat the slot as a flat array of 16-byte vectors.  Four vectors x two slots are
+  // loaded before the first add, so every thread keeps 8 independent 16-byte loads in flight (HBM latency bound
+  // otherwise: this phase is pure streaming of world+1 x [rows, N] bf16)
+  const long long total_vec = (long long)c.rs_rows_per_rank * p.N / 8;
+  const long long slot_vec = (long long)c.rs_rows_per_rank * p.ldc / 8;
+  const uint4* slots = reinterpret_cast<const uint4*>(c.rs_slots);
+  uint4* out = reinterpret_cast<uint4*>(c.rs_out);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 4;
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total_vec; i0 += U * stride) {
+    float acc[U][8];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[u][e] = 0.f;
+    for (int s = 0; s < c.world; s += 2) {
+      uint4 v[2][U];
+      const bool two = s + 1 < c.world;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        v[0][u] = i < total_vec ? __ldcg(slots + s * slot_vec + i) : make_uint4(0, 0, 0, 0);
+        v[1][u] = (two && i < total_vec) ? __ldcg(slots + (s + 1) * slot_vec + i) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const float2 f0 = unpack_bf16x2(v[h][u].x), f1 = unpack_bf16x2(v[h][u].y), f2 = unpack_bf16x2(v[h][u].z),
+                       f3 = unpack_bf16x2(v[h][u].w);
+          acc[u][0] += f0.x; acc[u][1] += f0.y; acc[u][2] += f1.x; acc[u][3] += f1.y;
+          acc[u][4] += f2.x; acc[u][5] += f2.y; acc[u][6] += f3.x; acc[u][7] += f3.y;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < total_vec) {
+        uint4 o;
+        o.x = pack_bf16x2(acc[u][0], acc[u][1]); o.y = pack_bf16x2(acc[u][2], acc[u][3]);
+        o.z = pack_bf16x2(acc[u][4], acc[u][5]); o.w = pack_bf16x2(acc[u][6], acc[u][7]);
+        out[i] = o;
+      }
+    }
+  }
+  // last CTA out tells every peer that this rank's receive slot (this parity) is free again
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = (atomicAdd(c.rs_reduce_counter, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    *c.rs_reduce_counter = 0;
+    __threadfence_system();
+    const int epoch = comm_epoch(c, STATE_RS_EPOCH);
+    for (int d = 0; d < c.world; ++d)
+      if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, epoch);
   }
 }
 
@@ -249,7 +323,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
         if constexpr (MODE == MODE_AG_GEMM) {
-          spin_until_ge(p.comm.ag_chunk_flags + m_blk, comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
+          if (m0 / p.comm.ag_rows_per_rank != p.comm.rank)     // (the own shard was placed before the launch)
+            spin_until_ge(p.comm.ag_chunk_flags + m_blk, comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
           fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
         }
         for (int kb = 0; kb < num_k; ++kb) {
@@ -410,49 +485,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     tmem_dealloc<1>(tmem_base, TMEM_COLS);
   }
 
-  if constexpr (MODE == MODE_GEMM_RS) {
-    // ================================ reduce the local chunk ================================
-    const GemmComm& c = p.comm;
-    __shared__ int s_last;
-    if (threadIdx.x == 0) {
-      for (int s = 0; s < c.world; ++s) spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, comm_rs_expected(c), c.pad_local);
-    }
-    __syncthreads();
-    const int vec_per_row = p.N / 8;
-    const long long total_vec = (long long)c.rs_rows_per_rank * vec_per_row;
-    const size_t slot_elems = (size_t)c.rs_rows_per_rank * p.ldc;
-    const __nv_bfloat16* slots = reinterpret_cast<const __nv_bfloat16*>(c.rs_slots);
-    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(c.rs_out);
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total_vec;
-         i += (long long)gridDim.x * blockDim.x) {
-      const long long r = i / vec_per_row;
-      const int v = (int)(i - r * vec_per_row);
-      float acc8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int s = 0; s < c.world; ++s) {
-        const uint4 u = __ldcg(reinterpret_cast<const uint4*>(slots + s * slot_elems + r * p.ldc + v * 8));
-        const float2 f0 = unpack_bf16x2(u.x), f1 = unpack_bf16x2(u.y), f2 = unpack_bf16x2(u.z), f3 = unpack_bf16x2(u.w);
-        acc8[0] += f0.x; acc8[1] += f0.y; acc8[2] += f1.x; acc8[3] += f1.y;
-        acc8[4] += f2.x; acc8[5] += f2.y; acc8[6] += f3.x; acc8[7] += f3.y;
-      }
-      uint4 o;
-      o.x = pack_bf16x2(acc8[0], acc8[1]); o.y = pack_bf16x2(acc8[2], acc8[3]);
-      o.z = pack_bf16x2(acc8[4], acc8[5]); o.w = pack_bf16x2(acc8[6], acc8[7]);
-      *reinterpret_cast<uint4*>(out + r * p.ldc + v * 8) = o;
-    }
-    // last CTA out tells every peer that this rank's receive slot (this parity) is free again
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      __threadfence();
-      s_last = (atomicAdd(c.rs_reduce_counter, 1) == (int)gridDim.x - 1);
-    }
-    __syncthreads();
-    if (s_last && threadIdx.x == 0) {
-      *c.rs_reduce_counter = 0;
-      __threadfence_system();
-      for (int d = 0; d < c.world; ++d)
-        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, comm_epoch(c, STATE_RS_EPOCH));
-    }
-  }
+  if constexpr (MODE == MODE_GEMM_RS) rs_reduce_phase(p);
 }
 
 }  // namespace mlb

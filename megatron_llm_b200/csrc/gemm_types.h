@@ -32,6 +32,7 @@ struct GemmComm {
   int rank, world, epoch;
   int num_comm_ctas;     // AG: trailing CTAs of the grid that pull peer shards
   int m_rotate_blocks;   // first m-block processed
+  int m_group_blocks;    // 2-CTA fused modes: 256-row blocks per tile group (n-major inside a group); 0 = default
   // ---- all-gather side
   const void* ag_src[GEMM_MAX_PEERS];  // ag_src[p]: peer p's published shard [rows_per_rank, K] (NVLink-mapped)
   void* ag_dst;                        // local gathered activations [world*rows_per_rank, K]

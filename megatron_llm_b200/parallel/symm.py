@@ -94,8 +94,16 @@ class TPCommunicator:
         assert m <= self.max_rows and K <= self.max_k and m % 128 == 0, (m, K, self.max_rows, self.max_k)
         # publish my shard (stream-ordered before the kernel; the previous call's kernel only retired after every
         # peer had acknowledged reading the old content)
-        self.xs[: m * K].view(m, K).copy_(x2d)
         gathered = torch.empty((self.world * m, K), dtype=torch.bfloat16, device=self.device)
+        # one pass over my rows: into the symmetric buffer the peers pull from, and into their place in `gathered`
+        # (the kernel's puller CTAs only move the remote shards)
+        mine = gathered[self.rank * m: (self.rank + 1) * m]
+        if x2d.is_contiguous() and x2d.data_ptr() % 16 == 0:
+            self.mod.comm_copy2(x2d, self.xs[: m * K].view(m, K), mine)
+            _ext.count()
+        else:
+            self.xs[: m * K].view(m, K).copy_(x2d)
+            mine.copy_(x2d)
         if out is None:
             out = torch.empty((self.world * m, N), dtype=torch.bfloat16, device=self.device)
         self.ag_epoch += 1
@@ -234,7 +242,7 @@ def bind_tp_communicator(args) -> Optional[TPCommunicator]:
     vocab_shard = getattr(args, "padded_vocab_size", 0) // tp
     max_n = max(args.hidden_size, ffn // tp, vocab_shard)
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), rows, max_k, max_n,
-                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "8")))
+                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")))   # upper bound: the launcher picks per shape
     fused_tp.bind(comm)
     return comm
 
