@@ -146,6 +146,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
   c.state = reinterpret_cast<const int*>(state_ptr);
   c.m_rotate_blocks = (int)(((rank + 1) % world) * rows_per_rank / mlb::GEMM_BLOCK_M);  // remote chunks first
   c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
+  c.m_interleave = (world == 2 && (M / 256) % (2 * c.m_group_blocks) == 0) ? 1 : 0;
   for (int i = 0; i < world; ++i) c.rs_dst[i] = reinterpret_cast<void*>(rs_dst[i]);
   c.rs_slots = reinterpret_cast<const void*>(rs_slots);
   c.rs_out = rs_out.data_ptr();

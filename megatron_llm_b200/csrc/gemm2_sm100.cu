@@ -119,7 +119,12 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       int G = p.comm.m_group_blocks;
       if (G <= 0 || num_m % G != 0) G = (num_m % 4 == 0) ? 4 : ((num_m % 2 == 0) ? 2 : 1);
       const int per_group = G * num_n;
-      const int group = tile / per_group, in_group = tile - group * per_group;
+      int group = tile / per_group;
+      const int in_group = tile - group * per_group;
+      if (p.comm.m_interleave) {          // rotated order is [remote groups | own groups]: take them alternately
+        const int half = (num_m / G) >> 1;
+        group = (group & 1) ? half + (group >> 1) : (group >> 1);
+      }
       m_blk = group * G + in_group % G + (p.comm.m_rotate_blocks >> 1);
       if (m_blk >= num_m) m_blk -= num_m;
       n_blk = in_group / G;

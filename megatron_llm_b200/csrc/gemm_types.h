@@ -33,6 +33,7 @@ struct GemmComm {
   int num_comm_ctas;     // AG: trailing CTAs of the grid that pull peer shards
   int m_rotate_blocks;   // first m-block processed
   int m_group_blocks;    // 2-CTA fused modes: 256-row blocks per tile group (n-major inside a group); 0 = default
+  int m_interleave;      // reduce-scatter, world 2: alternate remote / own tile groups (evens out the NVLink stores)
   // ---- all-gather side
   const void* ag_src[GEMM_MAX_PEERS];  // ag_src[p]: peer p's published shard [rows_per_rank, K] (NVLink-mapped)
   void* ag_dst;                        // local gathered activations [world*rows_per_rank, K]
