@@ -66,12 +66,12 @@ static int pick_group_blocks(int64_t rows_per_rank, int64_t b_bytes) {
 }
 
 // Number of puller CTAs for all-gather -> GEMM.  Every puller moves ~PULL_GBPS (one thread, 5 x 32 KB bulk copies in
-// flight over an NVLink round trip) and costs the GEMM one SM, so small GEMMs behind a big gather want many pullers
+// flight over an NVLink round trip; measured 25-37 GB/s) and costs the GEMM one SM, so small GEMMs behind a big gather want many pullers
 // and big GEMMs few: minimise  max(gemm(c), pull(c) + one tile group of gemm(c))  over even c <= max_ctas.
 static int pick_comm_ctas(int64_t M, int64_t N, int64_t K, int64_t rows_per_rank, int world, int max_ctas, int sms) {
   static const char* fixed = getenv("MLB200_AG_CTAS_FIXED");
   if (fixed) return std::min(max_ctas, atoi(fixed));
-  constexpr double PULL_GBPS = 37.0, GEMM_TFLOPS = 1350.0;
+  constexpr double PULL_GBPS = 25.0, GEMM_TFLOPS = 1350.0;
   const double chunk_us = 128.0 * K * 2 / (PULL_GBPS * 1e3);
   const int remote_chunks = (int)((world - 1) * rows_per_rank / 128);
   const int groups = std::max<int>(1, (int)(M / 256 / pick_group_blocks(rows_per_rank, N * K * 2)));

@@ -230,6 +230,20 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     uint32_t acc_phase = 0;
     unsigned long long w_tf = 0, t_begin = dbg ? g2_clock() : 0;
     uint32_t free_checked = 0;   // RS: destinations whose receive slot is known to be reusable
+    int rs_prev_dst = -1;        // RS: destination of the previous tile (its arrival is signalled one tile late)
+    // this CTA's half tile counts as delivered once the stores of all four epilogue warps have completed at `dst`
+    auto rs_signal = [&](int dst, bool lagged) {
+      if (lane == 0) {
+        if (lagged) tma_store_wait<G2_BLOCK_N / 64>(); else tma_store_wait<0>();
+        fence_proxy_async_global();
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (q == 0 && lane == 0) {
+        __threadfence_system();
+        int* counter = (dst == p.comm.rank ? p.comm.pad_local : p.comm.pad_peer[dst]) + PAD_RS_ARRIVED + p.comm.rank;
+        red_add_release_sys(counter, 1);
+      }
+    };
     for (int tile = pair; tile < total_tiles; tile += num_pairs) {
       int m_blk, n_blk;
       tile_coords(tile, m_blk, n_blk);
@@ -352,21 +366,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(&tmem_empty_bar[acc], 0);   // the leader's MMA thread is the only waiter
       if constexpr (MODE == MODE_GEMM_RS) {
-        // (after the accumulator was handed back) this CTA's half tile is delivered once all four warps' stores have
-        // completed at the destination
-        if (lane == 0) {
-          tma_store_wait<0>();
-          fence_proxy_async_global();
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (q == 0 && lane == 0) {
-          __threadfence_system();
-          int* counter = (rs_dst == p.comm.rank ? p.comm.pad_local : p.comm.pad_peer[rs_dst]) + PAD_RS_ARRIVED +
-                         p.comm.rank;
-          red_add_release_sys(counter, 1);
-        }
+        // Arrival signalling runs one tile behind: the stores of the PREVIOUS tile have had a whole tile time to reach
+        // their destination, so waiting for them (all but this tile's 4 bulk groups per warp) does not stall the
+        // epilogue for an NVLink round trip.
+        if (rs_prev_dst >= 0) rs_signal(rs_prev_dst, /*pending_groups_allowed=*/true);
+        rs_prev_dst = rs_dst;
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if constexpr (MODE == MODE_GEMM_RS) {
+      if (rs_prev_dst >= 0) rs_signal(rs_prev_dst, false);
     }
     if (lane == 0) tma_store_wait<0>();     // all epilogue stores of this warp have completed
     if (dbg && warp == 4 && lane == 0) {
