@@ -37,6 +37,7 @@ def initialize_megatron(extra_args_provider=None, args_defaults={}, ignore_unkno
     def finish_mpu_init():
         args = get_args()
         _initialize_distributed()
+        _use_side_stream_for_graphs()
         if args.rank == 0:
             print("> setting random seeds to {} ...".format(args.seed))
         _set_random_seed(args.seed, args.data_parallel_random_init)
@@ -45,6 +46,18 @@ def initialize_megatron(extra_args_provider=None, args_defaults={}, ignore_unkno
     _init_autoresume()
     _bind_symmetric_communicators()
     return None
+
+
+def _use_side_stream_for_graphs():
+    """CUDA-graph capture cannot touch the legacy default stream, and autograd's AccumulateGrad nodes run on the stream
+    that was current when they were created (model construction): with --cuda_graph_microbatch do everything on one
+    ordinary side stream from the very beginning and capture on that same stream."""
+    args = get_args()
+    if use_cuda() and getattr(args, "cuda_graph_microbatch", False) \
+            and torch.cuda.current_stream() == torch.cuda.default_stream():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        torch.cuda.set_stream(side)
 
 
 def _initialize_distributed():
@@ -65,11 +78,6 @@ def _initialize_distributed():
             else:
                 args.local_rank = device
             torch.cuda.set_device(device)
-            if getattr(args, "cuda_graph_microbatch", False):
-                # CUDA-graph capture cannot touch the legacy default stream, and autograd's AccumulateGrad nodes run
-                # on the stream that was current when they were created (model construction): do everything on one
-                # ordinary side stream from the very beginning and capture on that same stream
-                torch.cuda.set_stream(torch.cuda.Stream())
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         kwargs = {}
