@@ -219,6 +219,20 @@ def run_ours(a):
 
     for _ in range(a.warmup):
         step(it_dev)
+    # safety net: a timed-out handshake inside the fused GEMM+collective kernels (PAD_ERROR) means those results
+    # cannot be trusted -> redo the warm-up on the NCCL path and say so in `config.tp_comm`
+    fused_fallback = False
+    from megatron_llm_b200.parallel import fused_tp, schedules
+    if fused_tp.communicator() is not None:
+        torch.cuda.synchronize()
+        err = torch.tensor([fused_tp.communicator().error_flag()], device=dev, dtype=torch.int32)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        if err.item() != 0:
+            fused_tp.communicator().enabled = False
+            schedules._GRAPH_RUNNERS.clear()
+            fused_fallback = True
+            for _ in range(a.warmup):
+                step(it_dev)
     sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         sampler.start()
@@ -246,7 +260,9 @@ def run_ours(a):
                           "parallelism": f"tp{a.gpus}" + ("+sp" if a.gpus > 1 else ""),
                           "cuda_graph_microbatch": bool(getattr(args, "cuda_graph_microbatch", False)),
                           "tp_comm": ("n/a" if a.gpus == 1 else "fused GEMM+collective kernels over peer memory"
-                                      if _fused_tp_active() else "nccl"),
+                                      if _fused_tp_active() else
+                                      "nccl (fused kernels disabled after a handshake timeout)" if fused_fallback
+                                      else "nccl"),
                           "optimizer": "AdamW fp32 master (in timed region), clip 1.0",
                           "l2": "no flush needed: each step streams >100 GB of weights/grads/optimizer state (>> 126 MB L2)"},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,

@@ -116,10 +116,11 @@ _GROUPS = {
         ("--sequence_parallel", _S()),
         ("--no_gradient_accumulation_fusion", _SF("gradient_accumulation_fusion")),
         # B200-native switches (not in the reference)
-        # fused GEMM+collective kernels over NVLink peer memory (all-gather->GEMM, GEMM->reduce-scatter).  Opt-in: as
-        # measured (profiles/README.md) the NCCL path + CUDA-graph micro-batches is currently faster at TP=2..8.
-        ("--fused_tp_comm", dict(action="store_true", default=False)),
-        ("--no_fused_tp_comm", _SF("fused_tp_comm")),
+        # fused GEMM+collective kernels over NVLink peer memory (all-gather->GEMM, GEMM->reduce-scatter).  Unset =
+        # automatic: on when one tensor-parallel group spans the whole job (the configuration measured faster than
+        # NCCL at TP=2 and TP=8, profiles/README.md), off (NCCL) when there are several TP groups.
+        ("--fused_tp_comm", dict(action="store_const", const=True, default=None)),
+        ("--no_fused_tp_comm", dict(action="store_const", const=False, dest="fused_tp_comm", default=None)),
         ("--no_fused_dp_comm", _SF("fused_dp_comm")),
         ("--ddp_bucket_size_mb", dict(type=int, default=256)),
     ],

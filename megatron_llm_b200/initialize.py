@@ -103,8 +103,12 @@ def _bind_symmetric_communicators():
         return
     try:
         from .parallel import symm
-        want = os.environ.get("MLB200_FUSED_TP", "1" if getattr(args, "fused_tp_comm", False) else "0") == "1"
-        if want and ps.get_tensor_model_parallel_world_size() > 1:
+        tp = ps.get_tensor_model_parallel_world_size()
+        flag = getattr(args, "fused_tp_comm", None)
+        if flag is None:      # automatic: a single TP group over the whole job
+            flag = tp > 1 and tp == dist.get_world_size()
+        want = os.environ.get("MLB200_FUSED_TP", "1" if flag else "0") == "1"
+        if want and tp > 1:
             symm.bind_tp_communicator(args)
     except Exception as e:  # never fatal: the NCCL path is the checked fallback
         if args.rank == 0:

@@ -23,6 +23,32 @@ def active(x: torch.Tensor) -> bool:
     return _COMM is not None and x.is_cuda and x.dtype == torch.bfloat16 and _COMM.enabled
 
 
+def active_column(x_shard: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Column-parallel linear under sequence parallelism: forward = all-gather(x) -> GEMM, backward = GEMM ->
+    reduce-scatter.  True when the bound communicator's buffers fit this call (else the layer uses NCCL)."""
+    if not active(x_shard):
+        return False
+    k = x_shard.size(-1)
+    rows = x_shard.numel() // k
+    return (rows % 128 == 0 and rows <= _COMM.max_rows and k % 8 == 0 and k <= min(_COMM.max_k, _COMM.max_n)
+            and weight.size(0) % 8 == 0 and weight.dtype == torch.bfloat16)
+
+
+def active_row(x_full: torch.Tensor, weight: torch.Tensor) -> bool:
+    """Row-parallel linear under sequence parallelism: forward = GEMM -> reduce-scatter, backward = all-gather(dy)
+    -> GEMM."""
+    if not active(x_full):
+        return False
+    k = x_full.size(-1)
+    total = x_full.numel() // k
+    n = weight.size(0)
+    if total % _COMM.world != 0:
+        return False
+    rows = total // _COMM.world
+    return (rows % 128 == 0 and rows <= _COMM.max_rows and k % 8 == 0 and n % 8 == 0
+            and n <= min(_COMM.max_n, _COMM.max_k) and weight.dtype == torch.bfloat16)
+
+
 def ag_gemm(x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None):
     """all-gather(x_shard along dim 0) then GEMM.  Returns (out2d [s*b, N], gathered input)."""
     return _COMM.ag_gemm(x_shard, weight, transposed_weight, out=out)

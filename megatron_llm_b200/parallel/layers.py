@@ -189,7 +189,7 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
         ctx.async_grad_allreduce = async_grad_allreduce
         ctx.sequence_parallel = sequence_parallel and ps.get_tensor_model_parallel_world_size() > 1
         from . import fused_tp
-        fused = fused_tp.active(input) and ctx.sequence_parallel
+        fused = ctx.sequence_parallel and fused_tp.active_column(input, weight)
         ctx.fused = fused
         if ctx.sequence_parallel:
             if fused:
@@ -399,7 +399,7 @@ class RowParallelLinear(torch.nn.Module):
             assert not self.sequence_parallel_enabled
             input_parallel = scatter_to_tensor_model_parallel_region(input_)
         from . import fused_tp
-        if self.sequence_parallel_enabled and self.world_size > 1 and fused_tp.active(input_parallel):
+        if self.sequence_parallel_enabled and self.world_size > 1 and fused_tp.active_row(input_parallel, self.weight):
             output_ = _RowLinearFusedRS.apply(input_parallel, self.weight, self.gradient_accumulation_fusion)
         else:
             output_parallel = linear_with_grad_accumulation_and_async_allreduce(
