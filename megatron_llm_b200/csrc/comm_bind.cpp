@@ -79,7 +79,9 @@ static int pick_comm_ctas(int64_t M, int64_t N, int64_t K, int64_t rows_per_rank
   double best_t = 1e30;
   for (int c = 2; c <= max_ctas; c += 2) {
     const double gemm_us = 2.0 * M * N * K / (GEMM_TFLOPS * 1e6) * sms / (double)(sms - c) + 4.0;
-    const double pull_us = ((remote_chunks + c - 1) / c) * chunk_us;
+    // whole chunks per puller, or (MLB200_AG_STREAM) every chunk shared piece-wise by all pullers
+    static const bool stream = getenv("MLB200_AG_STREAM") != nullptr;
+    const double pull_us = stream ? remote_chunks * chunk_us / c : ((remote_chunks + c - 1) / c) * chunk_us;
     const double t = std::max(gemm_us, pull_us + gemm_us / groups);
     if (t < best_t * 0.995) { best_t = t; best = c; }
   }
@@ -113,6 +115,12 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
   c.ag_row_bytes = K * 2;
   c.ag_chunk_flags = chunk_flags.data_ptr<int>();
   c.ag_read_counters = read_counters.data_ptr<int>();
+  // streaming pullers (opt-in until measured on hardware): per-chunk piece counters live behind the 8 peer counters
+  static const bool stream = getenv("MLB200_AG_STREAM") != nullptr;
+  if (stream && read_counters.numel() >= 8 + M / mlb::GEMM_BLOCK_M) {
+    c.ag_stream = 1;
+    c.ag_chunk_counts = read_counters.data_ptr<int>() + 8;
+  }
   fill_pads(c, pad_local, pad_peers);
   // the 2-CTA (256x256-tile, TMA-store epilogue) kernel when the shard is a whole number of its row blocks
   static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;

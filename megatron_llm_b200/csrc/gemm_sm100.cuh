@@ -76,7 +76,119 @@ __device__ __forceinline__ int comm_rs_expected(const GemmComm& c) {
   return c.rs_expected_total + (c.state ? *reinterpret_cast<const volatile int*>(c.state + STATE_RS_TOTAL) : 0);
 }
 
+// Streaming variant (GemmComm::ag_stream): the remote 32 KB pieces, taken in the order the GEMM consumes them, are dealt
+// round-robin to ALL puller CTAs, so chunk j completes after ~(j+1)/num_chunks of the gather instead of every puller
+// finishing "its" chunks at the very end.  (With whole chunks per puller, TP=8 had 28 pullers each delivering one
+// chunk ~40 us into a 60 us GEMM: the compute CTAs sat idle until then.)  A chunk's flag is released by the puller that
+// delivers its last piece (local counter, self-resetting).
+static __device__ void ag_puller_stream(const GemmComm& c, uint8_t* smem, int comm_id) {
+  if (threadIdx.x != 0) return;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);
+  for (int i = 0; i < AG_STAGES; ++i) mbar_init(&bars[i], 1);
+  fence_barrier_init();
+  fence_proxy_async_smem();
+
+  const int epoch = comm_epoch(c, STATE_AG_EPOCH);
+  const int C = c.num_comm_ctas;
+  const int cpr = c.ag_rows_per_rank / GEMM_BLOCK_M;                      // chunks per rank
+  const long long chunk_bytes = (long long)GEMM_BLOCK_M * c.ag_row_bytes;
+  const int ppc = (int)((chunk_bytes + AG_PIECE_BYTES - 1) / AG_PIECE_BYTES);   // pieces per chunk
+  const long long total = (long long)(c.world - 1) * cpr * ppc;          // remote pieces in consumption order
+  const long long n_mine = total > comm_id ? (total - comm_id + C - 1) / C : 0;
+
+  if (comm_id == 0) {
+    __threadfence_system();
+    for (int p = 0; p < c.world; ++p)
+      if (p != c.rank) st_release_sys(c.pad_peer[p] + PAD_AG_READY + c.rank, epoch);
+  }
+
+  struct Piece { int peer, chunk; long long off; uint32_t bytes; };
+  auto locate = [&](long long k) {
+    const long long s = comm_id + k * C;
+    const int rc = (int)(s / ppc);                       // remote chunk index in consumption order
+    const int piece = (int)(s - (long long)rc * ppc);
+    const int i = rc / cpr + 1;
+    Piece q;
+    q.peer = (c.rank + i) % c.world;
+    q.chunk = rc - (i - 1) * cpr;
+    q.off = (long long)piece * AG_PIECE_BYTES;
+    q.bytes = (uint32_t)min((long long)AG_PIECE_BYTES, chunk_bytes - q.off);
+    return q;
+  };
+  uint32_t ready_mask = 0, phase_bits = 0;
+  auto issue = [&](long long k) {
+    const Piece q = locate(k);
+    if (!((ready_mask >> q.peer) & 1u)) {
+      spin_until_ge(c.pad_local + PAD_AG_READY + q.peer, epoch, c.pad_local);
+      fence_proxy_async_global();
+      ready_mask |= 1u << q.peer;
+    }
+    const int stage = (int)(k % AG_STAGES);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.ag_src[q.peer]) + q.chunk * chunk_bytes + q.off;
+    mbar_arrive_expect_tx(&bars[stage], q.bytes);
+    bulk_g2s(smem + stage * AG_PIECE_BYTES, src, q.bytes, &bars[stage]);
+  };
+  // pieces [retired, upto) are in local HBM: count them into their chunks; the last piece of a chunk releases its flag
+  long long retired = 0;
+  auto retire = [&](long long upto) {
+    if (upto <= retired) return;
+    fence_proxy_async_global();
+    __threadfence();
+    for (long long k = retired; k < upto; ++k) {
+      const Piece q = locate(k);
+      const int g = q.peer * cpr + q.chunk;
+      if (atomicAdd(c.ag_chunk_counts + g, 1) + 1 == ppc) {
+        c.ag_chunk_counts[g] = 0;
+        __threadfence();
+        st_release_sys(c.ag_chunk_flags + g, epoch);
+      }
+    }
+    retired = upto;
+  };
+  constexpr int LAG = 4;   // local stores complete within a few pieces: counting them LAG behind never waits
+  long long issued = 0, stored = 0;
+  while (issued < n_mine && issued < AG_STAGES - 1) issue(issued++);
+  while (stored < n_mine) {
+    const int stage = (int)(stored % AG_STAGES);
+    mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
+    phase_bits ^= (1u << stage);
+    const Piece q = locate(stored);
+    uint8_t* dst = reinterpret_cast<uint8_t*>(c.ag_dst) + ((long long)q.peer * cpr + q.chunk) * chunk_bytes + q.off;
+    bulk_s2g(dst, smem + stage * AG_PIECE_BYTES, q.bytes);
+    tma_store_commit();
+    ++stored;
+    if (issued < n_mine) {
+      tma_store_wait_read<1>();     // the stage refilled next held the piece stored one iteration ago
+      issue(issued++);
+    }
+    if (stored > LAG) {
+      tma_store_wait<LAG>();
+      retire(stored - LAG);
+    }
+  }
+  tma_store_wait<0>();
+  retire(n_mine);
+  // every puller is done reading every peer: the last one acknowledges, so the owners may overwrite their shards
+  __threadfence();
+  for (int p = 0; p < c.world; ++p) {
+    if (p == c.rank) continue;
+    if (atomicAdd(c.ag_read_counters + p, 1) + 1 == C) {
+      c.ag_read_counters[p] = 0;
+      __threadfence_system();
+      st_release_sys(c.pad_peer[p] + PAD_AG_ACK + c.rank, epoch);
+    }
+  }
+  if (comm_id == 0) {
+    for (int p = 0; p < c.world; ++p)
+      if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, epoch, c.pad_local);
+  }
+}
+
 static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
+  if (c.ag_stream) {
+    ag_puller_stream(c, smem, comm_id);
+    return;
+  }
   // one thread drives the whole copy pipeline (bulk copies are issued by a single thread anyway)
   if (threadIdx.x != 0) return;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);

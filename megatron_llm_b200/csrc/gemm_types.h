@@ -41,6 +41,8 @@ struct GemmComm {
   int ag_row_bytes;                    // K * 2
   int* ag_chunk_flags;                 // local, one per 128-row chunk of the gathered buffer: set to epoch
   int* ag_read_counters;               // local, [world]: puller CTAs done with peer p (for the ack)
+  int* ag_chunk_counts;                // local, one per 128-row chunk: pieces delivered (streaming pullers), self-resetting
+  int ag_stream;                       // 1: all pullers share every chunk piece-wise, chunks complete in arrival order
   // ---- reduce-scatter side
   void* rs_dst[GEMM_MAX_PEERS];        // rs_dst[d]: my receive slot on rank d: [rows_per_rank, N] bf16
   const void* rs_slots;                // local receive buffer of this epoch parity: [world][rows_per_rank, N]

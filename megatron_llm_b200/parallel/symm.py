@@ -68,7 +68,8 @@ class TPCommunicator:
         self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
         max_chunks = self.world * max_rows_per_rank // 128
         self.chunk_flags = torch.zeros(max(max_chunks, 1), dtype=torch.int32, device=self.device)
-        self.read_counters = torch.zeros(8, dtype=torch.int32, device=self.device)
+        # [0:8] pullers done per peer; [8:] pieces delivered per 128-row chunk (streaming pullers); self-resetting
+        self.read_counters = torch.zeros(8 + max(max_chunks, 1), dtype=torch.int32, device=self.device)
         self.reduce_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.ag_epoch = 0
         self.rs_epoch = 0
