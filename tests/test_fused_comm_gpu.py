@@ -59,6 +59,16 @@ def test_fused_tp_kernels_match_nccl():
     run_distributed(_tp_kernels, 2, backend="nccl")
 
 
+def _tp_kernels_streaming(rank, world):
+    os.environ["MLB200_AG_STREAM"] = "1"     # read once per process by the launcher
+    _tp_kernels(rank, world)
+
+
+def test_fused_tp_kernels_streaming_pullers_match_nccl():
+    """Same checks with the all-gather pieces dealt round-robin to all puller CTAs (MLB200_AG_STREAM)."""
+    run_distributed(_tp_kernels_streaming, 2, backend="nccl")
+
+
 def _tp_kernels_in_graph(rank, world):
     """The fused kernels captured in a CUDA graph: every replay must continue the live epoch sequence, also when eager
     calls run in between (which flips the receive-slot parity the captured reduce-scatter was recorded with)."""
