@@ -19,6 +19,8 @@ extern "C" {
 int mlb_gemm_bf16_2cta_ag(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
                           int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
 int mlb_copy2(const void* src, void* d1, void* d2, long long bytes, int num_sms, cudaStream_t stream);
+int mlb_p2p_bench(int mode, const void* src, void* dst, long long bytes, int ctas, int piece_bytes, int stages,
+                  int row_bytes, long long dst_stride, cudaStream_t stream);
 int mlb_set_ints3(int* dst, int a, int b, int c, cudaStream_t stream);
 int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int lda, int ldb, int b_mn_major,
                           mlb::GemmComm* comm, int prev_total, int num_sms, cudaStream_t stream);
@@ -208,7 +210,18 @@ static void comm_copy2(const torch::Tensor& src, torch::Tensor& d1, torch::Tenso
   CHK(mlb_copy2(src.data_ptr(), d1.data_ptr(), d2.data_ptr(), bytes, sm_count(), cur()));
 }
 
+// NVLink transfer micro-benchmark (raw pointers: symmetric-memory peer / multicast addresses); see p2p_bench.cu
+static void p2p_bench(int64_t mode, int64_t src_ptr, int64_t dst_ptr, int64_t bytes, int64_t ctas, int64_t piece_bytes,
+                      int64_t stages, int64_t row_bytes, int64_t dst_stride) {
+  TORCH_CHECK(bytes % 16 == 0 && src_ptr % 16 == 0 && dst_ptr % 16 == 0);
+  TORCH_CHECK(mode == 0 || mode == 3 || (piece_bytes % 16 == 0 && stages >= 2 && stages * piece_bytes <= 200 * 1024));
+  TORCH_CHECK(mode != 2 || (row_bytes % 16 == 0 && piece_bytes % row_bytes == 0 && bytes % piece_bytes == 0));
+  CHK(mlb_p2p_bench((int)mode, reinterpret_cast<const void*>(src_ptr), reinterpret_cast<void*>(dst_ptr), bytes,
+                    (int)ctas, (int)piece_bytes, (int)stages, (int)row_bytes, dst_stride, cur()));
+}
+
 void register_comm(pybind11::module_& m) {
+  m.def("p2p_bench", &p2p_bench);
   m.def("comm_copy2", &comm_copy2);
   m.def("comm_set_state", &comm_set_state);
   m.def("fused_ag_gemm", &fused_ag_gemm);
