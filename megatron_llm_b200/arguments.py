@@ -122,6 +122,12 @@ _GROUPS = {
         ("--fused_tp_comm", dict(action="store_const", const=True, default=None)),
         ("--no_fused_tp_comm", dict(action="store_const", const=False, dest="fused_tp_comm", default=None)),
         ("--no_fused_dp_comm", _SF("fused_dp_comm")),
+        # step-range profiling (megatron_llm_b200/profiler.py): torch.profiler trace + cudaProfilerStart/Stop + NVTX
+        ("--profile", _S()),
+        ("--profile_step_start", dict(type=int, default=10)),
+        ("--profile_step_end", dict(type=int, default=12)),
+        ("--profile_ranks", dict(type=int, nargs="+", default=[0])),
+        ("--profile_dir", dict(type=str, default=None)),
         ("--ddp_bucket_size_mb", dict(type=int, default=256)),
     ],
     "initialization": [

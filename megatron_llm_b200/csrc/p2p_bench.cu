@@ -1,4 +1,4 @@
-// NVLink transfer micro-benchmarks (tools/dev/nvlink_bench.py): how fast can a few CTAs move data between peers, and
+// NVLink transfer micro-benchmarks (tools/profiling/nvlink_bench.py): how fast can a few CTAs move data between peers, and
 // with which instruction path?  These decide the design of the fused GEMM+collective kernels' communication side:
 //   mode 0  ld/st      : every thread LDG.128 x4 -> STG.128 x4 (pull when src is the peer, push when dst is)
 //   mode 1  bulk       : one thread per CTA, cp.async.bulk global->smem->global pipeline (piece_bytes, stages)

@@ -128,7 +128,6 @@ class TPCommunicator:
         base = (parity * self.world) * self.max_rows * self.max_n
         rs_dst = [self.rs_ptrs[d] + 2 * (base + self.rank * slot_elems) for d in range(self.world)]
         rs_slots = self.rs_ptrs[self.rank] + 2 * base
-        num_n_256 = None  # tile count is computed with the same heuristic as the kernel launcher
         out = torch.empty((m, N), dtype=torch.bfloat16, device=self.device)
         tiles_per_dst = (m // 128) * self._num_n_tiles(M, N)      # arrivals if the 1-CTA kernel is chosen
         x = x2d if (x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0) else x2d.contiguous()

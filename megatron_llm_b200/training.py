@@ -423,9 +423,12 @@ def _train(args, forward_step_func, model, optimizer, opt_param_scheduler, train
     timers("interval-time", log_level=0).start(barrier=True)
     print_datetime("before the start of training step")
     report_memory_flag = True
+    from .profiler import StepProfiler
+    step_profiler = StepProfiler(args, dist.get_rank() if dist.is_initialized() else 0)
     while iteration < args.train_iters:
         update_num_microbatches(args.consumed_train_samples)
         args.curr_iteration = iteration
+        step_profiler.step_begin(iteration)
         if iteration in args.skip_iters:
             print_rank_0(f"=== skipping iteration {iteration} (forward only) ===")
             fwd = get_forward_backward_func()
@@ -434,6 +437,10 @@ def _train(args, forward_step_func, model, optimizer, opt_param_scheduler, train
         else:
             loss_dict, skipped_iter, grad_norm, num_zeros_in_grad = train_step(
                 forward_step_func, train_data_iterator, model, optimizer, opt_param_scheduler)
+        trace = step_profiler.step_end(iteration)
+        if trace:
+            print(f"> profiler trace of iterations [{step_profiler.start}, {step_profiler.end}) written to {trace}",
+                  flush=True)
         iteration += 1
         args.consumed_train_samples += ps.get_data_parallel_world_size() * args.micro_batch_size * \
             get_num_microbatches()

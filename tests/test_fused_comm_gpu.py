@@ -69,6 +69,49 @@ def test_fused_tp_kernels_streaming_pullers_match_nccl():
     run_distributed(_tp_kernels_streaming, 2, backend="nccl")
 
 
+def _tp_kernels_with_skew(rank, world):
+    """Shake the flag protocol: every rank delays its launches by a different, changing amount (device-side spin on the
+    launching stream), so the READY / ACK / ARRIVED / FREE handshakes see peers that are early, late, or a whole call
+    behind.  Results must still match NCCL and no bounded spin may time out."""
+    import random
+    from megatron_llm_b200.parallel import state as ps
+    from megatron_llm_b200.parallel.symm import TPCommunicator
+    ps.initialize_model_parallel(world, 1)
+    dev = torch.device("cuda", rank)
+    group = ps.get_tensor_model_parallel_group()
+    m, K, N = 256, 512, 768
+    comm = TPCommunicator(group, max_rows_per_rank=512, max_k=2048, max_n=2048, num_comm_ctas=4)
+    rnd = random.Random(1234 + rank)
+    torch.manual_seed(3)
+    w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.05
+    results = []
+    for it in range(12):
+        torch.manual_seed(100 * it + rank)
+        x = torch.randn(m, K, device=dev, dtype=torch.bfloat16)
+        a = torch.randn(world * m, K, device=dev, dtype=torch.bfloat16)
+        torch.cuda._sleep(rnd.randrange(0, 3_000_000))          # up to ~1.5 ms of skew before the all-gather GEMM
+        out, gathered = comm.ag_gemm(x, w, False)
+        torch.cuda._sleep(rnd.randrange(0, 3_000_000))
+        got = comm.gemm_rs(a, w, False)
+        results.append((x, a, out, gathered, got))               # no host sync inside the loop
+    torch.cuda.synchronize()
+    for it, (x, a, out, gathered, got) in enumerate(results):
+        full = torch.empty(world * m, K, device=dev, dtype=torch.bfloat16)
+        dist.all_gather_into_tensor(full, x, group=group)
+        assert torch.equal(gathered, full), f"it {it}: gathered mismatch"
+        ref = full.float() @ w.float().t()
+        assert (out.float() - ref).abs().max() <= 2e-2 * ref.abs().max(), f"it {it}: ag_gemm"
+        refs = torch.empty(m, N, device=dev, dtype=torch.float32)
+        dist.reduce_scatter_tensor(refs, a.float() @ w.float().t(), group=group)
+        assert (got.float() - refs).abs().max() <= 3e-2 * refs.abs().max(), f"it {it}: gemm_rs"
+    assert comm.error_flag() == 0, "a spin-wait timed out"
+    ps.destroy_model_parallel()
+
+
+def test_fused_tp_kernels_tolerate_rank_skew():
+    run_distributed(_tp_kernels_with_skew, 2, backend="nccl")
+
+
 def _tp_kernels_in_graph(rank, world):
     """The fused kernels captured in a CUDA graph: every replay must continue the live epoch sequence, also when eager
     calls run in between (which flips the receive-slot parity the captured reduce-scatter was recorded with)."""

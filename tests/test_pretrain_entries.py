@@ -54,10 +54,15 @@ COMMON = ["--num_layers", "2", "--hidden_size", "32", "--num_attention_heads", "
 
 def test_pretrain_bert(tmp_path):
     vocab = _preprocess(tmp_path)
+    # (also exercises --profile: iteration 1 of 2 goes through torch.profiler and must leave a trace + kernel table)
     out = _run("pretrain_bert.py", COMMON + ["--seq_length", "48", "--max_position_embeddings", "48", "--vocab_file",
                                              str(vocab), "--data_path", str(tmp_path / "data_text_sentence"),
-                                             "--make_vocab_size_divisible_by", "8"])
+                                             "--make_vocab_size_divisible_by", "8", "--profile",
+                                             "--profile_step_start", "1", "--profile_step_end", "2", "--profile_dir",
+                                             str(tmp_path / "trace")])
     assert "lm loss" in out and "sop loss" in out and "iteration        2/" in out
+    assert (tmp_path / "trace" / "trace_rank0_it1-2.json").stat().st_size > 1000
+    assert (tmp_path / "trace" / "kernels_rank0_it1-2.txt").exists()
 
 
 def test_pretrain_t5(tmp_path):

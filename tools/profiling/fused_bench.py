@@ -1,6 +1,6 @@
 """Per-shape timing of the fused TP kernels against (NCCL collective + plain GEMM) and the plain GEMM alone.
 
-torchrun --nproc-per-node N tools/dev/fused_bench.py [hidden ffn seq]   -> one JSON line per shape on rank 0
+torchrun --nproc-per-node N tools/profiling/fused_bench.py [hidden ffn seq]   -> one JSON line per shape on rank 0
 """
 import json
 import os

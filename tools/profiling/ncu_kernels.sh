@@ -1,0 +1,22 @@
+#!/bin/bash
+# ncu --set full capture of every hot kernel, one launch each (one GPU: ncu replays a kernel ~40 times).
+#   tools/profiling/ncu_kernels.sh [outdir]      -> <outdir>/ncu_<kernel>.ncu-rep (+ .log)
+# then, anywhere:  python tools/profiling/ncu_report.py <outdir>/*.ncu-rep > profiles/ncu_summary.md
+# Numbers printed by a command running under ncu are never benchmark values.
+out=${1:-gpurun_out}
+mkdir -p "$out"
+NCU="ncu --set full --clock-control none --import-source on -f"
+cap() {  # name, kernel regex, launches to skip, command...
+  local name=$1 regex=$2 skip=$3; shift 3
+  timeout 300 $NCU -k "regex:$regex" -s "$skip" -c 1 -o "$out/ncu_$name" "$@" > "$out/ncu_$name.log" 2>&1
+  echo "$name: exit $? $(ls -la "$out/ncu_$name.ncu-rep" 2>/dev/null | awk '{print $5}') bytes"
+}
+G="python tools/profiling/gemm_check.py"
+A="python tools/profiling/attn_check.py"
+MLB200_GEMM_TILE=256 cap gemm_1cta_nt      gemm_bf16_kernel       2 $G nt 4096 22016 4096 t
+cap gemm_2cta_nt      gemm_bf16_2cta_kernel  2 $G nt 4096 22016 4096 t
+cap gemm_2cta_nn      gemm_bf16_2cta_kernel  2 $G nn 4096 4096 11008 t
+cap gemm_2cta_wgrad   gemm_bf16_2cta_kernel  2 $G tn_acc 22016 4096 4096 t
+cap attn_fwd2         attn_fwd2_kernel       1 $A 1 4096 32 32 none t
+cap attn_bwd_dkdv     attn_bwd_dkdv_kernel   1 $A 1 4096 32 32 none t
+cap attn_bwd_dq       attn_bwd_dq_kernel     1 $A 1 4096 32 32 none t

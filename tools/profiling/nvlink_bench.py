@@ -1,6 +1,6 @@
 """NVLink transfer micro-benchmark: GB/s per GPU for the instruction paths a fused GEMM+collective kernel can use.
 
-  torchrun --nproc-per-node N tools/dev/nvlink_bench.py [MB_per_peer]     (rank 0 prints one JSON line per case)
+  torchrun --nproc-per-node N tools/profiling/nvlink_bench.py [MB_per_peer]     (rank 0 prints one JSON line per case)
 
 Every rank runs the same transfer at the same time (device-timed, max over ranks):
   pattern "ring": all bytes go to / come from rank+1;  "all": an equal share to / from each of the N-1 peers
