@@ -30,6 +30,7 @@ struct AttnBwdParams {
 // ------------------------------------------------------------------------------------------------
 // delta = rowsum(dO * O)
 // ------------------------------------------------------------------------------------------------
+template <int D>
 __global__ void attn_delta_kernel(RowAddr o, RowAddr dout, float* __restrict__ delta, int seq, int batch, int heads) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row_id = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -39,10 +40,17 @@ __global__ void attn_delta_kernel(RowAddr o, RowAddr dout, float* __restrict__ d
   const int s = (int)(row_id % seq);
   const int h = (int)((row_id / seq) % heads);
   const int b = (int)(row_id / ((long long)seq * heads));
-  const uint2 a = *reinterpret_cast<const uint2*>(o.row(s, b, h) + lane * 4);
-  const uint2 g = *reinterpret_cast<const uint2*>(dout.row(s, b, h) + lane * 4);
-  const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
-  float v = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
+  float v;
+  if constexpr (D == 128) {          // 4 elements per lane
+    const uint2 a = *reinterpret_cast<const uint2*>(o.row(s, b, h) + lane * 4);
+    const uint2 g = *reinterpret_cast<const uint2*>(dout.row(s, b, h) + lane * 4);
+    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+    v = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
+  } else {                           // 2 elements per lane
+    const float2 a0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o.row(s, b, h) + lane * 2));
+    const float2 g0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout.row(s, b, h) + lane * 2));
+    v = a0.x * g0.x + a0.y * g0.y;
+  }
   v = warp_sum(v);
   if (lane == 0) delta[((long long)b * heads + h) * seq + s] = v;
 }
@@ -59,6 +67,7 @@ constexpr int AT_ROWS64 = 64 * 128;   // byte offset of tile row 64 inside a 64-
 constexpr uint32_t KV_ST = 0, KV_DPT = 128, KV_DV = 256, KV_DK = 384;
 constexpr int BWD_SMEM = 6 * AT_TILE_BYTES + 2 * 2 * 128 * 4 + 256 + 1024;   // K, V, 2 x (Q, dO), 2 x (lse, D)
 
+template <int D>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -108,21 +117,21 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
   constexpr uint32_t ID_KK = make_idesc_f16(AT_N, 64, false, false, true);     // [128 kv] x [64 q], both K-major smem
-  constexpr uint32_t ID_TS = make_idesc_f16(AT_N, AT_D, false, true, true);    // A from TMEM, B MN-major smem
+  constexpr uint32_t ID_TS = make_idesc_f16(AT_N, D, false, true, true);    // A from TMEM, B MN-major smem
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * AT_TILE_BYTES);
-      load_tile(sK, &tmK, kv_full, p.hm.k(kvh), kv0, b);
-      load_tile(sV, &tmV, kv_full, p.hm.v(kvh), kv0, b);
+      mbar_arrive_expect_tx(kv_full, 2 * at_tile_tx<D>());
+      load_tile<D>(sK, &tmK, kv_full, p.hm.k(kvh), kv0, b);
+      load_tile<D>(sV, &tmV, kv_full, p.hm.v(kvh), kv0, b);
       for (int it = 0; it < n_iter; ++it) {
         const int st = it & 1;
         const int hq = kvh * g + it / tiles_per_head;
         const int q0 = (j + it % tiles_per_head) * AT_M;
         mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&in_full[st], 2 * AT_TILE_BYTES);
-        load_tile(sQ + st * AT_TILE_BYTES, &tmQ, &in_full[st], p.hm.q(hq), q0, b);
-        load_tile(sDO + st * AT_TILE_BYTES, &tmDO, &in_full[st], hq, q0, b);
+        mbar_arrive_expect_tx(&in_full[st], 2 * at_tile_tx<D>());
+        load_tile<D>(sQ + st * AT_TILE_BYTES, &tmQ, &in_full[st], p.hm.q(hq), q0, b);
+        load_tile<D>(sDO + st * AT_TILE_BYTES, &tmDO, &in_full[st], hq, q0, b);
       }
     }
   } else if (warp == 1) {
@@ -136,10 +145,10 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         mbar_wait(&in_full[st], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
+        for (int k = 0; k < D / 16; ++k)
           umma_f16_ss<1>(tmem + KV_ST + x * 64, desc_kmajor(aK, k), desc_kmajor(aQ, k), ID_KK, k != 0);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
+        for (int k = 0; k < D / 16; ++k)
           umma_f16_ss<1>(tmem + KV_DPT + x * 64, desc_kmajor(aV, k), desc_kmajor(aDO, k), ID_KK, k != 0);
         umma_commit<1>(&sdp_full[x]);
       };
@@ -227,18 +236,18 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       __syncwarp();
       if (lane == 0) mbar_arrive(&pds_full[x]);
     }
-    // epilogue: dV, dK -> bf16 (each warpgroup writes 64 of the 128 head-dim columns)
+    // epilogue: dV, dK -> bf16 (each warpgroup writes one half of the head-dim columns)
     mbar_wait(acc_done, 0);
     tc_fence_after();
     if (kv < p.seq) {
       // gradients use the same head -> coordinate map as the inputs (separate tensors or one packed QKV buffer)
-      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh)) + x * 64;
-      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh)) + x * 64;
+      __nv_bfloat16* dvrow = p.dv.row(kv, b, p.hm.v(kvh)) + x * (D / 2);
+      __nv_bfloat16* dkrow = p.dk.row(kv, b, p.hm.k(kvh)) + x * (D / 2);
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < D / 64; ++c) {
         uint32_t a[32], bb[32];
-        tmem_ld_32x32(tmem + lane_addr + KV_DV + x * 64 + c * 32, a);
-        tmem_ld_32x32(tmem + lane_addr + KV_DK + x * 64 + c * 32, bb);
+        tmem_ld_32x32(tmem + lane_addr + KV_DV + x * (D / 2) + c * 32, a);
+        tmem_ld_32x32(tmem + lane_addr + KV_DK + x * (D / 2) + c * 32, bb);
         tmem_ld_wait();
         uint4* d0 = reinterpret_cast<uint4*>(dvrow + c * 32);
         uint4* d1 = reinterpret_cast<uint4*>(dkrow + c * 32);
@@ -268,6 +277,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 constexpr uint32_t Q_S = 0, Q_DP = 128, Q_DQ = 256;
 constexpr int BWD_DQ_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;   // Q, dO, 2 x (K, V)
 
+template <int D>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -313,20 +323,20 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
   constexpr uint32_t ID_KK = make_idesc_f16(AT_M, 64, false, false, true);
-  constexpr uint32_t ID_TS = make_idesc_f16(AT_M, AT_D, false, true, true);
+  constexpr uint32_t ID_TS = make_idesc_f16(AT_M, D, false, true, true);
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
-      load_tile(sQ, &tmQ, q_full, p.hm.q(h), q0, b);
-      load_tile(sDO, &tmDO, q_full, h, q0, b);
+      mbar_arrive_expect_tx(q_full, 2 * at_tile_tx<D>());
+      load_tile<D>(sQ, &tmQ, q_full, p.hm.q(h), q0, b);
+      load_tile<D>(sDO, &tmDO, q_full, h, q0, b);
       for (int it = 0; it < n_iter; ++it) {
         const int st = it & 1;
         const int kv0 = (j_lo + it) * AT_N;
         mbar_wait(&in_empty[st], ((it >> 1) & 1) ^ 1);
-        mbar_arrive_expect_tx(&in_full[st], 2 * AT_TILE_BYTES);
-        load_tile(sK + st * AT_TILE_BYTES, &tmK, &in_full[st], p.hm.k(kvh), kv0, b);
-        load_tile(sV + st * AT_TILE_BYTES, &tmV, &in_full[st], p.hm.v(kvh), kv0, b);
+        mbar_arrive_expect_tx(&in_full[st], 2 * at_tile_tx<D>());
+        load_tile<D>(sK + st * AT_TILE_BYTES, &tmK, &in_full[st], p.hm.k(kvh), kv0, b);
+        load_tile<D>(sV + st * AT_TILE_BYTES, &tmV, &in_full[st], p.hm.v(kvh), kv0, b);
       }
     }
   } else if (warp == 1) {
@@ -339,10 +349,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(&in_full[st], (it >> 1) & 1);
         tc_fence_after();
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
+        for (int k = 0; k < D / 16; ++k)
           umma_f16_ss<1>(tmem + Q_S + x * 64, desc_kmajor(aQ, k), desc_kmajor(aK, k), ID_KK, k != 0);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
+        for (int k = 0; k < D / 16; ++k)
           umma_f16_ss<1>(tmem + Q_DP + x * 64, desc_kmajor(aDO, k), desc_kmajor(aV, k), ID_KK, k != 0);
         umma_commit<1>(&sdp_full[x]);
       };
@@ -413,11 +423,11 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     mbar_wait(acc_done, 0);
     tc_fence_after();
     if (row < p.seq) {
-      __nv_bfloat16* dqrow = p.dq.row(row, b, p.hm.q(h)) + x * 64;
+      __nv_bfloat16* dqrow = p.dq.row(row, b, p.hm.q(h)) + x * (D / 2);
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = 0; c < D / 64; ++c) {
         uint32_t a[32];
-        tmem_ld_32x32(tmem + lane_addr + Q_DQ + x * 64 + c * 32, a);
+        tmem_ld_32x32(tmem + lane_addr + Q_DQ + x * (D / 2) + c * 32, a);
         tmem_ld_wait();
         uint4* d0 = reinterpret_cast<uint4*>(dqrow + c * 32);
 #pragma unroll
@@ -437,6 +447,27 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 2) { tc_fence_after(); tmem_dealloc<1>(tmem, 512); }
 }
 
+template <int D>
+static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
+                           const AttnBwdParams& p, const RowAddr& ro, const RowAddr& rdo, float* delta, int q_per_kv,
+                           cudaStream_t stream) {
+  const long long rows = (long long)p.seq * p.batch * p.heads;
+  attn_delta_kernel<D><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ro, rdo, delta, p.seq, p.batch, p.heads);
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_DQ_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  dim3 g1(p.seq / AT_N, p.heads / q_per_kv, p.batch);
+  attn_bwd_dkdv_kernel<D><<<g1, BW_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  dim3 g2(p.seq / AT_M, p.heads, p.batch);
+  attn_bwd_dq_kernel<D><<<g2, BW_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  return (int)cudaGetLastError();
+}
+
 }  // namespace mlb
 
 extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
@@ -445,22 +476,18 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
                             int v_map_heads, const int* head_map, int q_per_kv, int seq, int batch, int heads,
                             int window, float softmax_scale, const float* lse, float* delta, void* dq, void* dk,
                             void* dv, const long long* dq_str, const long long* dk_str, const long long* dv_str,
-                            cudaStream_t stream) {
+                            int head_dim, cudaStream_t stream) {
   using namespace mlb;
-  if (seq % AT_M != 0) return -2;
-  static const bool dbg = getenv("MLB200_ATTN_DEBUG") != nullptr;
-#define ATT_DBG(msg) do { if (dbg) { fprintf(stderr, "[attn_bwd] %s\n", msg); fflush(stderr); } } while (0)
-  ATT_DBG("enter");
+  if (seq % AT_M != 0 || (head_dim != 64 && head_dim != 128)) return -2;
   CUtensorMap tq, tk, tv, tdo;
-  int r = make_tmap_heads(&tq, q, AT_D, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
+  int r = make_tmap_heads(&tq, q, head_dim, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
   if (r) return 1000 + r;
-  r = make_tmap_heads(&tk, k, AT_D, k_map_heads, seq, batch, k_str[0], k_str[1], k_str[2], AT_N);
+  r = make_tmap_heads(&tk, k, head_dim, k_map_heads, seq, batch, k_str[0], k_str[1], k_str[2], AT_N);
   if (r) return 2000 + r;
-  r = make_tmap_heads(&tv, v, AT_D, v_map_heads, seq, batch, v_str[0], v_str[1], v_str[2], AT_N);
+  r = make_tmap_heads(&tv, v, head_dim, v_map_heads, seq, batch, v_str[0], v_str[1], v_str[2], AT_N);
   if (r) return 3000 + r;
-  r = make_tmap_heads(&tdo, dout, AT_D, heads, seq, batch, do_str[0], do_str[1], do_str[2], AT_M);
+  r = make_tmap_heads(&tdo, dout, head_dim, heads, seq, batch, do_str[0], do_str[1], do_str[2], AT_M);
   if (r) return 4000 + r;
-  ATT_DBG("tensor maps built");
   AttnBwdParams p;
   memset(&p, 0, sizeof(p));
   p.hm.q_group_stride = head_map[0]; p.hm.q_off = head_map[1]; p.hm.k_group_stride = head_map[2];
@@ -471,24 +498,8 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
   p.dq = RowAddr{dq, dq_str[0], dq_str[1], dq_str[2]};
   p.dk = RowAddr{dk, dk_str[0], dk_str[1], dk_str[2]};
   p.dv = RowAddr{dv, dv_str[0], dv_str[1], dv_str[2]};
-  RowAddr ro{const_cast<void*>(o), o_str[0], o_str[1], o_str[2]};
-  RowAddr rdo{const_cast<void*>(dout), do_str[0], do_str[1], do_str[2]};
-  const long long rows = (long long)seq * batch * heads;
-  attn_delta_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ro, rdo, delta, seq, batch, heads);
-  ATT_DBG("delta launched");
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_DQ_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  dim3 g1(seq / AT_N, heads / q_per_kv, batch);
-  attn_bwd_dkdv_kernel<<<g1, BW_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
-  ATT_DBG("dkdv launched");
-  dim3 g2(seq / AT_M, heads, batch);
-  attn_bwd_dq_kernel<<<g2, BW_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
-  ATT_DBG("dq launched");
-  return (int)cudaGetLastError();
+  const RowAddr ro{const_cast<void*>(o), o_str[0], o_str[1], o_str[2]};
+  const RowAddr rdo{const_cast<void*>(dout), do_str[0], do_str[1], do_str[2]};
+  return head_dim == 128 ? launch_attn_bwd<128>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream)
+                         : launch_attn_bwd<64>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
 }

@@ -44,16 +44,24 @@ static inline int make_tmap_heads(CUtensorMap* tm, const void* base, int hn, int
   return r == CUDA_SUCCESS ? 0 : (int)r;
 }
 
-// load a [128 rows x 128 hn] tile as two 64-column swizzled boxes
+// load a [128 rows x D hn] tile as D/64 swizzled boxes of 64 columns.  A tile slot in shared memory is always
+// AT_TILE_BYTES (the head_dim-64 instantiations use the first box of a slot only), so the descriptor helpers below and
+// every smem offset are the same for both head dims.
+template <int D = AT_D>
 __device__ __forceinline__ void load_tile(uint8_t* smem_dst, const CUtensorMap* tm, uint64_t* bar, int head, int row0,
                                           int b) {
+  static_assert(D == 64 || D == 128, "head_dim 64 or 128");
   tma_load_4d(smem_dst, tm, bar, 0, head, row0, b);
-  tma_load_4d(smem_dst + AT_HALF_BYTES, tm, bar, 64, head, row0, b);
+  if constexpr (D == 128) tma_load_4d(smem_dst + AT_HALF_BYTES, tm, bar, 64, head, row0, b);
 }
+// bytes one load_tile<D> delivers (the mbarrier's expect_tx)
+template <int D>
+constexpr int at_tile_tx() { return AT_M * D * 2; }
 
 // The same smem tile ([128 rows][2 boxes of 64 hn]) can feed an MMA two ways:
 //  * K-major  : rows = the MMA's M or N index, hn = the reduction dim; k-step `k` covers 16 hn elements
-//  * MN-major : rows = the reduction dim, hn = the MMA's N index (128); k-step `k` covers 16 rows
+//  * MN-major : rows = the reduction dim, hn = the MMA's N index (D: one or two 64-wide atoms, LBO = the box stride);
+//               k-step `k` covers 16 rows
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k) {
   const uint32_t a = tile_addr + (k >> 2) * AT_HALF_BYTES + (k & 3) * 32;
   return make_smem_desc(a, 16, 1024, kSwizzle128B);

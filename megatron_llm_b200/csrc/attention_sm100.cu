@@ -38,6 +38,7 @@ struct AttnParams {
 // =================================================================================================
 // forward
 // =================================================================================================
+template <int D>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -93,22 +94,22 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
   constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, true);   // Q K^T : both K-major
-  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, AT_D, false, true, true);   // P (TMEM) x V (MN-major)
+  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, D, false, true, true);   // P (TMEM) x V (MN-major)
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-      load_tile(sQ, &tmQ, q_full, q_coord, q0, b);
+      mbar_arrive_expect_tx(q_full, at_tile_tx<D>());
+      load_tile<D>(sQ, &tmQ, q_full, q_coord, q0, b);
       for (int t = 0; t < n_tiles; ++t) {
         const int st = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         const int kv0 = (j_lo + t) * AT_N;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
-        load_tile(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], k_coord, kv0, b);
+        mbar_arrive_expect_tx(&k_full[st], at_tile_tx<D>());
+        load_tile<D>(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], k_coord, kv0, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
-        load_tile(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], v_coord, kv0, b);
+        mbar_arrive_expect_tx(&v_full[st], at_tile_tx<D>());
+        load_tile<D>(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], v_coord, kv0, b);
       }
     }
   } else if (warp == 1) {
@@ -120,7 +121,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
         const uint32_t aK = smem_u32(sK + st * AT_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
+        for (int k = 0; k < D / 16; ++k)
           umma_f16_ss<1>(tmem + (st ? TM_S1 : TM_S0), desc_kmajor(aQ, k), desc_kmajor(aK, k), IDESC_S, k != 0);
         umma_commit<1>(&k_empty[st]);
         umma_commit<1>(&s_full[st]);
@@ -184,7 +185,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         const float alpha = grow ? ((m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new)) : 1.f;
         if (grow) { m_used = m_new; l *= alpha; }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < D / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
           tmem_ld_wait();
@@ -230,9 +231,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
     if (row < p.seq) {
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.out_s_stride +
-                            (long long)b * p.out_b_stride + (long long)h * AT_D;
+                            (long long)b * p.out_b_stride + (long long)h * D;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < D / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(tmem + lane_addr + TM_O + c * 32, v);
         tmem_ld_wait();
@@ -274,6 +275,7 @@ constexpr int AT2_THREADS = 384;
 constexpr uint32_t T2_S0 = 0, T2_S1 = 128, T2_O0 = 256, T2_O1 = 384;
 constexpr int AT_FWD2_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;
 
+template <int D>
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -329,23 +331,23 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
   constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, true);
-  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, AT_D, false, true, true);
+  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, D, false, true, true);
 
   if (warp == 0) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, 2 * AT_TILE_BYTES);
-      load_tile(sQ, &tmQ, q_full, q_coord, q0, b);
-      load_tile(sQ + AT_TILE_BYTES, &tmQ, q_full, q_coord, q0 + AT_M, b);
+      mbar_arrive_expect_tx(q_full, 2 * at_tile_tx<D>());
+      load_tile<D>(sQ, &tmQ, q_full, q_coord, q0, b);
+      load_tile<D>(sQ + AT_TILE_BYTES, &tmQ, q_full, q_coord, q0 + AT_M, b);
       for (int t = 0; t < n_b; ++t) {
         const int st = t & 1;
         const uint32_t ph = (t >> 1) & 1;
         const int kv0 = (j_lo + t) * AT_N;
         mbar_wait(&k_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[st], AT_TILE_BYTES);
-        load_tile(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], k_coord, kv0, b);
+        mbar_arrive_expect_tx(&k_full[st], at_tile_tx<D>());
+        load_tile<D>(sK + st * AT_TILE_BYTES, &tmK, &k_full[st], k_coord, kv0, b);
         mbar_wait(&v_empty[st], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[st], AT_TILE_BYTES);
-        load_tile(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], v_coord, kv0, b);
+        mbar_arrive_expect_tx(&v_full[st], at_tile_tx<D>());
+        load_tile<D>(sV + st * AT_TILE_BYTES, &tmV, &v_full[st], v_coord, kv0, b);
       }
     }
   } else if (warp == 1) {
@@ -357,7 +359,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const uint32_t aQ = smem_u32(sQ + x * AT_TILE_BYTES);
         const uint32_t aK = smem_u32(sK + st * AT_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < AT_D / 16; ++k)
+        for (int k = 0; k < D / 16; ++k)
           umma_f16_ss<1>(tmem + (x ? T2_S1 : T2_S0), desc_kmajor(aQ, k), desc_kmajor(aK, k), IDESC_S, k != 0);
         umma_commit<1>(&s_full[x]);
       };
@@ -441,7 +443,7 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         const float alpha = grow ? ((m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new)) : 1.f;
         if (grow) { m_used = m_new; l *= alpha; }
 #pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < D / 32; ++c) {
           uint32_t v[32];
           tmem_ld_32x32(o_addr + c * 32, v);
           tmem_ld_wait();
@@ -488,9 +490,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
     if (row < p.seq) {
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.out_s_stride +
-                            (long long)b * p.out_b_stride + (long long)h * AT_D;
+                            (long long)b * p.out_b_stride + (long long)h * D;
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 0; c < D / 32; ++c) {
         uint32_t v[32];
         tmem_ld_32x32(o_addr + c * 32, v);
         tmem_ld_wait();
@@ -517,23 +519,45 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
+template <int D>
+static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                           cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(attn_fwd2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD2_SMEM);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  static const int force_single = getenv("MLB200_ATTN_FWD1") != nullptr;
+  if (p.seq % (2 * AT_M) == 0 && !force_single) {
+    dim3 grid(p.seq / (2 * AT_M), p.heads, p.batch);
+    attn_fwd2_kernel<D><<<grid, AT2_THREADS, AT_FWD2_SMEM, stream>>>(tq, tk, tv, p);
+  } else {
+    dim3 grid(p.seq / AT_M, p.heads, p.batch);
+    attn_fwd_kernel<D><<<grid, AT_THREADS, AT_FWD_SMEM, stream>>>(tq, tk, tv, p);
+  }
+  return (int)cudaGetLastError();
+}
+
 }  // namespace mlb
 
 // q/k/v described by (base pointer, head stride, seq stride, batch stride) in elements + number of heads in the map;
-// head coordinates come from the group-stride / offset triple (see AttnParams).
+// head coordinates come from the group-stride / offset triple (see AttnParams).  head_dim = 128 or 64.
 extern "C" int mlb_attn_fwd(const void* q, const void* k, const void* v, const long long* q_str, const long long* k_str,
                             const long long* v_str, int q_map_heads, int k_map_heads, int v_map_heads,
                             const int* head_map /* 6 ints */, int q_per_kv, int seq, int batch, int heads, int window,
                             float softmax_scale, void* out, long long out_s_stride, long long out_b_stride, float* lse,
-                            cudaStream_t stream) {
+                            int head_dim, cudaStream_t stream) {
   using namespace mlb;
-  if (seq % AT_M != 0) return -2;
+  if (seq % AT_M != 0 || (head_dim != 64 && head_dim != 128)) return -2;
   CUtensorMap tq, tk, tv;
-  int r = make_tmap_heads(&tq, q, AT_D, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
+  int r = make_tmap_heads(&tq, q, head_dim, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
   if (r) return 1000 + r;
-  r = make_tmap_heads(&tk, k, AT_D, k_map_heads, seq, batch, k_str[0], k_str[1], k_str[2], AT_N);
+  r = make_tmap_heads(&tk, k, head_dim, k_map_heads, seq, batch, k_str[0], k_str[1], k_str[2], AT_N);
   if (r) return 2000 + r;
-  r = make_tmap_heads(&tv, v, AT_D, v_map_heads, seq, batch, v_str[0], v_str[1], v_str[2], AT_N);
+  r = make_tmap_heads(&tv, v, head_dim, v_map_heads, seq, batch, v_str[0], v_str[1], v_str[2], AT_N);
   if (r) return 3000 + r;
   AttnParams p;
   memset(&p, 0, sizeof(p));
@@ -542,21 +566,5 @@ extern "C" int mlb_attn_fwd(const void* q, const void* k, const void* v, const l
   p.q_per_kv = q_per_kv; p.seq = seq; p.batch = batch; p.heads = heads; p.window = window;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.out = out; p.out_s_stride = out_s_stride; p.out_b_stride = out_b_stride; p.lse = lse;
-  static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attn_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD2_SMEM);
-    if (e != cudaSuccess) return (int)e;
-    configured = true;
-  }
-  static const int force_single = getenv("MLB200_ATTN_FWD1") != nullptr;
-  if (seq % (2 * AT_M) == 0 && !force_single) {
-    dim3 grid(seq / (2 * AT_M), heads, batch);
-    attn_fwd2_kernel<<<grid, AT2_THREADS, AT_FWD2_SMEM, stream>>>(tq, tk, tv, p);
-  } else {
-    dim3 grid(seq / AT_M, heads, batch);
-    attn_fwd_kernel<<<grid, AT_THREADS, AT_FWD_SMEM, stream>>>(tq, tk, tv, p);
-  }
-  return (int)cudaGetLastError();
+  return head_dim == 128 ? launch_attn_fwd<128>(tq, tk, tv, p, stream) : launch_attn_fwd<64>(tq, tk, tv, p, stream);
 }

@@ -262,7 +262,7 @@ class ParallelAttention(MegatronModule):
                 if self.sliding_window_size is not None and sq > self.sliding_window_size:
                     window = self.sliding_window_size
                 context_layer = attention_sm100.packed_attention(mixed, self.num_kv_heads_per_partition,
-                                                                 self.q_per_kv, window, None)
+                                                                 self.q_per_kv, window, None, hn)
                 return self.dense(context_layer)
             qkv = mixed.view(sq, b, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn)
             if self.q_per_kv == 1:

@@ -8,6 +8,13 @@ import torch
 from . import _ext
 
 
+def _head_dim_ok(hn: int) -> bool:
+    """128 always; 64 (Falcon, GPT-2 style models) is compiled in but stays opt-in (``MLB200_ATTN_HD64=1``) until its
+    instantiations have been validated on hardware with tools/profiling/attn_check.py -- until then those models use
+    the FA-2 library fallback in ops/attention.py."""
+    return hn == 128 or (hn == 64 and os.environ.get("MLB200_ATTN_HD64", "0") == "1")
+
+
 def supported(q, k, v, causal, window, dropout_p) -> bool:
     if os.environ.get("MLB200_ATTN", "1") == "0":
         return False
@@ -18,7 +25,7 @@ def supported(q, k, v, causal, window, dropout_p) -> bool:
     if not hasattr(mod, "attn_fwd"):
         return False
     hn = q.size(-1)
-    return (q.dtype == torch.bfloat16 and hn == 128 and dropout_p == 0.0 and causal
+    return (q.dtype == torch.bfloat16 and _head_dim_ok(hn) and dropout_p == 0.0 and causal
             and q.size(1) == k.size(1) and q.size(1) % 128 == 0 and q.size(2) % k.size(2) == 0)
 
 
@@ -53,7 +60,7 @@ def packed_supported(mixed, nkv, g, hn, dropout_p) -> bool:
     """``mixed`` = QKV projection output [s, b, nkv * (g + 2) * hn] (per KV group: g query heads, then k, then v)."""
     if os.environ.get("MLB200_ATTN", "1") == "0" or os.environ.get("MLB200_ATTN_PACKED", "1") == "0":
         return False
-    if not (mixed.is_cuda and mixed.dtype == torch.bfloat16 and hn == 128 and dropout_p == 0.0
+    if not (mixed.is_cuda and mixed.dtype == torch.bfloat16 and _head_dim_ok(hn) and dropout_p == 0.0
             and mixed.dim() == 3 and mixed.stride(2) == 1 and mixed.size(0) % 128 == 0):
         return False
     try:
@@ -64,27 +71,29 @@ def packed_supported(mixed, nkv, g, hn, dropout_p) -> bool:
 
 class _PackedAttnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, mixed, nkv, g, window, scale):
+    def forward(ctx, mixed, nkv, g, window, scale, hn):
         mod = _ext.load()
-        out, lse = mod.attn_fwd_packed(mixed, nkv, g, -1 if window is None else int(window), float(scale))
+        out, lse = mod.attn_fwd_packed(mixed, nkv, g, -1 if window is None else int(window), float(scale), hn)
         _ext.count()
         ctx.save_for_backward(mixed, out, lse)
-        ctx.cfg = (nkv, g, window, scale)
+        ctx.cfg = (nkv, g, window, scale, hn)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         mixed, out, lse = ctx.saved_tensors
-        nkv, g, window, scale = ctx.cfg
+        nkv, g, window, scale, hn = ctx.cfg
         mod = _ext.load()
         d = dout if dout.stride(-1) == 1 else dout.contiguous()
-        dmixed = mod.attn_bwd_packed(d, mixed, out, lse, nkv, g, -1 if window is None else int(window), float(scale))
+        dmixed = mod.attn_bwd_packed(d, mixed, out, lse, nkv, g, -1 if window is None else int(window), float(scale),
+                                     hn)
         _ext.count(3)
-        return dmixed, None, None, None, None
+        return dmixed, None, None, None, None, None
 
 
-def packed_attention(mixed, nkv, g, window=None, scale=None):
-    """Causal attention straight from the packed (already rotated) QKV buffer -> context [s, b, nkv * g * 128]."""
+def packed_attention(mixed, nkv, g, window=None, scale=None, hn=None):
+    """Causal attention straight from the packed (already rotated) QKV buffer -> context [s, b, nkv * g * hn]."""
     import math
-    scale = scale if scale is not None else 1.0 / math.sqrt(128)
-    return _PackedAttnFn.apply(mixed, nkv, g, window, scale)
+    hn = hn if hn is not None else mixed.size(-1) // (nkv * (g + 2))
+    scale = scale if scale is not None else 1.0 / math.sqrt(hn)
+    return _PackedAttnFn.apply(mixed, nkv, g, window, scale, hn)
