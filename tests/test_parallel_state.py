@@ -71,3 +71,37 @@ def _bad_init(rank, world):
 
 def test_invalid_sizes_raise():
     run_distributed(_bad_init, 2)
+
+
+def test_fused_tp_graph_replay_bookkeeping():
+    """Host side of replaying fused TP kernels from a CUDA graph (parallel/symm.py): the offsets written before a
+    replay re-base the captured epochs onto the live counters, the reduce-scatter offset stays even (the receive-slot
+    parity is frozen in the captured arguments) and the counters advance by what one replay executes."""
+    from megatron_llm_b200.parallel.symm import TPCommunicator
+
+    class FakeMod:
+        def __init__(self):
+            self.calls = []
+
+        def comm_set_state(self, state, a, b, c):
+            self.calls.append((a, b, c))
+
+    comm = object.__new__(TPCommunicator)
+    comm.mod, comm.state = FakeMod(), None
+    comm.ag_epoch, comm.rs_epoch, comm.rs_arrived_total = 10, 7, 700
+    before = comm.counters()
+    # a capture pass "issues" 4 all-gather GEMMs and 3 reduce-scatter GEMMs worth 96 arrivals each
+    comm.ag_epoch += 4
+    comm.rs_epoch += 3
+    comm.rs_arrived_total += 288
+    advance = comm.end_capture(before)
+    assert advance == (4, 3, 288) and comm.counters() == before            # rewound: the capture did not execute
+    comm.begin_replay(before, advance)
+    assert comm.mod.calls[-1] == (0, 0, 0) and comm.counters() == (14, 10, 988)
+    comm.begin_replay(before, advance)                                      # rs delta would be 3 -> one epoch skipped
+    assert comm.mod.calls[-1] == (4, 4, 288) and comm.counters() == (18, 14, 1276)
+    comm.rs_epoch += 1                                                      # an eager reduce-scatter in between
+    comm.rs_arrived_total += 96
+    comm.begin_replay(before, advance)
+    a, b, c = comm.mod.calls[-1]
+    assert b % 2 == 0 and (a, c) == (8, 672) and comm.rs_epoch == before[1] + b + 3
