@@ -136,6 +136,50 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
                           (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
 }
 
+// Push variant of the all-gather -> GEMM (opt-in, MLB200_AG_PUSH): `gathered` is this rank's symmetric gather buffer
+// of the call's parity viewed as [M, K]; the pusher CTAs store `x_shard` into everybody's buffer (push_dst[d]) and
+// count pieces into sig[d]; the GEMM reads A from `gathered`.
+static void fused_ag_gemm_push(torch::Tensor& gathered, const torch::Tensor& x_shard, const torch::Tensor& weight,
+                               torch::Tensor& out, bool b_mn, const std::vector<int64_t>& push_dst,
+                               const std::vector<int64_t>& sig, torch::Tensor& done_counter, int64_t rows_per_rank,
+                               int64_t pad_local, const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world,
+                               int64_t epoch, int64_t num_comm_ctas, int64_t sms, int64_t state_ptr) {
+  c10::cuda::CUDAGuard guard(gathered.device());
+  const int M = gathered.size(0), K = gathered.size(1);
+  const int N = b_mn ? weight.size(1) : weight.size(0);
+  TORCH_CHECK(gathered.is_contiguous() && x_shard.is_contiguous() && out.stride(1) == 1 && weight.stride(1) == 1);
+  TORCH_CHECK(x_shard.size(0) == rows_per_rank && x_shard.size(1) == K && M == rows_per_rank * world);
+  TORCH_CHECK(rows_per_rank % mlb::GEMM_BLOCK_M == 0 && K % 8 == 0 && N % 8 == 0);
+  TORCH_CHECK((uintptr_t)x_shard.data_ptr() % 16 == 0 && num_comm_ctas >= 2 && num_comm_ctas % 2 == 0);
+  mlb::GemmComm c;
+  memset(&c, 0, sizeof(c));
+  c.rank = rank; c.world = world; c.epoch = epoch;
+  c.num_comm_ctas = (int)num_comm_ctas;
+  c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
+  c.m_rotate_blocks = (int)(rank * rows_per_rank / mlb::GEMM_BLOCK_M);
+  c.state = reinterpret_cast<const int*>(state_ptr);
+  c.ag_push = 1;
+  c.ag_local_src = x_shard.data_ptr();
+  for (int i = 0; i < world; ++i) {
+    c.ag_push_dst[i] = reinterpret_cast<void*>(push_dst[i]);
+    c.ag_sig_peer[i] = reinterpret_cast<int*>(sig[i]);
+  }
+  c.ag_dst = gathered.data_ptr();
+  c.ag_rows_per_rank = rows_per_rank;
+  c.ag_row_bytes = K * 2;
+  c.ag_done_counter = done_counter.data_ptr<int>();
+  fill_pads(c, pad_local, pad_peers);
+  static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;
+  if (!force_1cta && rows_per_rank % 256 == 0 && N >= 256 && (out.stride(0) * 2) % 16 == 0) {
+    CHK(mlb_gemm_bf16_2cta_ag(gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
+                              (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(),
+                              cur()));
+    return;
+  }
+  CHK(mlb_gemm_bf16_fused(mlb::MODE_AG_GEMM, gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
+                          (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
+}
+
 // rs_out[M/world, N] = reduce_scatter(x[M, K] @ W^T or @ W) over the group; tiles travel through rs_dst[] (peer slots).
 // ``prev_total``: cumulative arrivals every source had delivered per destination before this call; returns the new
 // cumulative count (the tile granularity depends on the kernel variant that is chosen here).
@@ -225,6 +269,7 @@ void register_comm(pybind11::module_& m) {
   m.def("comm_copy2", &comm_copy2);
   m.def("comm_set_state", &comm_set_state);
   m.def("fused_ag_gemm", &fused_ag_gemm);
+  m.def("fused_ag_gemm_push", &fused_ag_gemm_push);
   m.def("fused_gemm_rs", &fused_gemm_rs);
   m.def("dp_reduce", &dp_reduce);
 }

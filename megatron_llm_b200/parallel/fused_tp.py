@@ -49,9 +49,11 @@ def active_row(x_full: torch.Tensor, weight: torch.Tensor) -> bool:
             and n <= min(_COMM.max_n, _COMM.max_k) and weight.dtype == torch.bfloat16)
 
 
-def ag_gemm(x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None):
-    """all-gather(x_shard along dim 0) then GEMM.  Returns (out2d [s*b, N], gathered input)."""
-    return _COMM.ag_gemm(x_shard, weight, transposed_weight, out=out)
+def ag_gemm(x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None,
+            keep: bool = True):
+    """all-gather(x_shard along dim 0) then GEMM.  Returns (out2d [s*b, N], gathered input); ``keep=False`` if the
+    gathered input is consumed before the next fused call (lets the push variant skip a copy)."""
+    return _COMM.ag_gemm(x_shard, weight, transposed_weight, out=out, keep=keep)
 
 
 def gemm_rs(x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):

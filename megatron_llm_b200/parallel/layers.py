@@ -347,7 +347,7 @@ class _RowLinearFusedRS(torch.autograd.Function):
         from . import fused_tp
         input, weight = ctx.saved_tensors
         # dX = AG(dY) @ W ; dW = AG(dY)^T @ X
-        gi2d, total_g = fused_tp.ag_gemm(grad_output.contiguous(), weight, transposed_weight=True)
+        gi2d, total_g = fused_tp.ag_gemm(grad_output.contiguous(), weight, transposed_weight=True, keep=False)
         grad_input = gi2d.view(*input.shape)
         grad_weight = _wgrad(total_g.reshape(-1, total_g.size(-1)), input.reshape(-1, input.size(-1)), weight,
                              ctx.gradient_accumulation_fusion)

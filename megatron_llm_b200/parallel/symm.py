@@ -49,7 +49,8 @@ class TPCommunicator:
       pad  [64] int32                                    -- ready / ack / arrived / free signals
     """
 
-    def __init__(self, group, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 8):
+    def __init__(self, group, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 8,
+                 ag_k: Optional[int] = None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -74,6 +75,18 @@ class TPCommunicator:
         self.ag_epoch = 0
         self.rs_epoch = 0
         self.rs_arrived_total = 0
+        # push variant of the all-gather (opt-in): two parities of a symmetric gather buffer + arrival counters
+        self.push = os.environ.get("MLB200_AG_PUSH", "0") == "1"
+        if self.push:
+            self.ag_k = ag_k or max_k
+            self.agbuf, self.h_agbuf = _alloc_symmetric(2 * self.world * max_rows_per_rank * self.ag_k, torch.bfloat16,
+                                                        self.device, group)
+            self.agsig, self.h_agsig = _alloc_symmetric(2 * max(max_chunks, 1), torch.int32, self.device, group)
+            self.agsig.zero_()
+            self.agbuf_ptrs = [int(p) for p in self.h_agbuf.buffer_ptrs]
+            self.agsig_ptrs = [int(p) for p in self.h_agsig.buffer_ptrs]
+            self.ag_done = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.push_ctas = int(os.environ.get("MLB200_AG_PUSH_CTAS", "8"))
         # offsets that calls captured in a CUDA graph add to their (frozen) epoch arguments -- see replay_offsets()
         self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
@@ -85,14 +98,20 @@ class TPCommunicator:
         return (self.enabled and rows_per_rank % 128 == 0 and rows_per_rank <= self.max_rows and k % 8 == 0
                 and n % 8 == 0)
 
-    def ag_gemm(self, x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None):
-        """x_shard [m, ..., K] (this rank's rows) -> (out [world*m*..., N], gathered [world*m, ..., K])."""
+    def ag_gemm(self, x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, out=None,
+                keep: bool = True):
+        """x_shard [m, ..., K] (this rank's rows) -> (out [world*m*..., N], gathered [world*m, ..., K]).
+
+        ``keep=False`` says the caller consumes ``gathered`` before the next call on this communicator (the push
+        variant then returns a view of its symmetric buffer instead of a copy)."""
         lead = x_shard.shape[:-1]
         K = x_shard.size(-1)
         x2d = x_shard.reshape(-1, K)
         m = x2d.size(0)
         N = weight.size(1) if transposed_weight else weight.size(0)
         assert m <= self.max_rows and K <= self.max_k and m % 128 == 0, (m, K, self.max_rows, self.max_k)
+        if self.push and K <= self.ag_k:
+            return self._ag_gemm_push(x2d, weight, transposed_weight, out, keep, lead, m, K, N)
         # publish my shard (stream-ordered before the kernel; the previous call's kernel only retired after every
         # peer had acknowledged reading the old content)
         gathered = torch.empty((self.world * m, K), dtype=torch.bfloat16, device=self.device)
@@ -113,6 +132,27 @@ class TPCommunicator:
                                self.read_counters, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
                                self.ag_epoch, self.num_comm_ctas, 0, self._state_ptr())
         _ext.count()
+        return out, gathered.view(self.world * lead[0], *lead[1:], K)
+
+    def _ag_gemm_push(self, x2d, weight, transposed_weight, out, keep, lead, m, K, N):
+        self.ag_epoch += 1
+        parity = self.ag_epoch % 2
+        buf_elems = self.world * self.max_rows * self.ag_k           # one parity of the gather buffer
+        sig_ints = self.agsig.numel() // 2
+        view = self.agbuf[parity * buf_elems: parity * buf_elems + self.world * m * K].view(self.world * m, K)
+        push_dst = [p + 2 * parity * buf_elems for p in self.agbuf_ptrs]
+        sig = [p + 4 * parity * sig_ints for p in self.agsig_ptrs]
+        if out is None:
+            out = torch.empty((self.world * m, N), dtype=torch.bfloat16, device=self.device)
+        x = x2d.contiguous()
+        if x.data_ptr() % 16:
+            x = x.clone()
+        w = weight if weight.stride(-1) == 1 else weight.contiguous()
+        self.mod.fused_ag_gemm_push(view, x, w, out, transposed_weight, push_dst, sig, self.ag_done, m,
+                                    self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.ag_epoch,
+                                    self.push_ctas, 0, self._state_ptr())
+        _ext.count()
+        gathered = view.clone() if keep else view
         return out, gathered.view(self.world * lead[0], *lead[1:], K)
 
     def gemm_rs(self, x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
@@ -163,6 +203,8 @@ class TPCommunicator:
         handshake only needs monotonic epochs.)"""
         if (self.rs_epoch - before[1]) % 2:
             self.rs_epoch += 1
+        if getattr(self, "push", False) and (self.ag_epoch - before[0]) % 2:   # (push all-gather: parity is frozen too)
+            self.ag_epoch += 1
         self.mod.comm_set_state(self.state, self.ag_epoch - before[0], self.rs_epoch - before[1],
                                 self.rs_arrived_total - before[2])
         self.ag_epoch += advance[0]
@@ -242,7 +284,8 @@ def bind_tp_communicator(args) -> Optional[TPCommunicator]:
     vocab_shard = getattr(args, "padded_vocab_size", 0) // tp
     max_n = max(args.hidden_size, ffn // tp, vocab_shard)
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), rows, max_k, max_n,
-                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")))   # upper bound: the launcher picks per shape
+                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")),   # upper bound: picked per shape
+                          ag_k=args.hidden_size)          # every all-gathered operand has K = hidden size
     fused_tp.bind(comm)
     return comm
 

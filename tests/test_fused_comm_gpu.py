@@ -69,6 +69,26 @@ def test_fused_tp_kernels_streaming_pullers_match_nccl():
     run_distributed(_tp_kernels_streaming, 2, backend="nccl")
 
 
+def _tp_kernels_push(rank, world):
+    os.environ["MLB200_AG_PUSH"] = "1"       # read when the communicator is built
+    _tp_kernels(rank, world)
+
+
+def test_fused_tp_kernels_push_all_gather_match_nccl():
+    """Same checks with the push variant of the all-gather (owner stores its shard into every rank's symmetric
+    gather buffer; MLB200_AG_PUSH)."""
+    run_distributed(_tp_kernels_push, 2, backend="nccl")
+
+
+def _tp_kernels_push_in_graph(rank, world):
+    os.environ["MLB200_AG_PUSH"] = "1"
+    _tp_kernels_in_graph(rank, world)
+
+
+def test_fused_tp_kernels_push_replay_in_cuda_graph():
+    run_distributed(_tp_kernels_push_in_graph, 2, backend="nccl")
+
+
 def _tp_kernels_with_skew(rank, world):
     """Shake the flag protocol: every rank delays its launches by a different, changing amount (device-side spin on the
     launching stream), so the READY / ACK / ARRIVED / FREE handshakes see peers that are early, late, or a whole call
