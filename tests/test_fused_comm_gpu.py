@@ -9,6 +9,11 @@ from tests.dist_utils import run_distributed
 
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
 
+# Variants that were written after the last hardware session of the round they were added in: they run only on request
+# (MLB200_TEST_EXPERIMENTAL=1) until they have passed on a GPU box once, then the marker is dropped.
+experimental = pytest.mark.skipif(os.environ.get("MLB200_TEST_EXPERIMENTAL", "0") != "1",
+                                  reason="not yet validated on hardware; set MLB200_TEST_EXPERIMENTAL=1")
+
 
 def _tp_kernels(rank, world):
     from megatron_llm_b200.parallel import state as ps
@@ -64,6 +69,7 @@ def _tp_kernels_streaming(rank, world):
     _tp_kernels(rank, world)
 
 
+@experimental
 def test_fused_tp_kernels_streaming_pullers_match_nccl():
     """Same checks with the all-gather pieces dealt round-robin to all puller CTAs (MLB200_AG_STREAM)."""
     run_distributed(_tp_kernels_streaming, 2, backend="nccl")
@@ -74,6 +80,7 @@ def _tp_kernels_push(rank, world):
     _tp_kernels(rank, world)
 
 
+@experimental
 def test_fused_tp_kernels_push_all_gather_match_nccl():
     """Same checks with the push variant of the all-gather (owner stores its shard into every rank's symmetric
     gather buffer; MLB200_AG_PUSH)."""
@@ -85,6 +92,7 @@ def _tp_kernels_push_in_graph(rank, world):
     _tp_kernels_in_graph(rank, world)
 
 
+@experimental
 def test_fused_tp_kernels_push_replay_in_cuda_graph():
     run_distributed(_tp_kernels_push_in_graph, 2, backend="nccl")
 
@@ -128,6 +136,7 @@ def _tp_kernels_with_skew(rank, world):
     ps.destroy_model_parallel()
 
 
+@experimental
 def test_fused_tp_kernels_tolerate_rank_skew():
     run_distributed(_tp_kernels_with_skew, 2, backend="nccl")
 
