@@ -33,6 +33,7 @@ MODELS = {
     "llama2-70b": (80, 8192, 64, 8, 28672, 32000),
     "mistral-7b": (32, 4096, 32, 8, 14336, 32000),
     "llama2-tiny": (4, 1024, 8, 8, 2816, 32000),
+    "falcon-40b": (60, 8192, 128, 8, 32768, 65024),
 }
 
 
@@ -47,6 +48,12 @@ def parse():
     p.add_argument("--global_batch", type=int, default=8)
     p.add_argument("--micro_batch", type=int, default=1)
     p.add_argument("--layers", type=int, default=None, help="DEV ONLY: override layer count (invalidates the number)")
+    # the headline config is TP = #GPUs; the other BASELINE.json configs (Mistral TP2xDP4, Falcon-40B TP4xPP2,
+    # Llama-2-70B TP8 + recompute) are reachable with these
+    p.add_argument("--tp", type=int, default=None, help="tensor-parallel size (default: --gpus)")
+    p.add_argument("--pp", type=int, default=1, help="pipeline-parallel size; data-parallel = gpus / (tp * pp)")
+    p.add_argument("--recompute", action="store_true", help="full activation recompute (uniform, 1 layer per chunk)")
+    p.add_argument("--dist_opt", action="store_true", help="ZeRO-1 distributed optimizer over the DP group")
     p.add_argument("--no_e2e", action="store_true")
     p.add_argument("--graph", type=int, default=-1,
                    help="1/0: replay each micro-batch from a CUDA graph (default: on when TP > 1, where the step is "
@@ -104,27 +111,59 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def parallel_layout(a, n_gpus):
+    """(tp, pp, dp) for this run: TP = #GPUs unless --tp / --pp say otherwise."""
+    pp = getattr(a, "pp", 1) or 1
+    tp = getattr(a, "tp", None) or max(n_gpus // pp, 1)
+    assert n_gpus % (tp * pp) == 0, f"--gpus {n_gpus} is not a multiple of tp*pp = {tp * pp}"
+    return tp, pp, n_gpus // (tp * pp)
+
+
+def parallelism_string(a, n_gpus):
+    tp, pp, dp = parallel_layout(a, n_gpus)
+    s = f"tp{tp}" + ("+sp" if tp > 1 else "")
+    if pp > 1:
+        s += f"+pp{pp}"
+    if dp > 1:
+        s += f"+dp{dp}" + ("(zero1)" if getattr(a, "dist_opt", False) else "")
+    if getattr(a, "recompute", False):
+        s += "+recompute"
+    return s
+
+
 def megatron_argv(a, n_gpus):
     layers, hidden, heads, kv, ffn, vocab = MODELS[a.model]
     if a.layers:
         layers = a.layers
-    argv = ["--model_name", "mistral" if a.model.startswith("mistral") else "llama2",
+    tp, pp = parallel_layout(a, n_gpus)[:2]
+    family = a.model.split("-")[0].rstrip("2")          # llama / mistral / falcon
+    argv = ["--model_name", {"llama": "llama2", "mistral": "mistral", "falcon": "falcon"}[family],
             "--num_layers", str(layers), "--hidden_size", str(hidden), "--num_attention_heads", str(heads),
             "--num_attention_heads_kv", str(kv), "--ffn_hidden_size", str(ffn), "--seq_length", str(a.seq),
             "--max_position_embeddings", str(a.seq), "--micro_batch_size", str(a.micro_batch),
-            "--global_batch_size", str(a.global_batch), "--tensor_model_parallel_size", str(n_gpus),
-            "--pipeline_model_parallel_size", "1", "--train_iters", "1000000", "--lr", "1e-5", "--min_lr", "1e-6",
+            "--global_batch_size", str(a.global_batch), "--tensor_model_parallel_size", str(tp),
+            "--pipeline_model_parallel_size", str(pp), "--train_iters", "1000000", "--lr", "1e-5", "--min_lr", "1e-6",
             "--lr_decay_style", "cosine", "--weight_decay", "0.1", "--clip_grad", "1.0", "--adam_beta1", "0.9",
-            "--adam_beta2", "0.95", "--adam_eps", "1e-5", "--bf16", "--use_flash_attn", "--use_rms_norm",
-            "--glu_activation", "swiglu", "--no_tie_embed_logits", "--position_embedding_type", "rotary",
+            "--adam_beta2", "0.95", "--adam_eps", "1e-5", "--bf16", "--use_flash_attn",
+            "--position_embedding_type", "rotary",
             "--hidden_dropout", "0.0", "--attention_dropout", "0.0", "--layernorm_epsilon", "1e-5",
             "--no_bias_gelu_fusion", "--no_bias_dropout_fusion", "--log_interval", "1000000", "--eval_iters", "0",
             "--eval_interval", "1000000", "--num_workers", "0", "--seed", "1234"]
-    if n_gpus > 1:
+    if family == "falcon":      # parallel attention + MLP, two layernorms, GELU MLP, tied embeddings, MQA/GQA
+        argv += ["--parallel_attn", "--parallel_layernorm"]
+    else:
+        argv += ["--use_rms_norm", "--glu_activation", "swiglu", "--no_tie_embed_logits"]
+    if tp > 1:
         argv.append("--sequence_parallel")
-    if a.model.startswith("mistral"):
+    if family == "mistral":
         argv += ["--sliding_window_size", "4096"]
-    use_graph = a.graph == 1 or (a.graph == -1 and n_gpus > 1 and os.environ.get("MLB200_BENCH_GRAPH", "1") == "1")
+    if getattr(a, "recompute", False):
+        argv += ["--recompute_granularity", "full", "--recompute_method", "uniform", "--recompute_num_layers", "1"]
+    if getattr(a, "dist_opt", False):
+        argv.append("--use_distributed_optimizer")
+    graph = getattr(a, "graph", -1)
+    use_graph = graph == 1 or (graph == -1 and tp > 1 and tp == n_gpus and not getattr(a, "recompute", False)
+                                 and os.environ.get("MLB200_BENCH_GRAPH", "1") == "1")
     if use_graph:
         argv += ["--cuda_graph_microbatch"]
     return argv, vocab
@@ -257,7 +296,7 @@ def run_ours(a):
                "impl": "ours",
                "config": {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
                           "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
-                          "parallelism": f"tp{a.gpus}" + ("+sp" if a.gpus > 1 else ""),
+                          "parallelism": parallelism_string(a, a.gpus),
                           "cuda_graph_microbatch": bool(getattr(args, "cuda_graph_microbatch", False)),
                           "tp_comm": ("n/a" if a.gpus == 1 else "fused GEMM+collective kernels over peer memory"
                                       if _fused_tp_active() else
@@ -279,6 +318,11 @@ def run_ours(a):
 
 
 def run_reference(a):
+    tp, pp, dp = parallel_layout(a, a.gpus)
+    if (tp, pp) != (a.gpus, 1) or a.recompute or a.dist_opt or a.model.startswith("falcon"):
+        print(json.dumps({"impl": "reference", "unavailable": "the reference arm drives the headline configuration only "
+                          "(Llama/Mistral, TP = #GPUs, no recompute)"}))
+        return
     ref_root = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref_root, "megatron")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/megatron is missing (reference not installed)"}))

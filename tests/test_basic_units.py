@@ -116,3 +116,41 @@ def test_layernorm_order():
     from tests.dist_utils import run_distributed
     run_distributed(_layernorm_order, 1)
     run_distributed(_post_ln, 1)
+
+
+def test_bench_presets_build_valid_arguments(monkeypatch):
+    """bench.py's argument builder for the headline run (TP = #GPUs) and for the other BASELINE.json configurations
+    must produce flag lists that the framework's parser and validator accept."""
+    import argparse
+    import bench
+    import finetune
+    from megatron_llm_b200.arguments import parse_args, validate_args
+
+    def ns(**kw):
+        base = dict(model="llama2-7b", layers=None, seq=4096, micro_batch=1, global_batch=8, graph=-1, tp=None, pp=1,
+                    recompute=False, dist_opt=False)
+        base.update(kw)
+        return argparse.Namespace(**base)
+
+    cases = [
+        (ns(), 1, "tp1", (1, 1, 1)),
+        (ns(), 8, "tp8+sp", (8, 1, 1)),
+        (ns(model="mistral-7b", tp=2, dist_opt=True), 8, "tp2+sp+dp4(zero1)", (2, 1, 4)),
+        (ns(model="falcon-40b", tp=4, pp=2, global_batch=16), 8, "tp4+sp+pp2", (4, 2, 1)),
+        (ns(model="llama2-70b", recompute=True), 8, "tp8+sp+recompute", (8, 1, 1)),
+    ]
+    for a, gpus, name, layout in cases:
+        assert bench.parallel_layout(a, gpus) == layout
+        assert bench.parallelism_string(a, gpus) == name
+        argv, vocab = bench.megatron_argv(a, gpus)
+        monkeypatch.setenv("WORLD_SIZE", str(gpus))
+        monkeypatch.setenv("RANK", "0")
+        args = parse_args(finetune.extra_args, False, args_list=argv + ["--tokenizer_type", "NullTokenizer",
+                                                                        "--vocab_file", str(vocab), "--data_type",
+                                                                        "synthetic"])
+        if not hasattr(args, "data_parallel_size"):
+            args = validate_args(args, {})
+        assert args.tensor_model_parallel_size == layout[0] and args.pipeline_model_parallel_size == layout[1]
+        assert args.data_parallel_size == layout[2]
+        assert bool(getattr(args, "cuda_graph_microbatch", False)) == (layout[0] > 1 and layout[0] == gpus
+                                                                        and not a.recompute)
