@@ -65,7 +65,7 @@ def main():
             res["gemm_ms"] = timeit(gemm)
             res["nccl_ms"] = timeit(lambda: dist.all_gather_into_tensor(full, x, group=group))
             res["nccl_plus_gemm_ms"] = timeit(lambda: (dist.all_gather_into_tensor(full, x, group=group), gemm()))
-            res["fused_ms"] = timeit(lambda: comm.ag_gemm(x, w, tw, out=out))
+            res["fused_ms"] = timeit(lambda: comm.ag_gemm(x, w, tw, out=out, keep=not tw))   # bwd consumes the gather at once
         else:
             a = torch.randn(seq, K, device=dev, dtype=bf)
             part = torch.empty(seq, N, device=dev, dtype=bf)
