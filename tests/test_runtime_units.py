@@ -1,0 +1,186 @@
+"""Unit tests of the small runtime components that the end-to-end tests only touch indirectly: micro-batch calculators,
+LR / weight-decay scheduler, dynamic loss scaler, data samplers, beam hypotheses, timers, signal handler, gradient
+clipping (CPU path).  (The reference ships no tests for these)"""
+import math
+import os
+import signal
+
+import pytest
+import torch
+
+os.environ.setdefault("MLB200_FORCE_CPU", "1")
+
+
+# ----------------------------------------------------------------------------------------------- micro-batches
+def test_constant_and_rampup_microbatch_calculators():
+    from megatron_llm_b200.microbatches import ConstantNumMicroBatches, RampupBatchsizeNumMicroBatches
+    c = ConstantNumMicroBatches(global_batch_size=64, micro_batch_size=2, data_parallel_size=4)
+    assert c.get() == 8 and c.get_current_global_batch_size() == 64
+    with pytest.raises(AssertionError):
+        ConstantNumMicroBatches(65, 2, 4)
+    # 16 -> 64 in steps of 16 over 300 samples: 3 increments, 100 samples each
+    r = RampupBatchsizeNumMicroBatches(16, 16, 300, 64, micro_batch_size=2, data_parallel_size=4)
+    seen = []
+    for consumed in (0, 99, 100, 199, 200, 299, 300, 10_000):
+        r.update(consumed, True)
+        seen.append((r.get_current_global_batch_size(), r.get()))
+    assert seen == [(16, 2), (16, 2), (32, 4), (32, 4), (48, 6), (48, 6), (64, 8), (64, 8)]
+
+
+# ----------------------------------------------------------------------------------------------- LR / WD schedule
+class _Opt:
+    def __init__(self):
+        self.param_groups = [{"lr": 0.0, "weight_decay": 0.0}, {"lr": 0.0, "weight_decay": 0.0, "lr_mult": 2.0,
+                                                                 "wd_mult": 0.0}]
+
+
+@pytest.mark.parametrize("style", ["constant", "linear", "cosine", "inverse-square-root"])
+def test_lr_schedules(style):
+    from megatron_llm_b200.optimizer_param_scheduler import OptimizerParamScheduler
+    opt = _Opt()
+    s = OptimizerParamScheduler(opt, max_lr=1.0, min_lr=0.1, lr_warmup_steps=10, lr_decay_steps=110,
+                                lr_decay_style=style, start_wd=0.0, end_wd=0.1, wd_incr_steps=100,
+                                wd_incr_style="linear")
+    assert opt.param_groups[0]["lr"] == 0.0
+    s.step(5)
+    assert opt.param_groups[0]["lr"] == pytest.approx(0.5) and opt.param_groups[1]["lr"] == pytest.approx(1.0)
+    assert opt.param_groups[0]["weight_decay"] == pytest.approx(0.005) and opt.param_groups[1]["weight_decay"] == 0.0
+    s.step(5)                                                        # end of warm-up
+    assert opt.param_groups[0]["lr"] == pytest.approx(1.0)
+    s.step(50)                                                       # half way through the decay
+    lr = opt.param_groups[0]["lr"]
+    expect = {"constant": 1.0, "linear": 0.55, "cosine": 0.1 + 0.9 * 0.5 * (math.cos(math.pi * 0.5) + 1.0),
+              "inverse-square-root": max(0.1, 10 ** 0.5 / 60 ** 0.5)}[style]
+    assert lr == pytest.approx(expect)
+    s.step(1000)
+    assert opt.param_groups[0]["lr"] == pytest.approx(1.0 if style == "constant" else 0.1)
+    assert opt.param_groups[0]["weight_decay"] == pytest.approx(0.1)
+    # state round trip
+    sd = s.state_dict()
+    s2 = OptimizerParamScheduler(_Opt(), 1.0, 0.1, 10, 110, style, 0.0, 0.1, 100, "linear")
+    s2.load_state_dict(sd)
+    assert s2.num_steps == s.num_steps and s2.get_lr() == pytest.approx(s.get_lr())
+
+
+# ----------------------------------------------------------------------------------------------- loss scaler
+def test_dynamic_grad_scaler_backoff_growth_hysteresis():
+    from megatron_llm_b200.optimizer.grad_scaler import ConstantGradScaler, DynamicGradScaler
+    s = DynamicGradScaler(initial_scale=1024.0, min_scale=1.0, growth_factor=2.0, backoff_factor=0.5,
+                          growth_interval=3, hysteresis=2)
+    s.update(True)                        # first overflow is absorbed by the hysteresis
+    assert s.scale.item() == 1024.0
+    s.update(True)
+    assert s.scale.item() == 512.0
+    s.update(True)                        # hysteresis stays exhausted until a growth interval completes
+    assert s.scale.item() == 256.0
+    for _ in range(3):
+        s.update(False)
+    assert s.scale.item() == 512.0
+    s.update(True)                        # hysteresis was re-armed by the growth
+    assert s.scale.item() == 512.0
+    for _ in range(20):
+        s.update(True)
+    assert s.scale.item() == 1.0          # clamped at min_scale
+    assert s.inv_scale.item() == 1.0
+    sd = s.state_dict()
+    t = DynamicGradScaler(1024.0, 1.0, 2.0, 0.5, 3, 2)
+    t.load_state_dict(sd)
+    assert t.scale.item() == 1.0 and t._growth_tracker == s._growth_tracker
+    c = ConstantGradScaler(8.0)
+    c.update(True)
+    assert c.scale.item() == 8.0
+
+
+# ----------------------------------------------------------------------------------------------- samplers
+def test_sequential_sampler_shards_and_resumes():
+    from megatron_llm_b200.data.data_samplers import MegatronPretrainingSampler
+    per_rank = [list(MegatronPretrainingSampler(22, 0, micro_batch_size=2, data_parallel_rank=r, data_parallel_size=2))
+                for r in range(2)]
+    assert per_rank[0][:2] == [[0, 1], [4, 5]] and per_rank[1][:2] == [[2, 3], [6, 7]]
+    flat = sorted(i for rank in per_rank for b in rank for i in b)
+    assert flat == list(range(20))                    # 22 samples, step 4: the last 2 are dropped
+    resumed = list(MegatronPretrainingSampler(22, 8, 2, 1, 2))
+    assert resumed[0] == [10, 11]
+    tail = list(MegatronPretrainingSampler(22, 0, 2, 0, 2, drop_last=False))[-1]
+    assert tail == [20, 21]
+
+
+def test_random_sampler_is_a_permutation_and_resumable():
+    from megatron_llm_b200.data.data_samplers import MegatronPretrainingRandomSampler
+    total, mb, dp = 40, 2, 2
+    for sharding in (True, False):
+        seen = []
+        for r in range(dp):
+            s = MegatronPretrainingRandomSampler(None, total, 0, mb, r, dp, sharding)
+            batches = list(s)
+            assert all(len(b) == mb for b in batches)
+            seen += [i for b in batches for i in b]
+        assert sorted(seen) == list(range(total))     # every sample once per epoch across the DP ranks
+        # resume after 2 global steps: the remaining batches are the tail of the same permutation
+        full = list(MegatronPretrainingRandomSampler(None, total, 0, mb, 0, dp, sharding))
+        rest = list(MegatronPretrainingRandomSampler(None, total, 2 * mb * dp, mb, 0, dp, sharding))
+        assert rest == full[2:]
+
+
+# ----------------------------------------------------------------------------------------------- beam search n-best
+def test_beam_hypotheses_keeps_the_best_and_knows_when_done():
+    from megatron_llm_b200.text_generation.beam_utils import BeamHypotheses
+    h = BeamHypotheses(num_beams=2, length_penalty=1.0)
+    h.add("a", -4.0, 4)      # score -1.0
+    assert not h.is_done(-0.1, 4)
+    h.add("b", -2.0, 4)      # -0.5
+    h.add("c", -1.0, 4)      # -0.25 evicts "a"
+    assert sorted(s for s, _ in h.beams) == [-0.5, -0.25] and h.worst_score == -0.5
+    h.add("d", -8.0, 4)      # worse than the worst: ignored
+    assert len(h) == 2
+    assert h.is_done(best_sum_logprobs=-4.0, cur_len=4)        # -1.0 cannot beat -0.5
+    assert not h.is_done(best_sum_logprobs=-1.0, cur_len=4)    # -0.25 still could
+    assert BeamHypotheses(1, early_stopping=True).is_done(0.0, 1) is False
+
+
+# ----------------------------------------------------------------------------------------------- timers
+def test_timers_accumulate_and_respect_log_level(capsys):
+    from megatron_llm_b200.timers import Timers
+    timers = Timers(log_level=1, log_option="minmax")
+    t = timers("fwd", log_level=0)
+    t.start()
+    t.stop()
+    t.start()
+    t.stop()
+    assert t.elapsed(reset=False) >= 0.0
+    silent = timers("too-detailed", log_level=2)       # above --timing_log_level: a shared no-op timer
+    silent.start()
+    silent.stop()
+    with pytest.raises(Exception):                     # (same contract as the reference: a dummy has no elapsed time)
+        silent.elapsed()
+    timers.log(["fwd", "too-detailed"], normalizer=2.0)
+    out = capsys.readouterr().out
+    assert "fwd" in out and "too-detailed" not in out
+
+
+# ----------------------------------------------------------------------------------------------- SIGTERM handler
+def test_signal_handler_records_sigterm_and_restores():
+    from megatron_llm_b200.dist_signal_handler import DistributedSignalHandler
+    before = signal.getsignal(signal.SIGTERM)
+    with DistributedSignalHandler() as h:
+        assert h.signals_received() == [False]
+        os.kill(os.getpid(), signal.SIGTERM)
+        assert h.signals_received() == [True]
+    assert signal.getsignal(signal.SIGTERM) == before
+
+
+# ----------------------------------------------------------------------------------------------- grad clipping
+def test_clip_grad_norm_matches_torch():
+    from megatron_llm_b200.optimizer.clip_grads import clip_grad_norm_fp32, count_zeros_fp32
+    torch.manual_seed(0)
+    params = [torch.nn.Parameter(torch.randn(7, 5)), torch.nn.Parameter(torch.randn(11))]
+    for p in params:
+        p.grad = torch.randn_like(p) * 3
+    params[1].grad[:4] = 0.0
+    ref = [p.grad.clone() for p in params]
+    total = torch.sqrt(sum((g ** 2).sum() for g in ref))
+    norm = clip_grad_norm_fp32(params, [p.grad for p in params], max_norm=1.0, norm_type=2, model_parallel_group=None)
+    assert float(norm) == pytest.approx(total.item(), rel=1e-5)
+    for p, g in zip(params, ref):
+        assert torch.allclose(p.grad, g / (total + 1e-6), rtol=1e-5, atol=1e-7)
+    assert int(count_zeros_fp32(params, model_parallel_group=None)) == 4
