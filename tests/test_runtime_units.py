@@ -184,3 +184,91 @@ def test_clip_grad_norm_matches_torch():
     for p, g in zip(params, ref):
         assert torch.allclose(p.grad, g / (total + 1e-6), rtol=1e-5, atol=1e-7)
     assert int(count_zeros_fp32(params, model_parallel_group=None)) == 4
+
+
+# ----------------------------------------------------------------------------------------------- blended datasets
+def test_blendable_dataset_follows_the_weights():
+    from megatron_llm_b200.data.blendable_dataset import BlendableDataset
+
+    class Tagged(torch.utils.data.Dataset):
+        def __init__(self, tag, n):
+            self.tag, self.n = tag, n
+
+        def __len__(self):
+            return self.n
+
+        def __getitem__(self, i):
+            return (self.tag, i)
+
+    ds = BlendableDataset([Tagged("a", 300), Tagged("b", 100)], weights=[3.0, 1.0])
+    assert len(ds) == 400
+    first = [ds[i] for i in range(400)]
+    counts = {t: sum(1 for tag, _ in first if tag == t) for t in "ab"}
+    assert counts == {"a": 300, "b": 100}
+    # the interleave is greedy on the running error: after any prefix the shares are within one sample of 3:1
+    a_seen = 0
+    for n, (tag, _) in enumerate(first[:200], start=1):
+        a_seen += tag == "a"
+        assert abs(a_seen - 0.75 * n) <= 1.0
+    # every dataset is walked in order
+    assert [i for tag, i in first if tag == "b"][:5] == [0, 1, 2, 3, 4]
+
+
+# ----------------------------------------------------------------------------------------------- TP helpers
+def test_split_and_vocab_ranges():
+    from megatron_llm_b200.parallel.tp_utils import VocabUtility, split_tensor_along_last_dim
+    x = torch.arange(24).view(2, 12)
+    parts = split_tensor_along_last_dim(x, 3)
+    assert [p.shape for p in parts] == [torch.Size([2, 4])] * 3 and not parts[1].is_contiguous()
+    assert all(p.is_contiguous() for p in split_tensor_along_last_dim(x, 3, contiguous_split_chunks=True))
+    assert torch.equal(torch.cat(parts, dim=-1), x)
+    assert VocabUtility.vocab_range_from_global_vocab_size(32000, 3, 8) == (12000, 16000)
+    with pytest.raises(Exception):
+        VocabUtility.vocab_range_from_global_vocab_size(32001, 0, 8)
+
+
+# ----------------------------------------------------------------------------------------------- softmax module
+@pytest.mark.parametrize("causal", [True, False])
+def test_fused_scale_mask_softmax_fused_path_equals_torch_path(causal):
+    """With ``scaled_masked_softmax_fusion`` the module calls the softmax ops (CUDA kernels on a GPU, their PyTorch
+    reference on CPU); without it the plain masked softmax: both must agree (causal, padding mask, no mask)."""
+    from megatron_llm_b200.models.enums import AttnMaskType
+    from megatron_llm_b200.models.fused_softmax import FusedScaleMaskSoftmax
+    from megatron_llm_b200.models.activations import attention_mask_func
+    torch.manual_seed(0)
+    b, n, s = 2, 3, 16
+    x = torch.randn(b, n, s, s).bfloat16()
+    kind = AttnMaskType.causal if causal else AttnMaskType.padding
+    if causal:
+        mask = torch.triu(torch.ones(s, s, dtype=torch.bool), diagonal=1).view(1, 1, s, s)
+    else:
+        mask = torch.zeros(b, 1, s, s, dtype=torch.bool)
+        mask[:, :, :, -3:] = True
+    mods = [FusedScaleMaskSoftmax(False, True, kind, fusion, attention_mask_func, True, 0.5) for fusion in (True, False)]
+    outs = [m(x, mask) for m in mods]
+    assert outs[0].dtype == torch.bfloat16 and torch.allclose(outs[0].float(), outs[1].float(), atol=1e-2)
+    assert torch.allclose(outs[0].float().sum(-1), torch.ones(b, n, s), atol=2e-2)
+    if causal:
+        assert outs[0][0, 0, 0, 1:].abs().max() == 0          # the first query only sees itself
+    nomask = [m(x, None) for m in mods] if not causal else None
+    if nomask:
+        assert torch.allclose(nomask[0].float(), nomask[1].float(), atol=1e-2)
+
+
+# ----------------------------------------------------------------------------------------------- GPT-2 BPE
+def test_gpt2_bpe_tokenizer_round_trip(tmp_path):
+    import json
+    from megatron_llm_b200.tokenizer.gpt2_tokenization import GPT2Tokenizer, bytes_to_unicode
+    b2u = bytes_to_unicode()
+    space = b2u[ord(" ")]
+    base = sorted(set(b2u.values()))
+    merges = [("l", "o"), ("lo", "w"), (space, "low"), ("e", "r"), ("low", "er")]
+    vocab = {tok: i for i, tok in enumerate(base + ["".join(m) for m in merges] + ["<|endoftext|>"])}
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n" + "\n".join(" ".join(m) for m in merges) + "\n")
+    tok = GPT2Tokenizer(str(tmp_path / "vocab.json"), str(tmp_path / "merges.txt"))
+    assert tok.tokenize("lower low") == ["lower", space + "low"]
+    ids = tok.encode("lower low")
+    assert ids == [vocab["lower"], vocab[space + "low"]] and tok.decode(ids) == "lower low"
+    text = "slow flow, 100% löwer!"
+    assert tok.decode(tok.encode(text)) == text                # byte-level: any string survives the round trip
