@@ -272,3 +272,67 @@ def test_gpt2_bpe_tokenizer_round_trip(tmp_path):
     assert ids == [vocab["lower"], vocab[space + "low"]] and tok.decode(ids) == "lower low"
     text = "slow flow, 100% löwer!"
     assert tok.decode(tok.encode(text)) == text                # byte-level: any string survives the round trip
+
+
+# ----------------------------------------------------------------------------------------------- sampling
+def test_sampling_filters_and_modes():
+    from megatron_llm_b200.text_generation.sampling import (modify_logits_for_top_k_filtering,
+                                                            modify_logits_for_top_p_filtering, sample)
+    logits = torch.tensor([[1.0, 3.0, 2.0, 0.0], [0.0, 0.0, 5.0, 4.0]])
+    k = logits.clone()
+    modify_logits_for_top_k_filtering(k, 2)
+    assert torch.isinf(k).tolist() == [[True, False, False, True], [True, True, False, False]]
+    p = torch.log(torch.tensor([[0.5, 0.3, 0.15, 0.05]]))
+    modify_logits_for_top_p_filtering(p, 0.6)            # 0.5 alone is below 0.6: the token that crosses it stays too
+    assert torch.isinf(p).tolist() == [[False, False, True, True]]
+    assert sample(logits, top_k=1).tolist() == [1, 2]
+    torch.manual_seed(0)
+    draws = torch.stack([sample(logits, top_k=2) for _ in range(50)])
+    assert set(draws[:, 0].tolist()) <= {1, 2} and set(draws[:, 1].tolist()) <= {2, 3}
+    draws = torch.stack([sample(logits, top_p=0.5) for _ in range(50)])
+    assert set(draws[:, 0].tolist()) <= {1, 2}
+    padded = torch.tensor([[0.0, 0.0, 0.0, 9.0]])
+    assert sample(padded, top_k=1, vocab_size=3).tolist() == [2]          # padded-vocab ids are clamped away
+    with pytest.raises(AssertionError):
+        sample(logits, top_k=1, top_p=0.5)
+
+
+# ----------------------------------------------------------------------------------------------- BERT / T5 sample building
+def test_split_string_and_blend_weights():
+    from megatron_llm_b200.data.dataset_utils import (get_datasets_weights_and_num_samples,
+                                                      get_train_valid_test_split_)
+    assert get_train_valid_test_split_("969,30,1", 1000) == [0, 969, 999, 1000]
+    assert get_train_valid_test_split_("90/5/5", 200) == [0, 180, 190, 200]
+    assert get_train_valid_test_split_("1", 10) == [0, 10, 10, 10]
+    prefixes, weights, counts = get_datasets_weights_and_num_samples(["3", " a ", "1", "b"], [1000, 100, 10])
+    assert prefixes == ["a", "b"] and weights == [0.75, 0.25]
+    assert counts == [[754, 76, 8], [252, 26, 3]]           # ceil(n * w * 1.005)
+
+
+def test_bert_sample_construction_pieces():
+    import numpy as np
+    from megatron_llm_b200.data.dataset_utils import (create_masked_lm_predictions, create_tokens_and_tokentypes,
+                                                      get_a_and_b_segments, pad_and_convert_to_numpy,
+                                                      truncate_segments)
+    rng = np.random.RandomState(3)
+    sample = [[10, 11], [12], [13, 14, 15]]
+    a, b, swapped = get_a_and_b_segments(sample, rng)
+    assert sorted(a + b) == [10, 11, 12, 13, 14, 15] and isinstance(swapped, bool)
+    ta, tb = list(range(20)), list(range(100, 110))
+    assert truncate_segments(ta, tb, len(ta), len(tb), 16, rng) and len(ta) + len(tb) == 16
+    tokens, types = create_tokens_and_tokentypes([5, 6], [7], cls_id=1, sep_id=2)
+    assert tokens == [1, 5, 6, 2, 7, 2] and types == [0, 0, 0, 0, 1, 1]
+    # whole-word masking: pieces "##x" stay with their word; CLS / SEP are never masked
+    vocab = {1: "[CLS]", 2: "[SEP]", 3: "[MASK]", 20: "play", 21: "##ing", 22: "chess", 23: "is", 24: "fun", 25: "##ny"}
+    seq = [1, 20, 21, 22, 23, 24, 25, 2]
+    out, pos, labels, boundary, spans = create_masked_lm_predictions(
+        seq, list(vocab), vocab, masked_lm_prob=0.4, cls_id=1, sep_id=2, mask_id=3, max_predictions_per_seq=4,
+        np_rng=np.random.RandomState(0), max_ngrams=1)
+    assert len(out) == len(seq) and out[0] == 1 and out[-1] == 2 and 0 not in pos and 7 not in pos
+    assert [seq[p] for p in pos] == labels and 1 <= len(pos) <= 4
+    words = [{1, 2}, {3}, {4}, {5, 6}]
+    assert all(any(set(w) <= set(pos) for w in words if p in w) for p in pos)      # whole words only
+    assert boundary == [1, 1, 0, 1, 1, 1, 0, 1]
+    t, ty, lab, pad_mask, loss_mask = pad_and_convert_to_numpy(out, [0] * 8, pos, labels, pad_id=0, max_seq_length=12)
+    assert t.shape == (12,) and pad_mask.tolist() == [1] * 8 + [0] * 4
+    assert loss_mask.sum() == len(pos) and all(lab[p] == l for p, l in zip(pos, labels)) and (lab == -1).sum() == 12 - len(pos)
