@@ -336,3 +336,52 @@ def test_bert_sample_construction_pieces():
     t, ty, lab, pad_mask, loss_mask = pad_and_convert_to_numpy(out, [0] * 8, pos, labels, pad_id=0, max_seq_length=12)
     assert t.shape == (12,) and pad_mask.tolist() == [1] * 8 + [0] * 4
     assert loss_mask.sum() == len(pos) and all(lab[p] == l for p, l in zip(pos, labels)) and (lab == -1).sum() == 12 - len(pos)
+
+
+# ----------------------------------------------------------------------------------------------- norm modules
+def test_norm_modules_match_reference_math_and_fuse_the_residual():
+    from megatron_llm_b200.models.norms import LayerNorm, RMSNorm
+    torch.manual_seed(0)
+    x, res = torch.randn(6, 3, 32), torch.randn(6, 3, 32)
+    ln = LayerNorm(32, eps=1e-5, sequence_parallel=True)
+    with torch.no_grad():
+        ln.weight.uniform_(0.5, 1.5)
+        ln.bias.uniform_(-0.5, 0.5)
+    assert ln.weight.sequence_parallel and ln.bias.sequence_parallel      # flags the optimizer's TP all-reduce reads
+    ref = torch.nn.functional.layer_norm(x, (32,), ln.weight, ln.bias, 1e-5)
+    assert torch.allclose(ln(x), ref, atol=1e-5)
+    y, new_res = ln(x, residual=res)                                        # fused add: norm(x + res), and x + res
+    assert torch.allclose(new_res, x + res) and torch.allclose(
+        y, torch.nn.functional.layer_norm(x + res, (32,), ln.weight, ln.bias, 1e-5), atol=1e-5)
+    rms = RMSNorm(32, eps=1e-6)
+    with torch.no_grad():
+        rms.weight.uniform_(0.5, 1.5)
+    ref = x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + 1e-6) * rms.weight
+    assert torch.allclose(rms(x), ref, atol=1e-5)
+    # gradients flow to input, residual and weight
+    xr, rr = x.clone().requires_grad_(True), res.clone().requires_grad_(True)
+    y, nr = rms(xr, residual=rr)
+    (y.sum() + nr.sum()).backward()
+    assert xr.grad is not None and torch.allclose(xr.grad, rr.grad) and rms.weight.grad is not None
+
+
+# ----------------------------------------------------------------------------------------------- vision data
+def test_image_folder_subsampling_and_autoaugment(tmp_path):
+    from PIL import Image
+    from megatron_llm_b200.data.autoaugment import ImageNetPolicy
+    from megatron_llm_b200.data.image_folder import ImageFolder
+    for cls in ("ant", "bee", "cat", "dog"):
+        (tmp_path / cls).mkdir()
+        for i in range(4):
+            Image.new("RGB", (8, 8), color=(i * 40, 10, 200)).save(tmp_path / cls / f"{i}.png")
+        (tmp_path / cls / "notes.txt").write_text("not an image")
+    full = ImageFolder(str(tmp_path))
+    assert len(full) == 16 and full.classes == ["ant", "bee", "cat", "dog"] and full.class_to_idx["cat"] == 2
+    img, label = full[5]
+    assert img.size == (8, 8) and label == 1
+    half = ImageFolder(str(tmp_path), classes_fraction=0.5, data_per_class_fraction=0.5)
+    assert len(half) == 4 and {l for _, l in half.samples} == {0, 1}
+    import random
+    random.seed(0)
+    out = ImageNetPolicy()(Image.new("RGB", (32, 32), color=(120, 30, 60)))
+    assert out.size == (32, 32) and out.mode == "RGB"
