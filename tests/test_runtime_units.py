@@ -385,3 +385,60 @@ def test_image_folder_subsampling_and_autoaugment(tmp_path):
     random.seed(0)
     out = ImageNetPolicy()(Image.new("RGB", (32, 32), color=(120, 30, 60)))
     assert out.size == (32, 32) and out.mode == "RGB"
+
+
+# ----------------------------------------------------------------------------------------------- local DDP layout
+def test_local_ddp_flat_buffers_buckets_and_accumulation():
+    """Single-process view of the bucketed local DDP (parallel/ddp.py): one fp32 grad buffer with ``main_grad`` views
+    in reverse parameter order, flat parameter storage with the same offsets, buckets that tile the buffer, gradient
+    accumulation over micro-batches through the AccumulateGrad hooks, and the zeroing at the start of a step."""
+    from megatron_llm_b200.parallel import state as ps
+    from megatron_llm_b200.parallel.ddp import DistributedDataParallel
+    from tests.dist_utils import run_distributed  # noqa: F401  (imported for parity with the other suites)
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT="29641", RANK="0", WORLD_SIZE="1")
+    if not dist.is_initialized():
+        dist.init_process_group("gloo", rank=0, world_size=1)
+    ps.initialize_model_parallel(1, 1)
+    try:
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(96, 200), torch.nn.Tanh(), torch.nn.Linear(200, 40)).bfloat16()
+        before = [p.detach().clone() for p in net.parameters()]
+        # (the smallest bucket size, 1 MB, already holds this whole model: one bucket that tiles the padded buffer)
+        ddp = DistributedDataParallel(net, accumulate_allreduce_grads_in_fp32=True, bucket_size_mb=1)
+        (gdt, buf), = ddp.grad_buffers().items()
+        assert gdt == torch.float32 and buf.data.dtype == torch.float32 and buf.data.is_contiguous()
+        params = list(net.parameters())
+        assert all(torch.equal(p.detach(), b) for p, b in zip(params, before))       # flattening kept the values
+        index = ddp._grad_buffer_param_index_map[gdt]
+        spans = sorted(index[p] for p in params)
+        assert all(a_end <= b_start for (_, a_end), (b_start, _) in zip(spans, spans[1:]))   # no overlap
+        assert index[params[-1]][0] == 0                                             # last parameter comes first
+        for p in params:
+            s, e = index[p]
+            assert p.main_grad.dtype == torch.float32 and p.main_grad.shape == p.shape
+            assert p.main_grad.data_ptr() == buf.data[s:e].data_ptr()
+            pb = ddp.param_buffers()[gdt][p.dtype]
+            assert p.data.data_ptr() == pb[s:e].data_ptr()
+        buckets = ddp._buckets[gdt]
+        assert buckets[0].start == 0 and buckets[-1].end == buf.numel_padded
+        assert all(a.end == b.start for a, b in zip(buckets, buckets[1:]))
+        assert sorted(id(p) for b in buckets for p in b.params) == sorted(id(p) for p in params)
+        # two micro-batches accumulate into main_grad in fp32; .grad is released
+        ddp.zero_grad_buffer()
+        xs = [torch.randn(8, 96).bfloat16() for _ in range(2)]
+        for x in xs:
+            ddp(x).float().pow(2).mean().backward()
+        assert all(p.grad is None for p in params)
+        ref = torch.nn.Sequential(torch.nn.Linear(96, 200), torch.nn.Tanh(), torch.nn.Linear(200, 40)).bfloat16()
+        ref.load_state_dict({k: v.clone() for k, v in net.state_dict().items()})
+        for x in xs:
+            ref(x).float().pow(2).mean().backward()
+        for p, q in zip(params, ref.parameters()):
+            assert torch.allclose(p.main_grad, q.grad.float(), rtol=2e-2, atol=1e-3)
+        ddp.allreduce_gradients()                                                    # DP = 1: nothing to reduce
+        ddp.zero_grad_buffer()
+        assert float(buf.data.abs().sum()) == 0.0
+    finally:
+        ps.destroy_model_parallel()
+        dist.destroy_process_group()
