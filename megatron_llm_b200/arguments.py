@@ -102,7 +102,7 @@ _GROUPS = {
         ("--train_samples", dict(type=int, default=None)),
         ("--log_interval", dict(type=int, default=100)),
         ("--exit_interval", dict(type=int, default=None)),
-        ("--exit_duration_in_mins", dict(type=int, default=None)),
+        ("--exit_duration_in_mins", dict(type=float, default=None)),
         ("--exit_signal_handler", _S()),
         ("--tensorboard_dir", dict(type=str, default=None)),
         ("--no_masked_softmax_fusion", _SF("masked_softmax_fusion")),
