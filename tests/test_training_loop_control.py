@@ -125,3 +125,27 @@ def test_checkpoint_args_are_checked_and_can_be_adopted(tmp_path):
     ok = _run(["--train_iters", "2", "--load", ckpt, "--use_checkpoint_args"], arch=minimal)
     assert "Setting num_layers to 2 from checkpoint" in ok.stdout and "Setting use_rms_norm to True" in ok.stdout
     assert [i for i, *_ in _iters(ok.stdout)] == [2]
+
+
+def test_validation_metrics_tensorboard_and_timers(tmp_path):
+    """--metrics plug-ins are evaluated during validation; the TensorBoard writer gets the scalars (loss, lr, timers,
+    memory, validation metrics) and the per-interval timer report is printed at --timing_log_level 2."""
+    tb = tmp_path / "tb"
+    out = _run(["--train_iters", "4", "--eval_interval", "2", "--eval_iters", "2", "--metrics", "perplexity", "accuracy",
+                "count_loss_mask", "--tensorboard_dir", str(tb), "--log_timers_to_tensorboard",
+                "--log_memory_to_tensorboard", "--log_params_norm", "--timing_log_level", "2"]).stdout
+    val = [l for l in out.splitlines() if "validation loss at iteration" in l]
+    assert len(val) == 2
+    for key in ("lm loss value", "lm loss PPL", "ppl value", "lm accuracy value", "count loss mask value: 1.600000E+01"):
+        assert key in val[0], (key, val[0])
+    assert "validation loss at the end of training for test data" in out and "params norm:" in out
+    assert "forward-backward" in out and "optimizer" in out            # timer report
+    events = [f for f in os.listdir(tb) if f.startswith("events.out.tfevents")]
+    assert events
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    acc = EventAccumulator(str(tb))
+    acc.Reload()
+    tags = set(acc.Tags()["scalars"])
+    for tag in ("learning-rate", "lm loss", "lm loss validation", "ppl validation", "lm accuracy validation"):
+        assert tag in tags, (tag, sorted(tags)[:40])
+    assert [e.step for e in acc.Scalars("lm loss")] == [1, 2, 3, 4]
