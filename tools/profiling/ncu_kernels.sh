@@ -13,7 +13,7 @@ cap() {  # name, kernel regex, launches to skip, command...
 }
 G="python tools/profiling/gemm_check.py"
 A="python tools/profiling/attn_check.py"
-MLB200_GEMM_TILE=256 cap gemm_1cta_nt      gemm_bf16_kernel       2 $G nt 4096 22016 4096 t
+MLB200_GEMM_2CTA=0 cap gemm_1cta_nt      gemm_bf16_kernel       2 $G nt 4096 22016 4096 t
 cap gemm_2cta_nt      gemm_bf16_2cta_kernel  2 $G nt 4096 22016 4096 t
 cap gemm_2cta_nn      gemm_bf16_2cta_kernel  2 $G nn 4096 4096 11008 t
 cap gemm_2cta_wgrad   gemm_bf16_2cta_kernel  2 $G tn_acc 22016 4096 4096 t
