@@ -208,23 +208,25 @@ def run_ours(a):
     dev = torch.device("cuda", torch.cuda.current_device())
     n_mb = a.global_batch // a.micro_batch
     g = torch.Generator().manual_seed(1234)
-    # a pool of distinct synthetic micro-batches, pinned on the host
+    # distinct synthetic micro-batches for every step of the run (uniform random tokens: nothing to memorise, the loss
+    # stays near ln(vocab)), pinned on the host; both feeds walk the same pool with one shared cursor
+    n_pool = min(4096, n_mb * (a.warmup + 2 * a.steps + 3))
     pool = [torch.randint(0, vocab, (a.micro_batch, a.seq + 1), generator=g, dtype=torch.int64).pin_memory()
-            for _ in range(max(n_mb, 8))]
+            for _ in range(n_pool)]
     pool_dev = [t.to(dev) for t in pool]
-    tp_rank0 = True  # TP-rank 0 feeds the data; other TP ranks get it via broadcast_data
+    cursor = [0]
 
     def host_iter():
-        i = 0
         while True:
-            yield {"text": pool[i % len(pool)]}
-            i += 1
+            i = cursor[0]
+            cursor[0] += 1
+            yield {"text": pool[i % n_pool]}
 
     def dev_iter():
-        i = 0
         while True:
-            yield {"text": pool_dev[i % len(pool_dev)]}
-            i += 1
+            i = cursor[0]
+            cursor[0] += 1
+            yield {"text": pool_dev[i % n_pool]}
 
     from megatron_llm_b200.parallel import state as ps
     feeds = ps.get_tensor_model_parallel_rank() == 0
@@ -292,7 +294,7 @@ def run_ours(a):
         out = {"metric": "tokens/sec (whole job, device-timed, max over ranks), Llama-2-7B TP=#GPUs seq4096 training step",
                "value": tokens / (ms_dev / 1e3), "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong",
-               "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+               "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens (fresh uniform-random micro-batches every step), random-init weights",
                "impl": "ours",
                "config": {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
                           "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
