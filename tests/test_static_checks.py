@@ -48,3 +48,39 @@ def test_every_python_file_parses_and_binds_the_names_it_reads():
         if missing:
             problems[os.path.relpath(path, ROOT)] = missing
     assert not problems, problems
+
+
+def test_every_args_attribute_is_a_flag_or_assigned_somewhere():
+    """``args.<name>`` read anywhere in the package / entry points / tasks must be a destination of one of the argument
+    parsers or be assigned somewhere (the reference lost ``--bert_no_binary_head`` from its parser while
+    pretrain_bert.py kept reading it: this is the check that would have caught it)."""
+    import re
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ.setdefault("MLB200_FORCE_CPU", "1")
+    import finetune
+    from megatron_llm_b200.arguments import build_base_parser
+    dests = {a.dest for a in finetune.extra_args(build_base_parser())._actions}
+    for mod_name, fn_name in (("pretrain_bert", "extra_args"), ("pretrain_t5", "extra_args"),
+                              ("pretrain_ict", "extra_args"), ("tasks.main", "get_tasks_args"),
+                              ("tasks.msdp.main", "get_tasks_args"), ("verify_correctness", "extra_extra_args")):
+        try:
+            mod = __import__(mod_name, fromlist=[fn_name])
+        except Exception:  # noqa: BLE001 - optional entry points
+            continue
+        if hasattr(mod, fn_name):
+            dests |= {a.dest for a in getattr(mod, fn_name)(build_base_parser())._actions}
+    files = [f for f in _files() if os.sep + "tests" + os.sep not in f and os.sep + "tools" + os.sep not in f
+             and os.sep + "weights_conversion" + os.sep not in f]
+    assigned, used = set(), {}
+    for path in files:
+        src = open(path, errors="ignore").read()
+        assigned |= set(re.findall(r"\bargs\.([A-Za-z_]\w*)\s*(?:=[^=]|,\s*args\.)", src))
+        assigned |= set(re.findall(r"args\.[A-Za-z_]\w*,\s*args\.([A-Za-z_]\w*)\s*(?:=[^=]|,)", src))
+        assigned |= set(re.findall(r"""setattr\(args,\s*["'](\w+)["']""", src))
+        guarded = set(re.findall(r"""(?:hasattr|getattr)\(args,\s*["'](\w+)["']""", src))
+        for m in re.finditer(r"\bargs\.([A-Za-z_]\w*)", src):
+            if m.group(1) not in guarded:
+                used.setdefault(m.group(1), set()).add(os.path.relpath(path, ROOT))
+    unknown = {k: sorted(v)[:3] for k, v in used.items() if k not in dests and k not in assigned}
+    assert not unknown, unknown
