@@ -12,7 +12,7 @@ bash tools/profiling/attn_hd64_checks.sh > gpurun_out/pending_hd64.log 2>&1; tai
 
 if [ "$N" -ge 2 ]; then
   echo "== 2. fused TP variants: streaming pullers, push all-gather, rank skew (2 GPUs)"
-  MLB200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_fused_comm_gpu.py tests/test_model_gpu.py -m gpu -q \
+  MLB200_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_fused_comm_gpu.py tests/test_model_gpu.py tests/test_ops_gpu.py -m gpu -q \
     > gpurun_out/pending_fused_tests.log 2>&1; tail -6 gpurun_out/pending_fused_tests.log
 
   echo "== 3. NVLink transfer rates per instruction path"
