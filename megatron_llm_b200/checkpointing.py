@@ -154,9 +154,12 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler):
     model = unwrap_model(model)
     if not isinstance(model, list):
         model = [model]
-    print_rank_0("saving checkpoint at iteration {:7d} to {}".format(iteration, args.save))
+    release = iteration == "release"        # tools (converters, checkpoint_util) save "release" checkpoints
+    where = "release checkpoint" if release else "checkpoint at iteration {:7d}".format(iteration)
+    print_rank_0("saving {} to {}".format(where, args.save))
     rng_state = get_rng_state()
-    model_name, optim_name = get_checkpoint_names(args.save, iteration, args.use_distributed_optimizer)
+    model_name, optim_name = get_checkpoint_names(args.save, iteration, args.use_distributed_optimizer,
+                                                  release=release)
 
     save_optim = optimizer is not None and not args.no_save_optim
     model_state, optim_state = {}, {}
@@ -196,7 +199,7 @@ def save_checkpoint(iteration, model, optimizer, opt_param_scheduler):
 
     if dist.is_initialized():
         dist.barrier()
-    print_rank_0("  successfully saved checkpoint at iteration {:7d} to {}".format(iteration, args.save))
+    print_rank_0("  successfully saved {} to {}".format(where, args.save))
     if not dist.is_initialized() or dist.get_rank() == 0:
         with open(get_checkpoint_tracker_filename(args.save), "w") as f:
             f.write(str(iteration))

@@ -44,8 +44,8 @@ int mlb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int 
                    int nseg, float lr, float beta1, float beta2, float eps, float bc1, float bc2,
                    const float* grad_scale_ptr, const int* skip_flag, cudaStream_t st);
 int mlb_sgd_flat(float* p, const float* g, float* mom, void* p16, int p16_dtype, long long n, long long global_offset,
-                 const long long* seg_start, const float* seg_wd, int nseg, float lr, float momentum, int first_step,
-                 const float* grad_scale_ptr, const int* skip_flag, cudaStream_t st);
+                 const long long* seg_start, const float* seg_wd, const float* seg_lr_mult, int nseg, float lr,
+                 float momentum, int first_step, const float* grad_scale_ptr, const int* skip_flag, cudaStream_t st);
 int mlb_sqnorm_flat(int dtype, const void* x, long long n, long long global_offset, const long long* seg_start,
                     const float* seg_weight, int nseg, float* workspace, float* out, int accumulate, cudaStream_t st);
 int mlb_clip_coef(const float* total_sq, float max_norm, float* norm_out, float* coef_out, int* found_inf,
@@ -207,13 +207,15 @@ static void adamw_flat(torch::Tensor& p, const torch::Tensor& g, torch::Tensor& 
                      skip.has_value() ? skip->data_ptr<int>() : nullptr, cur()));
 }
 static void sgd_flat(torch::Tensor& p, const torch::Tensor& g, torch::Tensor& mom, const c10::optional<torch::Tensor>& p16,
-                     int64_t global_offset, const torch::Tensor& seg_start, const torch::Tensor& seg_wd, double lr,
-                     double momentum, bool first_step, const c10::optional<torch::Tensor>& grad_scale,
+                     int64_t global_offset, const torch::Tensor& seg_start, const torch::Tensor& seg_wd,
+                     const torch::Tensor& seg_lr_mult, double lr, double momentum, bool first_step,
+                     const c10::optional<torch::Tensor>& grad_scale,
                      const c10::optional<torch::Tensor>& skip) {
   c10::cuda::CUDAGuard guard(p.device());
   CHK(mlb_sgd_flat(p.data_ptr<float>(), g.data_ptr<float>(), mom.data_ptr<float>(), const_cast<void*>(optp(p16)),
                    p16.has_value() ? dt(*p16) : 0, p.numel(), global_offset, (const long long*)seg_start.data_ptr(),
-                   seg_wd.data_ptr<float>(), (int)seg_wd.numel(), (float)lr, (float)momentum, first_step,
+                   seg_wd.data_ptr<float>(), seg_lr_mult.data_ptr<float>(), (int)seg_wd.numel(), (float)lr,
+                   (float)momentum, first_step,
                    grad_scale.has_value() ? grad_scale->data_ptr<float>() : nullptr,
                    skip.has_value() ? skip->data_ptr<int>() : nullptr, cur()));
 }

@@ -103,8 +103,9 @@ template <typename TP16>
 __global__ void __launch_bounds__(256)
 sgd_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ mom, TP16* __restrict__ p16,
                 long long n, long long global_offset, const long long* __restrict__ seg_start,
-                const float* __restrict__ seg_wd, int nseg, float lr, float momentum, int first_step,
-                const float* __restrict__ grad_scale_ptr, const int* __restrict__ skip_flag) {
+                const float* __restrict__ seg_wd, const float* __restrict__ seg_lr_mult, int nseg, float lr,
+                float momentum, int first_step, const float* __restrict__ grad_scale_ptr,
+                const int* __restrict__ skip_flag) {
   if (skip_flag != nullptr && *skip_flag != 0) return;
   const float gscale = grad_scale_ptr ? *grad_scale_ptr : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -112,7 +113,7 @@ sgd_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     float gg = g[i] * gscale + seg_wd[seg] * p[i];
     float b = first_step ? gg : momentum * mom[i] + gg;
     if (momentum != 0.f) { mom[i] = b; gg = b; }
-    const float np_ = p[i] - lr * gg;
+    const float np_ = p[i] - lr * (seg_lr_mult ? seg_lr_mult[seg] : 1.f) * gg;
     p[i] = np_;
     if (p16 != nullptr) p16[i] = from_f<TP16>(np_);
   }
@@ -228,15 +229,15 @@ extern "C" int mlb_adamw_flat(float* p, const float* g, float* m, float* v, void
 }
 
 extern "C" int mlb_sgd_flat(float* p, const float* g, float* mom, void* p16, int p16_dtype, long long n,
-                            long long global_offset, const long long* seg_start, const float* seg_wd, int nseg,
-                            float lr, float momentum, int first_step, const float* grad_scale_ptr,
-                            const int* skip_flag, cudaStream_t st) {
+                            long long global_offset, const long long* seg_start, const float* seg_wd,
+                            const float* seg_lr_mult, int nseg, float lr, float momentum, int first_step,
+                            const float* grad_scale_ptr, const int* skip_flag, cudaStream_t st) {
   if (n <= 0) return 0;
   const int grid = mlb::opt_grid(n);
   if (p16 == nullptr || p16_dtype == mlb::DT_BF16)
-    mlb::sgd_flat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, g, mom, (__nv_bfloat16*)p16, n, global_offset, seg_start, seg_wd, nseg, lr, momentum, first_step, grad_scale_ptr, skip_flag);
+    mlb::sgd_flat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, g, mom, (__nv_bfloat16*)p16, n, global_offset, seg_start, seg_wd, seg_lr_mult, nseg, lr, momentum, first_step, grad_scale_ptr, skip_flag);
   else if (p16_dtype == mlb::DT_F16)
-    mlb::sgd_flat_kernel<__half><<<grid, 256, 0, st>>>(p, g, mom, (__half*)p16, n, global_offset, seg_start, seg_wd, nseg, lr, momentum, first_step, grad_scale_ptr, skip_flag);
+    mlb::sgd_flat_kernel<__half><<<grid, 256, 0, st>>>(p, g, mom, (__half*)p16, n, global_offset, seg_start, seg_wd, seg_lr_mult, nseg, lr, momentum, first_step, grad_scale_ptr, skip_flag);
   else return -100;
   return (int)cudaGetLastError();
 }

@@ -6,6 +6,8 @@ Pooler :97-130, Embedding :133-326, TransformerLanguageModel :329-638 (incl. che
 """
 from __future__ import annotations
 
+import math
+
 from typing import Callable
 
 import torch
@@ -237,12 +239,20 @@ class TransformerLanguageModel(MegatronModule):
             self.lm_head = nn.Parameter(data)
             self._lm_key = "lm_head"
             head_init = nn.init.xavier_uniform_ if args.init_method_xavier_uniform else nn.init.xavier_normal_
+            # Xavier scales with fan_in + fan_out.  The reference applies it to the TP *shard* (:448-457), so its LM-head
+            # std grows with the TP size (0.0074 at TP=1 -> 0.0156 at TP=8 for Llama-2-7B): the initial loss and the
+            # whole loss curve of a from-scratch run then depend on the parallel layout.  Here the fans are those of
+            # the full [padded_vocab, hidden] matrix, whatever the layout.
+            full_fans = float(args.padded_vocab_size + self.hidden_size)
+
+            def head_init_shard(w, _init=head_init, _fans=full_fans):
+                return _init(w, gain=math.sqrt((w.size(0) + w.size(1)) / _fans))
             if args.perform_initialization:
                 if args.use_cpu_initialization:
                     _initialize_affine_weight_cpu(self.lm_head, args.padded_vocab_size, self.hidden_size, num_embeds,
                                                   0, head_init, params_dtype=args.params_dtype)
                 else:
-                    _initialize_affine_weight_gpu(self.lm_head, head_init, partition_dim=0, stride=1)
+                    _initialize_affine_weight_gpu(self.lm_head, head_init_shard, partition_dim=0, stride=1)
             else:
                 tp_layers.set_tensor_model_parallel_attributes(self.lm_head, True, 0, 1)
 

@@ -397,7 +397,7 @@ class FlatOptimizer(MegatronOptimizer):
             elif name == "sgd":
                 mom = self.config["momentum"]
                 if ops.cuda_ops_available(grad):
-                    ops._C().sgd_flat(g.main_param, grad, g.exp_avg, p16, off, g.seg_start, seg_wd, lr, mom,
+                    ops._C().sgd_flat(g.main_param, grad, g.exp_avg, p16, off, g.seg_start, seg_wd, g.seg_lr_mult, lr, mom,
                                       self.step_count == 1, self._clip_coef, self.found_inf)
                     ops._count()
                 else:
@@ -409,7 +409,7 @@ class FlatOptimizer(MegatronOptimizer):
                             else:
                                 g.exp_avg.mul_(mom).add_(gg)
                             gg = g.exp_avg
-                        g.main_param.sub_(lr * gg)
+                        g.main_param.sub_(self._expand_segments(g, g.seg_lr_mult) * lr * gg)
                         if p16 is not None:
                             p16.copy_(g.main_param)
             else:

@@ -48,11 +48,14 @@ class MemoryBuffer:
 
 
 class Bucket:
-    def __init__(self, index: int, start: int, end: int, params: List[torch.nn.Parameter]):
+    def __init__(self, index: int, start: int, end: int, params: List[torch.nn.Parameter], deferred: bool = False):
         self.index, self.start, self.end, self.params = index, start, end, params
         self.pending = set()
         self.handle = None
         self.launched = False
+        # deferred buckets are never reduced from the backward hooks: their params get further gradient
+        # contributions / reductions after backward (tied embeddings, SP norm grads) -- see _deferred_params
+        self.deferred = deferred
 
 
 class DistributedDataParallelBase(MegatronModule):
@@ -108,22 +111,32 @@ class DistributedDataParallel(DistributedDataParallelBase):
         self._param_to_bucket = {}
         bucket_elems = max(1, bucket_size_mb) * 1024 * 1024 // 4
         pad_to = _ALIGN * max(1, self._dp_world)   # bucket boundaries are DP-shardable
+        deferred = self._deferred_params(module)
         for gdt, plist in by_dtype.items():
             offset, cur_start = 0, 0
             index_map, buckets, cur = {}, [], []
-            for p in reversed(plist):
-                n = p.data.nelement()
-                index_map[p] = (offset, offset + n)
-                offset += int(math.ceil(n / _ALIGN) * _ALIGN)
-                cur.append(p)
-                if offset - cur_start >= bucket_elems:
+            # backward order first; the deferred params (tiny norm weights, the embeddings whose gradient arrives
+            # last anyway) live behind them in buckets of their own that are reduced after backward
+            ordered = [p for p in reversed(plist) if p not in deferred]
+            late = [p for p in reversed(plist) if p in deferred]
+            for group, is_deferred in ((ordered, False), (late, True)):
+                if is_deferred and cur:
                     offset = int(math.ceil(offset / pad_to) * pad_to)
                     buckets.append(Bucket(len(buckets), cur_start, offset, cur))
                     cur, cur_start = [], offset
+                for p in group:
+                    n = p.data.nelement()
+                    index_map[p] = (offset, offset + n)
+                    offset += int(math.ceil(n / _ALIGN) * _ALIGN)
+                    cur.append(p)
+                    if offset - cur_start >= bucket_elems:
+                        offset = int(math.ceil(offset / pad_to) * pad_to)
+                        buckets.append(Bucket(len(buckets), cur_start, offset, cur, deferred=is_deferred))
+                        cur, cur_start = [], offset
             numel = offset
             numel_padded = int(math.ceil(numel / pad_to) * pad_to)
             if cur or not buckets:
-                buckets.append(Bucket(len(buckets), cur_start, numel_padded, cur))
+                buckets.append(Bucket(len(buckets), cur_start, numel_padded, cur, deferred=bool(late)))
             buf = MemoryBuffer(numel, numel_padded, gdt)
             self._grad_buffers[gdt] = buf
             self._grad_buffer_param_index_map[gdt] = index_map
@@ -156,6 +169,25 @@ class DistributedDataParallel(DistributedDataParallelBase):
             p._grad_ready_callback = self._make_ready_callback(p)
 
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _deferred_params(module) -> set:
+        """Params whose gradient is NOT final when their own backward contribution has been accumulated:
+
+        * sequence-parallel params (norm weights, Row biases): TP all-reduced after backward
+          (``allreduce_layernorm_grads``) -- a DP reduction in flight would race with it;
+        * embedding tables: a tied word embedding receives the LM-head wgrad (fused epilogue, reported through
+          ``_grad_ready_callback``) AND the lookup gradient (autograd hook), and with PP>1 / T5 the ``shared`` copies
+          are all-reduced over the embedding groups after backward."""
+        out = set()
+        for p in module.parameters():
+            if getattr(p, "sequence_parallel", False) or getattr(p, "shared", False):
+                out.add(p)
+        from .layers import VocabParallelEmbedding
+        for m in module.modules():
+            if isinstance(m, (VocabParallelEmbedding, torch.nn.Embedding)):
+                out.update(m.parameters(recurse=False))
+        return out
+
     def bind_symmetric_communicator(self, comm):
         self._symm = comm
 
@@ -199,7 +231,7 @@ class DistributedDataParallel(DistributedDataParallelBase):
             return
         gdt, bucket = self._param_to_bucket[param]
         bucket.pending.discard(param)
-        if not bucket.pending and not bucket.launched:
+        if not bucket.pending and not bucket.launched and not bucket.deferred:
             self._launch_bucket(gdt, bucket, async_op=True)
 
     def _launch_bucket(self, gdt, bucket, async_op):

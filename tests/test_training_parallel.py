@@ -87,6 +87,9 @@ LAYOUTS = [
     ("dp2", 2, 1, 1, []),
     ("dp2_distopt", 2, 1, 1, ["--use_distributed_optimizer"]),
     ("tp2_pp2", 4, 2, 2, []),
+    # SP norm grads are TP-reduced after backward while DP buckets may already be in flight (deferred buckets, ddp.py)
+    ("tp2_sp_dp2", 4, 2, 1, ["--sequence_parallel"]),
+    ("tp2_sp_dp2_distopt", 4, 2, 1, ["--sequence_parallel", "--use_distributed_optimizer"]),
     ("pp2_dp2_recompute", 4, 1, 2, ["--recompute_granularity", "full", "--recompute_method", "uniform"]),
 ]
 
@@ -102,6 +105,23 @@ def test_layout_matches_baseline(baseline, tmp_path, name, world, tp, pp, extra)
                           "--load", str(load), "--finetune", "--no_load_optim", "--no_load_rng"] + extra,
                   tmp_path / "loss.json")
     assert losses == pytest.approx(ref, rel=2e-4, abs=2e-4), (name, losses, ref)
+
+
+@pytest.mark.parametrize("extra", [[], ["--use_distributed_optimizer"]], ids=["dp2", "dp2_distopt"])
+def test_tied_embeddings_data_parallel(tmp_path, extra):
+    """Tied embedding + fused wgrad accumulation: the word-embedding weight gets the LM-head wgrad (GEMM epilogue,
+    reported through the ready callback) and the lookup gradient (autograd hook); its DP bucket must not be reduced
+    before both have landed."""
+    tied = [("gpt" if a == "llama2" else a) for a in MODEL if a != "--no_tie_embed_logits"]   # (Llama never ties)
+
+    def run(world, more, out):
+        run_distributed(_train_worker, world, tied + more, str(out), 3, world == 1, False)
+        with open(out) as f:
+            return json.load(f)
+    ref = run(1, ["--save", str(tmp_path / "ckpt")], tmp_path / "ref.json")
+    got = run(2, ["--load", str(tmp_path / "ckpt"), "--finetune", "--no_load_optim", "--no_load_rng"] + extra,
+              tmp_path / "dp2.json")
+    assert got == pytest.approx(ref, rel=2e-4, abs=2e-4), (got, ref)
 
 
 def test_interleaved_schedule_matches_baseline(baseline, tmp_path):

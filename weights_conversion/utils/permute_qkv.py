@@ -50,11 +50,11 @@ def update_checkpoint(input_dir: Path, output_dir: Path, overwrite_ok: bool = Fa
         args = ckpt["args"]
         lm = ckpt["model"]["language_model"]
         enc = lm["encoder"] if "encoder" in lm else lm["transformer"]
-        tp = args.tensor_model_parallel_size
+        # global head counts (as the reference): only their ratio and hidden/heads = head_dim are used, and the
+        # number of KV groups in this TP shard follows from the shard's row count
         for key, w in list(enc.items()):
             if "query_key_value.weight" in key:
-                enc[key] = permute_qkv(w, args.hidden_size, args.num_attention_heads // tp,
-                                       args.num_attention_heads_kv // tp)
+                enc[key] = permute_qkv(w, args.hidden_size, args.num_attention_heads, args.num_attention_heads_kv)
         (output_dir / sub / rank_dir.name).mkdir()
         torch.save(ckpt, output_dir / sub / rank_dir.name / "model_optim_rng.pt")
 
