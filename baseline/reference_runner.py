@@ -84,7 +84,40 @@ class _SyntheticTokenizer:
         return " ".join(map(str, ids))
 
 
-def main(a, MODELS, ClockSampler):
+def _install_torch_shims():
+    """torch 2.11 removed private storage helpers the reference's distributed optimizer calls
+    (optimizer/distrib_optimizer.py:384 ``storage()._untyped()``); BASELINE.md section 3."""
+    import torch
+    ts = torch.storage.TypedStorage
+    if not hasattr(ts, "_untyped"):
+        ts._untyped = lambda self: self.untyped()
+
+
+class _Tee:
+    """Keeps what the reference prints (its training log goes to stdout on the LAST rank) so the loss of the final
+    iteration can be reported; nothing is forwarded to the real stdout (the JSON line must be the only output)."""
+
+    def __init__(self):
+        self.buf = []
+
+    def write(self, s):
+        self.buf.append(s)
+        if len(self.buf) > 4096:
+            del self.buf[:2048]
+
+    def flush(self):
+        pass
+
+    def last_loss(self):
+        import re
+        for line in reversed("".join(self.buf).splitlines()):
+            m = re.search(r"lm loss: ([0-9.eE+-]+)", line)
+            if m:
+                return float(m.group(1))
+        return None
+
+
+def main(a, MODELS, ClockSampler, bench):
     import torch
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -101,26 +134,40 @@ def main(a, MODELS, ClockSampler):
         del sys.modules[k]
     sys.path = [REF] + [p for p in sys.path if os.path.abspath(p or ".") != os.path.dirname(HERE)]
     _install_apex_stub()
+    _install_torch_shims()
 
     layers, hidden, heads, kv, ffn, vocab = MODELS[a.model]
     if a.layers:
         layers = a.layers
+    tp, pp, dp = bench.parallel_layout(a, a.gpus)
+    family = a.model.split("-")[0].rstrip("2")          # llama / mistral / falcon
     W, K = a.warmup, a.steps
-    argv = ["reference_bench", "--model_name", "llama2", "--num_layers", str(layers), "--hidden_size", str(hidden),
+    argv = ["reference_bench", "--model_name", {"llama": "llama2", "mistral": "mistral", "falcon": "falcon"}[family],
+            "--num_layers", str(layers), "--hidden_size", str(hidden),
             "--num_attention_heads", str(heads), "--num_attention_heads_kv", str(kv), "--ffn_hidden_size", str(ffn),
             "--seq_length", str(a.seq), "--max_position_embeddings", str(a.seq), "--micro_batch_size",
             str(a.micro_batch), "--global_batch_size", str(a.global_batch), "--tensor_model_parallel_size",
-            str(a.gpus), "--pipeline_model_parallel_size", "1", "--train_iters", str(W + K), "--lr", "1e-5",
+            str(tp), "--pipeline_model_parallel_size", str(pp), "--train_iters", str(W + K), "--lr", "1e-5",
             "--min_lr", "1e-6", "--lr_decay_style", "cosine", "--weight_decay", "0.1", "--clip_grad", "1.0",
             "--adam_beta1", "0.9", "--adam_beta2", "0.95", "--adam_eps", "1e-5", "--bf16", "--use_flash_attn",
-            "--use_rms_norm", "--glu_activation", "swiglu", "--no_tie_embed_logits", "--position_embedding_type",
+            "--position_embedding_type",
             "rotary", "--hidden_dropout", "0.0", "--attention_dropout", "0.0", "--layernorm_epsilon", "1e-5",
             "--no_bias_gelu_fusion", "--no_bias_dropout_fusion", "--no_gradient_accumulation_fusion",
             "--log_interval", "1", "--eval_iters", "0", "--eval_interval", "1000000", "--num_workers", "0",
             "--seed", "1234", "--tokenizer_type", "SentencePieceTokenizer", "--vocab_file", "synthetic",
             "--data_type", "gpt", "--data_path", "synthetic"]
-    if a.gpus > 1:
+    if family == "falcon":
+        argv += ["--parallel_attn", "--parallel_layernorm"]
+    else:
+        argv += ["--use_rms_norm", "--glu_activation", "swiglu", "--no_tie_embed_logits"]
+    if family == "mistral":
+        argv += ["--sliding_window_size", "4096"]
+    if tp > 1:
         argv.append("--sequence_parallel")
+    if a.recompute:
+        argv += ["--recompute_granularity", "full", "--recompute_method", "uniform", "--recompute_num_layers", "1"]
+    if a.dist_opt:
+        argv.append("--use_distributed_optimizer")
     sys.argv = argv
 
     import megatron  # the reference package (baseline/_ref/megatron)
@@ -181,7 +228,8 @@ def main(a, MODELS, ClockSampler):
     training.train_step = timed_train_step
 
     real_stdout = sys.stdout
-    sys.stdout = open(os.devnull, "w") if rank == 0 else sys.stdout
+    tee = _Tee()
+    sys.stdout = tee
     try:
         init.initialize_megatron(ref_finetune.extra_args, {"tokenizer_type": "SentencePieceTokenizer"})
         args = megatron.get_args()
@@ -192,23 +240,27 @@ def main(a, MODELS, ClockSampler):
     import torch.distributed as dist
     ms = torch.tensor([dev_state["start"].elapsed_time(dev_state["end"])], device="cuda")
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    # the reference logs on the last rank: fetch its final "lm loss" (NaN = not found)
+    ll = tee.last_loss()
+    loss_t = torch.tensor([ll if ll is not None else float("nan")], device="cuda")
+    dist.broadcast(loss_t, src=world - 1)
+    peak = torch.tensor([torch.cuda.max_memory_allocated() / 2 ** 30], device="cuda")
+    dist.all_reduce(peak, op=dist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         tokens = K * a.global_batch * a.seq
         val = tokens / (ms.item() / 1e3)
-        n_mb = a.global_batch // a.micro_batch
+        last_loss = loss_t.item()
         print(json.dumps({
-            "metric": "tokens/sec (whole job, device-timed, max over ranks), Llama-2-7B TP=#GPUs seq4096 training step",
+            "metric": bench.METRIC.format(model=a.model, par=bench.parallelism_string(a, a.gpus), seq=a.seq),
             "value": val, "unit": "tokens/s", "n_gpus": a.gpus, "steps": K, "warmup": W,
             "ms_per_step": ms.item() / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic tokens, random-init weights",
             "impl": "reference", "label": "reference (shimmed: apex->torch fused AdamW, no wgrad-accum fusion)",
-            "config": {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
-                       "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
-                       "parallelism": f"tp{a.gpus}" + ("+sp" if a.gpus > 1 else ""),
-                       "l2": "each step streams >100 GB of state (>> L2)"},
+            "config": bench.bench_config(a, a.gpus),
+            "details": {"peak_mem_gb": round(peak.item(), 2)},
             "clocks": clocks,
-            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": n_mb * a.micro_batch * (a.seq + 1) * 8,
-                    "d2h_bytes_per_step": 4,
+            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": a.global_batch * (a.seq + 1) * 8,
+                    "d2h_bytes_per_step": 4, "last_loss": None if last_loss != last_loss else last_loss,
                     "note": "the reference's stock loop copies inputs H2D and reads the loss every step"},
             "gpu_launches": 0}), flush=True)

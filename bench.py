@@ -46,7 +46,10 @@ def parse():
     p.add_argument("--model", default="llama2-7b", choices=list(MODELS))
     p.add_argument("--seq", type=int, default=4096)
     p.add_argument("--global_batch", type=int, default=8)
-    p.add_argument("--micro_batch", type=int, default=1)
+    p.add_argument("--micro_batch", type=int, default=0,
+                   help="sequences per micro-batch; 0 = auto: the tensor-parallel size when there is no pipeline (every "
+                        "GPU then runs kernels of the single-GPU size and the TP collectives move tp x larger messages "
+                        "tp x less often), 1 with pipeline parallelism.  Same rule for both --impl arms.")
     p.add_argument("--layers", type=int, default=None, help="DEV ONLY: override layer count (invalidates the number)")
     # the headline config is TP = #GPUs; the other BASELINE.json configs (Mistral TP2xDP4, Falcon-40B TP4xPP2,
     # Llama-2-70B TP8 + recompute) are reachable with these
@@ -117,6 +120,30 @@ def parallel_layout(a, n_gpus):
     tp = getattr(a, "tp", None) or max(n_gpus // pp, 1)
     assert n_gpus % (tp * pp) == 0, f"--gpus {n_gpus} is not a multiple of tp*pp = {tp * pp}"
     return tp, pp, n_gpus // (tp * pp)
+
+
+def resolve_micro_batch(a, n_gpus):
+    """The micro-batch both arms use (see --micro_batch)."""
+    if a.micro_batch and a.micro_batch > 0:
+        return a.micro_batch
+    tp, pp, dp = parallel_layout(a, n_gpus)
+    per_dp = a.global_batch // dp
+    mb = tp if pp == 1 else 1
+    while mb > 1 and per_dp % mb:
+        mb //= 2
+    return max(1, min(mb, per_dp))
+
+
+def bench_config(a, n_gpus):
+    """``config`` of the JSON line: identical keys and values from both arms for the same command line."""
+    return {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
+            "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
+            "parallelism": parallelism_string(a, n_gpus),
+            "optimizer": "AdamW fp32 master weights (in the timed region), clip 1.0",
+            "l2": "no flush needed: each step streams >100 GB of weights/grads/optimizer state (>> 126 MB L2)"}
+
+
+METRIC = "tokens/sec (whole job, device-timed, max over ranks), {model} {par} seq{seq} training step"
 
 
 def parallelism_string(a, n_gpus):
@@ -206,8 +233,10 @@ def run_ours(a):
     finally:
         pass
     dev = torch.device("cuda", torch.cuda.current_device())
-    n_mb = a.global_batch // a.micro_batch
-    g = torch.Generator().manual_seed(1234)
+    from megatron_llm_b200.parallel import state as ps
+    dp_world, dp_rank = ps.get_data_parallel_world_size(), ps.get_data_parallel_rank()
+    n_mb = a.global_batch // (a.micro_batch * dp_world)     # micro-batches per step on this data-parallel rank
+    g = torch.Generator().manual_seed(1234 + dp_rank)
     # distinct synthetic micro-batches for every step of the run (uniform random tokens: nothing to memorise, the loss
     # stays near ln(vocab)), pinned on the host; both feeds walk the same pool with one shared cursor
     n_pool = min(4096, n_mb * (a.warmup + 2 * a.steps + 3))
@@ -228,7 +257,6 @@ def run_ours(a):
             cursor[0] += 1
             yield {"text": pool_dev[i % n_pool]}
 
-    from megatron_llm_b200.parallel import state as ps
     feeds = ps.get_tensor_model_parallel_rank() == 0
     it_dev = dev_iter() if feeds else None
     it_host = host_iter() if feeds else None
@@ -286,26 +314,27 @@ def run_ours(a):
         ms_e2e, _, last_loss = timed(it_host, a.steps, read_loss=True)
         tokens = a.steps * a.global_batch * a.seq
         e2e = {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s",
-               "h2d_bytes_per_step": n_mb * a.micro_batch * (a.seq + 1) * 8, "d2h_bytes_per_step": 4,
+               "h2d_bytes_per_step": a.global_batch * (a.seq + 1) * 8, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / a.steps, "last_loss": last_loss}
+    peak = torch.tensor([torch.cuda.max_memory_allocated() / 2 ** 30], device=dev)
+    dist.all_reduce(peak, op=dist.ReduceOp.MAX)
+    peak_gb = peak.item()
     sys.stdout = real_stdout
     if rank == 0:
         tokens = a.steps * a.global_batch * a.seq
-        out = {"metric": "tokens/sec (whole job, device-timed, max over ranks), Llama-2-7B TP=#GPUs seq4096 training step",
+        tp = parallel_layout(a, a.gpus)[0]
+        out = {"metric": METRIC.format(model=a.model, par=parallelism_string(a, a.gpus), seq=a.seq),
                "value": tokens / (ms_dev / 1e3), "unit": "tokens/s", "n_gpus": a.gpus, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms_dev / a.steps, "higher_is_better": True, "scaling": "strong",
                "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens (fresh uniform-random micro-batches every step), random-init weights",
                "impl": "ours",
-               "config": {"model": a.model if not a.layers else f"{a.model}[layers={a.layers}:DEV-ONLY]",
-                          "global_batch": a.global_batch, "micro_batch": a.micro_batch, "seq_len": a.seq,
-                          "parallelism": parallelism_string(a, a.gpus),
-                          "cuda_graph_microbatch": bool(getattr(args, "cuda_graph_microbatch", False)),
-                          "tp_comm": ("n/a" if a.gpus == 1 else "fused GEMM+collective kernels over peer memory"
-                                      if _fused_tp_active() else
-                                      "nccl (fused kernels disabled after a handshake timeout)" if fused_fallback
-                                      else "nccl"),
-                          "optimizer": "AdamW fp32 master (in timed region), clip 1.0",
-                          "l2": "no flush needed: each step streams >100 GB of weights/grads/optimizer state (>> 126 MB L2)"},
+               "config": bench_config(a, a.gpus),
+               "details": {"cuda_graph_microbatch": bool(getattr(args, "cuda_graph_microbatch", False)),
+                           "tp_comm": ("n/a" if tp == 1 else "fused GEMM+collective kernels over peer memory"
+                                       if _fused_tp_active() else
+                                       "nccl (fused kernels disabled after a handshake timeout)" if fused_fallback
+                                       else "nccl"),
+                           "peak_mem_gb": round(peak_gb, 2)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                "host_enqueue_ms_per_step": host_enqueue_ms}
         print(json.dumps(out), flush=True)
@@ -320,11 +349,6 @@ def run_ours(a):
 
 
 def run_reference(a):
-    tp, pp, dp = parallel_layout(a, a.gpus)
-    if (tp, pp) != (a.gpus, 1) or a.recompute or a.dist_opt or a.model.startswith("falcon"):
-        print(json.dumps({"impl": "reference", "unavailable": "the reference arm drives the headline configuration only "
-                          "(Llama/Mistral, TP = #GPUs, no recompute)"}))
-        return
     ref_root = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref_root, "megatron")):
         print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/megatron is missing (reference not installed)"}))
@@ -332,7 +356,7 @@ def run_reference(a):
     try:
         sys.path.insert(0, os.path.join(ROOT, "baseline"))
         import reference_runner
-        reference_runner.main(a, MODELS, ClockSampler)
+        reference_runner.main(a, MODELS, ClockSampler, sys.modules[__name__])
     except SystemExit:
         raise
     except Exception as e:
@@ -344,6 +368,7 @@ def run_reference(a):
 
 if __name__ == "__main__":
     a = parse()
+    a.micro_batch = resolve_micro_batch(a, a.gpus)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -67,23 +67,23 @@ static int pick_group_blocks(int64_t rows_per_rank, int64_t b_bytes) {
   return per_rank >= 2 ? 2 : 1;
 }
 
-// Number of puller CTAs for all-gather -> GEMM.  Every puller moves ~PULL_GBPS (one thread, 5 x 32 KB bulk copies in
-// flight over an NVLink round trip; measured 25-37 GB/s) and costs the GEMM one SM, so small GEMMs behind a big gather want many pullers
-// and big GEMMs few: minimise  max(gemm(c), pull(c) + one tile group of gemm(c))  over even c <= max_ctas.
+// Number of puller CTAs for all-gather -> GEMM.  Measured pairwise on B200 (profiles/nvlink_n2_r2.jsonl): a bulk-copy
+// puller CTA moves ~44 GB/s and the link saturates near 470 GB/s (16 CTAs) for 16 MB messages.  Every puller costs the
+// GEMM one SM, so small GEMMs behind a big gather want many pullers and big GEMMs few:
+// minimise  max(gemm(c), pull(c) + one tile group of gemm(c))  over even c <= max_ctas.
 static int pick_comm_ctas(int64_t M, int64_t N, int64_t K, int64_t rows_per_rank, int world, int max_ctas, int sms) {
   static const char* fixed = getenv("MLB200_AG_CTAS_FIXED");
   if (fixed) return std::min(max_ctas, atoi(fixed));
-  constexpr double PULL_GBPS = 25.0, GEMM_TFLOPS = 1350.0;
-  const double chunk_us = 128.0 * K * 2 / (PULL_GBPS * 1e3);
+  constexpr double PULL_GBPS = 40.0, LINK_GBPS = 470.0, GEMM_TFLOPS = 1350.0;
+  const double chunk_bytes = 128.0 * K * 2;
   const int remote_chunks = (int)((world - 1) * rows_per_rank / 128);
   const int groups = std::max<int>(1, (int)(M / 256 / pick_group_blocks(rows_per_rank, N * K * 2)));
   int best = 2;
   double best_t = 1e30;
   for (int c = 2; c <= max_ctas; c += 2) {
     const double gemm_us = 2.0 * M * N * K / (GEMM_TFLOPS * 1e6) * sms / (double)(sms - c) + 4.0;
-    // whole chunks per puller, or (MLB200_AG_STREAM) every chunk shared piece-wise by all pullers
-    static const bool stream = getenv("MLB200_AG_STREAM") != nullptr;
-    const double pull_us = stream ? remote_chunks * chunk_us / c : ((remote_chunks + c - 1) / c) * chunk_us;
+    const double rate = std::min(PULL_GBPS * c, LINK_GBPS) / c;                       // GB/s per puller
+    const double pull_us = ((remote_chunks + c - 1) / c) * chunk_bytes / (rate * 1e3);  // whole chunks per puller
     const double t = std::max(gemm_us, pull_us + gemm_us / groups);
     if (t < best_t * 0.995) { best_t = t; best = c; }
   }
@@ -117,60 +117,10 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
   c.ag_row_bytes = K * 2;
   c.ag_chunk_flags = chunk_flags.data_ptr<int>();
   c.ag_read_counters = read_counters.data_ptr<int>();
-  // streaming pullers (opt-in until measured on hardware): per-chunk piece counters live behind the 8 peer counters
-  static const bool stream = getenv("MLB200_AG_STREAM") != nullptr;
-  if (stream && read_counters.numel() >= 8 + M / mlb::GEMM_BLOCK_M) {
-    c.ag_stream = 1;
-    c.ag_chunk_counts = read_counters.data_ptr<int>() + 8;
-  }
   fill_pads(c, pad_local, pad_peers);
   // the 2-CTA (256x256-tile, TMA-store epilogue) kernel when the shard is a whole number of its row blocks
   static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;
   if (!force_1cta && rows_per_rank % 256 == 0 && num_comm_ctas % 2 == 0 && N >= 256 && (out.stride(0) * 2) % 16 == 0) {
-    CHK(mlb_gemm_bf16_2cta_ag(gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
-                              (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(),
-                              cur()));
-    return;
-  }
-  CHK(mlb_gemm_bf16_fused(mlb::MODE_AG_GEMM, gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
-                          (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
-}
-
-// Push variant of the all-gather -> GEMM (opt-in, MLB200_AG_PUSH): `gathered` is this rank's symmetric gather buffer
-// of the call's parity viewed as [M, K]; the pusher CTAs store `x_shard` into everybody's buffer (push_dst[d]) and
-// count pieces into sig[d]; the GEMM reads A from `gathered`.
-static void fused_ag_gemm_push(torch::Tensor& gathered, const torch::Tensor& x_shard, const torch::Tensor& weight,
-                               torch::Tensor& out, bool b_mn, const std::vector<int64_t>& push_dst,
-                               const std::vector<int64_t>& sig, torch::Tensor& done_counter, int64_t rows_per_rank,
-                               int64_t pad_local, const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world,
-                               int64_t epoch, int64_t num_comm_ctas, int64_t sms, int64_t state_ptr) {
-  c10::cuda::CUDAGuard guard(gathered.device());
-  const int M = gathered.size(0), K = gathered.size(1);
-  const int N = b_mn ? weight.size(1) : weight.size(0);
-  TORCH_CHECK(gathered.is_contiguous() && x_shard.is_contiguous() && out.stride(1) == 1 && weight.stride(1) == 1);
-  TORCH_CHECK(x_shard.size(0) == rows_per_rank && x_shard.size(1) == K && M == rows_per_rank * world);
-  TORCH_CHECK(rows_per_rank % mlb::GEMM_BLOCK_M == 0 && K % 8 == 0 && N % 8 == 0);
-  TORCH_CHECK((uintptr_t)x_shard.data_ptr() % 16 == 0 && num_comm_ctas >= 2 && num_comm_ctas % 2 == 0);
-  mlb::GemmComm c;
-  memset(&c, 0, sizeof(c));
-  c.rank = rank; c.world = world; c.epoch = epoch;
-  c.num_comm_ctas = (int)num_comm_ctas;
-  c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
-  c.m_rotate_blocks = (int)(rank * rows_per_rank / mlb::GEMM_BLOCK_M);
-  c.state = reinterpret_cast<const int*>(state_ptr);
-  c.ag_push = 1;
-  c.ag_local_src = x_shard.data_ptr();
-  for (int i = 0; i < world; ++i) {
-    c.ag_push_dst[i] = reinterpret_cast<void*>(push_dst[i]);
-    c.ag_sig_peer[i] = reinterpret_cast<int*>(sig[i]);
-  }
-  c.ag_dst = gathered.data_ptr();
-  c.ag_rows_per_rank = rows_per_rank;
-  c.ag_row_bytes = K * 2;
-  c.ag_done_counter = done_counter.data_ptr<int>();
-  fill_pads(c, pad_local, pad_peers);
-  static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;
-  if (!force_1cta && rows_per_rank % 256 == 0 && N >= 256 && (out.stride(0) * 2) % 16 == 0) {
     CHK(mlb_gemm_bf16_2cta_ag(gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K,
                               (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(),
                               cur()));
@@ -269,7 +219,6 @@ void register_comm(pybind11::module_& m) {
   m.def("comm_copy2", &comm_copy2);
   m.def("comm_set_state", &comm_set_state);
   m.def("fused_ag_gemm", &fused_ag_gemm);
-  m.def("fused_ag_gemm_push", &fused_ag_gemm_push);
   m.def("fused_gemm_rs", &fused_gemm_rs);
   m.def("dp_reduce", &dp_reduce);
 }

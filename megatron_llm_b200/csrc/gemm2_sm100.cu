@@ -151,10 +151,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
         if constexpr (MODE == MODE_AG_GEMM) {
-          if (p.comm.ag_push) {                                 // every chunk (own rows too) arrives through a pusher
-            spin_until_ge(p.comm.ag_sig_peer[p.comm.rank] + (m0 >> 7), ag_pieces_per_chunk(p.comm), p.comm.pad_local);
-            fence_proxy_async_global();
-          } else if (m0 / p.comm.ag_rows_per_rank != p.comm.rank) {   // (the own shard was placed before the launch)
+          if (m0 / p.comm.ag_rows_per_rank != p.comm.rank) {   // (the own shard was placed before the launch)
             spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
             fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
           }
@@ -394,9 +391,6 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 
   if constexpr (MODE == MODE_GEMM_RS) rs_reduce_phase(p);
-  if constexpr (MODE == MODE_AG_GEMM) {
-    if (p.comm.ag_push && threadIdx.x == 0) ag_push_finish(p.comm);   // (after the cluster barrier: no TMA load left)
-  }
 }
 
 template <bool A_MN, bool B_MN, int EPI, int MODE = MODE_PLAIN>

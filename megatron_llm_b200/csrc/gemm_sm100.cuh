@@ -76,232 +76,7 @@ __device__ __forceinline__ int comm_rs_expected(const GemmComm& c) {
   return c.rs_expected_total + (c.state ? *reinterpret_cast<const volatile int*>(c.state + STATE_RS_TOTAL) : 0);
 }
 
-// Streaming variant (GemmComm::ag_stream): the remote 32 KB pieces, taken in the order the GEMM consumes them, are dealt
-// round-robin to ALL puller CTAs, so chunk j completes after ~(j+1)/num_chunks of the gather instead of every puller
-// finishing "its" chunks at the very end.  (With whole chunks per puller, TP=8 had 28 pullers each delivering one
-// chunk ~40 us into a 60 us GEMM: the compute CTAs sat idle until then.)  A chunk's flag is released by the puller that
-// delivers its last piece (local counter, self-resetting).
-static __device__ void ag_puller_stream(const GemmComm& c, uint8_t* smem, int comm_id) {
-  if (threadIdx.x != 0) return;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);
-  for (int i = 0; i < AG_STAGES; ++i) mbar_init(&bars[i], 1);
-  fence_barrier_init();
-  fence_proxy_async_smem();
-
-  const int epoch = comm_epoch(c, STATE_AG_EPOCH);
-  const int C = c.num_comm_ctas;
-  const int cpr = c.ag_rows_per_rank / GEMM_BLOCK_M;                      // chunks per rank
-  const long long chunk_bytes = (long long)GEMM_BLOCK_M * c.ag_row_bytes;
-  const int ppc = (int)((chunk_bytes + AG_PIECE_BYTES - 1) / AG_PIECE_BYTES);   // pieces per chunk
-  const long long total = (long long)(c.world - 1) * cpr * ppc;          // remote pieces in consumption order
-  const long long n_mine = total > comm_id ? (total - comm_id + C - 1) / C : 0;
-
-  if (comm_id == 0) {
-    __threadfence_system();
-    for (int p = 0; p < c.world; ++p)
-      if (p != c.rank) st_release_sys(c.pad_peer[p] + PAD_AG_READY + c.rank, epoch);
-  }
-
-  struct Piece { int peer, chunk; long long off; uint32_t bytes; };
-  auto locate = [&](long long k) {
-    const long long s = comm_id + k * C;
-    const int rc = (int)(s / ppc);                       // remote chunk index in consumption order
-    const int piece = (int)(s - (long long)rc * ppc);
-    const int i = rc / cpr + 1;
-    Piece q;
-    q.peer = (c.rank + i) % c.world;
-    q.chunk = rc - (i - 1) * cpr;
-    q.off = (long long)piece * AG_PIECE_BYTES;
-    q.bytes = (uint32_t)min((long long)AG_PIECE_BYTES, chunk_bytes - q.off);
-    return q;
-  };
-  uint32_t ready_mask = 0, phase_bits = 0;
-  auto issue = [&](long long k) {
-    const Piece q = locate(k);
-    if (!((ready_mask >> q.peer) & 1u)) {
-      spin_until_ge(c.pad_local + PAD_AG_READY + q.peer, epoch, c.pad_local);
-      fence_proxy_async_global();
-      ready_mask |= 1u << q.peer;
-    }
-    const int stage = (int)(k % AG_STAGES);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.ag_src[q.peer]) + q.chunk * chunk_bytes + q.off;
-    mbar_arrive_expect_tx(&bars[stage], q.bytes);
-    bulk_g2s(smem + stage * AG_PIECE_BYTES, src, q.bytes, &bars[stage]);
-  };
-  // pieces [retired, upto) are in local HBM: count them into their chunks; the last piece of a chunk releases its flag
-  long long retired = 0;
-  auto retire = [&](long long upto) {
-    if (upto <= retired) return;
-    fence_proxy_async_global();
-    __threadfence();
-    for (long long k = retired; k < upto; ++k) {
-      const Piece q = locate(k);
-      const int g = q.peer * cpr + q.chunk;
-      if (atomicAdd(c.ag_chunk_counts + g, 1) + 1 == ppc) {
-        c.ag_chunk_counts[g] = 0;
-        __threadfence();
-        st_release_sys(c.ag_chunk_flags + g, epoch);
-      }
-    }
-    retired = upto;
-  };
-  constexpr int LAG = 4;   // local stores complete within a few pieces: counting them LAG behind never waits
-  long long issued = 0, stored = 0;
-  while (issued < n_mine && issued < AG_STAGES - 1) issue(issued++);
-  while (stored < n_mine) {
-    const int stage = (int)(stored % AG_STAGES);
-    mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
-    phase_bits ^= (1u << stage);
-    const Piece q = locate(stored);
-    uint8_t* dst = reinterpret_cast<uint8_t*>(c.ag_dst) + ((long long)q.peer * cpr + q.chunk) * chunk_bytes + q.off;
-    bulk_s2g(dst, smem + stage * AG_PIECE_BYTES, q.bytes);
-    tma_store_commit();
-    ++stored;
-    if (issued < n_mine) {
-      tma_store_wait_read<1>();     // the stage refilled next held the piece stored one iteration ago
-      issue(issued++);
-    }
-    if (stored > LAG) {
-      tma_store_wait<LAG>();
-      retire(stored - LAG);
-    }
-  }
-  tma_store_wait<0>();
-  retire(n_mine);
-  // every puller is done reading every peer: the last one acknowledges, so the owners may overwrite their shards
-  __threadfence();
-  for (int p = 0; p < c.world; ++p) {
-    if (p == c.rank) continue;
-    if (atomicAdd(c.ag_read_counters + p, 1) + 1 == C) {
-      c.ag_read_counters[p] = 0;
-      __threadfence_system();
-      st_release_sys(c.pad_peer[p] + PAD_AG_ACK + c.rank, epoch);
-    }
-  }
-  if (comm_id == 0) {
-    for (int p = 0; p < c.world; ++p)
-      if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, epoch, c.pad_local);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// push variant: the OWNER moves its shard.  Loads are local (short latency), the stores are posted writes into every
-// rank's gather buffer, and a stage of the smem ring is free again as soon as its store has been *read*
-// (wait_group.read) -- the NVLink round trip only delays the arrival signal, which runs PUSH_LAG pieces behind.
-// Arrival = per-chunk piece counters at the destination (red.release.sys); the consumer waits for `pieces per chunk`.
-// The counters are zeroed, and the buffer handed back (PAD_AG_FREE = epoch), by the last CTA of the destination's own
-// launch; two buffer parities let call e+1 be pushed while call e is still being consumed.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int ag_pieces_per_chunk(const GemmComm& c) {
-  return (int)(((long long)GEMM_BLOCK_M * c.ag_row_bytes + AG_PIECE_BYTES - 1) / AG_PIECE_BYTES);
-}
-
-// called by one thread of every CTA of the launch (compute CTAs and pushers) when it is done with the gather buffer
-static __device__ void ag_push_finish(const GemmComm& c) {
-  __threadfence();
-  if (atomicAdd(c.ag_done_counter, 1) + 1 != (int)gridDim.x) return;
-  *c.ag_done_counter = 0;
-  const int chunks = c.world * (c.ag_rows_per_rank / GEMM_BLOCK_M);
-  int* sig = c.ag_sig_peer[c.rank];
-  for (int i = 0; i < chunks; ++i) sig[i] = 0;
-  __threadfence_system();
-  const int epoch = comm_epoch(c, STATE_AG_EPOCH);
-  for (int d = 0; d < c.world; ++d)
-    if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_AG_FREE + c.rank, epoch);
-}
-
-static __device__ void ag_pusher(const GemmComm& c, uint8_t* smem, int comm_id) {
-  if (threadIdx.x != 0) return;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);
-  for (int i = 0; i < AG_STAGES; ++i) mbar_init(&bars[i], 1);
-  fence_barrier_init();
-  fence_proxy_async_smem();
-
-  const int epoch = comm_epoch(c, STATE_AG_EPOCH);
-  const int C = c.num_comm_ctas;
-  const int cpr = c.ag_rows_per_rank / GEMM_BLOCK_M;
-  const long long chunk_bytes = (long long)GEMM_BLOCK_M * c.ag_row_bytes;
-  const int ppc = ag_pieces_per_chunk(c);
-  const long long total = (long long)cpr * ppc;                  // pieces of my shard
-  const long long n_mine = total > comm_id ? (total - comm_id + C - 1) / C : 0;
-
-  // a destination's buffer of this parity was last used two calls ago: wait until its GEMM of that call retired
-  for (int d = 0; d < c.world; ++d)
-    if (d != c.rank) spin_until_ge(c.pad_local + PAD_AG_FREE + d, epoch - 2, c.pad_local);
-
-  struct Piece { int chunk; long long off; uint32_t bytes; };
-  auto locate = [&](long long k) {
-    const long long s = comm_id + k * C;
-    Piece q;
-    q.chunk = (int)(s / ppc);
-    q.off = (s - (long long)q.chunk * ppc) * AG_PIECE_BYTES;
-    q.bytes = (uint32_t)min((long long)AG_PIECE_BYTES, chunk_bytes - q.off);
-    return q;
-  };
-  uint32_t phase_bits = 0;
-  auto issue = [&](long long k) {
-    const Piece q = locate(k);
-    const int stage = (int)(k % AG_STAGES);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(c.ag_local_src) + q.chunk * chunk_bytes + q.off;
-    mbar_arrive_expect_tx(&bars[stage], q.bytes);
-    bulk_g2s(smem + stage * AG_PIECE_BYTES, src, q.bytes, &bars[stage]);
-  };
-  // pieces [retired, upto) have completed at every destination: add them to the destinations' chunk counters
-  long long retired = 0;
-  auto retire = [&](long long upto) {
-    if (upto <= retired) return;
-    fence_proxy_async_global();
-    __threadfence_system();
-    long long k = retired;
-    while (k < upto) {
-      const int chunk = locate(k).chunk;
-      int n = 0;
-      while (k < upto && locate(k).chunk == chunk) { ++n; ++k; }
-      for (int i = 1; i <= c.world; ++i) {
-        const int d = (c.rank + i) % c.world;                     // own counter last
-        red_add_release_sys(c.ag_sig_peer[d] + c.rank * cpr + chunk, n);
-      }
-    }
-    retired = upto;
-  };
-  constexpr int PUSH_LAG = 8;
-  long long issued = 0, stored = 0;
-  while (issued < n_mine && issued < AG_STAGES - 1) issue(issued++);
-  while (stored < n_mine) {
-    const int stage = (int)(stored % AG_STAGES);
-    mbar_wait(&bars[stage], (phase_bits >> stage) & 1u);
-    phase_bits ^= (1u << stage);
-    const Piece q = locate(stored);
-    const long long dst_off = ((long long)c.rank * cpr + q.chunk) * chunk_bytes + q.off;
-    for (int i = 1; i <= c.world; ++i) {
-      const int d = (c.rank + i) % c.world;
-      bulk_s2g(reinterpret_cast<uint8_t*>(c.ag_push_dst[d]) + dst_off, smem + stage * AG_PIECE_BYTES, q.bytes);
-    }
-    tma_store_commit();                                            // one bulk group per piece (all destinations)
-    ++stored;
-    if (issued < n_mine) {
-      tma_store_wait_read<1>();
-      issue(issued++);
-    }
-    if (stored > PUSH_LAG) {
-      tma_store_wait<PUSH_LAG>();
-      retire(stored - PUSH_LAG);
-    }
-  }
-  tma_store_wait<0>();
-  retire(n_mine);
-  ag_push_finish(c);
-}
-
 static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
-  if (c.ag_push) {
-    ag_pusher(c, smem, comm_id);
-    return;
-  }
-  if (c.ag_stream) {
-    ag_puller_stream(c, smem, comm_id);
-    return;
-  }
   // one thread drives the whole copy pipeline (bulk copies are issued by a single thread anyway)
   if (threadIdx.x != 0) return;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);
@@ -548,9 +323,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
         if constexpr (MODE == MODE_AG_GEMM) {
-          if (p.comm.ag_push)                                   // every chunk (own rows too) arrives through a pusher
-            spin_until_ge(p.comm.ag_sig_peer[p.comm.rank] + m_blk, ag_pieces_per_chunk(p.comm), p.comm.pad_local);
-          else if (m0 / p.comm.ag_rows_per_rank != p.comm.rank)     // (the own shard was placed before the launch)
+          if (m0 / p.comm.ag_rows_per_rank != p.comm.rank)     // (the own shard was placed before the launch)
             spin_until_ge(p.comm.ag_chunk_flags + m_blk, comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
           fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
         }
@@ -713,9 +486,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   if constexpr (MODE == MODE_GEMM_RS) rs_reduce_phase(p);
-  if constexpr (MODE == MODE_AG_GEMM) {
-    if (p.comm.ag_push && threadIdx.x == 0) ag_push_finish(p.comm);   // (after the __syncthreads above: no TMA load left)
-  }
 }
 
 }  // namespace mlb

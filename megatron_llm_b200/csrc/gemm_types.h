@@ -25,7 +25,6 @@ enum PadSlot : int {
   PAD_RS_ARRIVED = 16,  // [src]: cumulative number of tiles src delivered into my receive slots
   PAD_RS_FREE = 24,   // [dst]  : dst finished reducing epoch e (its receive slot of parity e may be reused)
   PAD_ERROR = 32,     // spin-wait timeout marker (debug)
-  PAD_AG_FREE = 40,   // [dst]  : (push all-gather) dst finished the GEMM of epoch e: its gather buffer of that parity is free
   PAD_INTS = 64,
 };
 
@@ -42,15 +41,6 @@ struct GemmComm {
   int ag_row_bytes;                    // K * 2
   int* ag_chunk_flags;                 // local, one per 128-row chunk of the gathered buffer: set to epoch
   int* ag_read_counters;               // local, [world]: puller CTAs done with peer p (for the ack)
-  int* ag_chunk_counts;                // local, one per 128-row chunk: pieces delivered (streaming pullers), self-resetting
-  int ag_stream;                       // 1: all pullers share every chunk piece-wise, chunks complete in arrival order
-  // ---- push variant of the all-gather (opt-in): the owner's pusher CTAs store their shard into every rank's
-  //      symmetric gather buffer (posted bulk stores) and bump per-chunk arrival counters there; A is read from it
-  int ag_push;
-  const void* ag_local_src;            // this rank's shard [rows_per_rank, K] (any local tensor)
-  void* ag_push_dst[GEMM_MAX_PEERS];   // rank d's gather buffer of this epoch parity (NVLink-mapped; [rank] = local)
-  int* ag_sig_peer[GEMM_MAX_PEERS];    // rank d's per-chunk piece counters of this parity ([rank] = local)
-  int* ag_done_counter;                // local: CTAs of this launch that are finished (last one frees the buffer)
   // ---- reduce-scatter side
   void* rs_dst[GEMM_MAX_PEERS];        // rs_dst[d]: my receive slot on rank d: [rows_per_rank, N] bf16
   const void* rs_slots;                // local receive buffer of this epoch parity: [world][rows_per_rank, N]

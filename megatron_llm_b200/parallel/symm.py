@@ -40,6 +40,27 @@ def _alloc_symmetric(numel: int, dtype, device, group):
     return t, hdl
 
 
+class LoopbackWorld:
+    """``world`` virtual ranks on ONE device (tests / single-GPU leases): the "symmetric" buffers are ordinary
+    allocations of the same process, so every rank's kernels see the others' buffers through plain device pointers,
+    and the rank kernels are launched on separate streams with ``sms`` SMs each so that all of them are resident at the
+    same time (they spin on each other's flags).  Exercises the whole flag / epoch / slot protocol and the address
+    arithmetic of the fused kernels without NVLink."""
+
+    def __init__(self, world: int, sms: Optional[int] = None, device=None):
+        self.world = world
+        self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        total = torch.cuda.get_device_properties(self.device).multi_processor_count
+        self.sms = sms if sms is not None else max(2, ((total - 4) // world) & ~1)
+        self._bufs = {}
+
+    def alloc(self, name: str, numel: int, dtype):
+        """-> list of ``world`` tensors (index = rank); created on first use, shared by all virtual ranks."""
+        if name not in self._bufs:
+            self._bufs[name] = [torch.zeros(numel, dtype=dtype, device=self.device) for _ in range(self.world)]
+        return self._bufs[name]
+
+
 class TPCommunicator:
     """Fused GEMM+collective for one tensor-parallel group.
 
@@ -50,48 +71,55 @@ class TPCommunicator:
     """
 
     def __init__(self, group, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 8,
-                 ag_k: Optional[int] = None):
+                 loopback: Optional[LoopbackWorld] = None, loopback_rank: int = 0):
         self.group = group
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
-        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.loopback = loopback
+        if loopback is not None:
+            self.world, self.rank, self.device = loopback.world, loopback_rank, loopback.device
+            self.sms = loopback.sms          # SMs this virtual rank's kernels may occupy
+        else:
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+            self.device = torch.device("cuda", torch.cuda.current_device())
+            self.sms = 0                     # 0 = all SMs of the device
         self.max_rows, self.max_k, self.max_n = max_rows_per_rank, max_k, max_n
         self.num_comm_ctas = num_comm_ctas
         self.enabled = False
         self.mod = _ext.load()
-        self.xs, self.h_xs = _alloc_symmetric(max_rows_per_rank * max_k, torch.bfloat16, self.device, group)
-        self.rs, self.h_rs = _alloc_symmetric(2 * self.world * max_rows_per_rank * max_n, torch.bfloat16, self.device,
-                                              group)
-        self.pad, self.h_pad = _alloc_symmetric(_PAD_INTS, torch.int32, self.device, group)
+        self.xs, self.xs_ptrs = self._symmetric("xs", max_rows_per_rank * max_k, torch.bfloat16)
+        self.rs, self.rs_ptrs = self._symmetric("rs", 2 * self.world * max_rows_per_rank * max_n, torch.bfloat16)
+        self.pad, self.pad_ptrs = self._symmetric("pad", _PAD_INTS, torch.int32)
         self.pad.zero_()
-        self.xs_ptrs = [int(p) for p in self.h_xs.buffer_ptrs]
-        self.rs_ptrs = [int(p) for p in self.h_rs.buffer_ptrs]
-        self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
         max_chunks = self.world * max_rows_per_rank // 128
         self.chunk_flags = torch.zeros(max(max_chunks, 1), dtype=torch.int32, device=self.device)
-        # [0:8] pullers done per peer; [8:] pieces delivered per 128-row chunk (streaming pullers); self-resetting
-        self.read_counters = torch.zeros(8 + max(max_chunks, 1), dtype=torch.int32, device=self.device)
+        self.read_counters = torch.zeros(8, dtype=torch.int32, device=self.device)   # pullers done per peer (self-resetting)
         self.reduce_counter = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.ag_epoch = 0
         self.rs_epoch = 0
         self.rs_arrived_total = 0
-        # push variant of the all-gather (opt-in): two parities of a symmetric gather buffer + arrival counters
-        self.push = os.environ.get("MLB200_AG_PUSH", "0") == "1"
-        if self.push:
-            self.ag_k = ag_k or max_k
-            self.agbuf, self.h_agbuf = _alloc_symmetric(2 * self.world * max_rows_per_rank * self.ag_k, torch.bfloat16,
-                                                        self.device, group)
-            self.agsig, self.h_agsig = _alloc_symmetric(2 * max(max_chunks, 1), torch.int32, self.device, group)
-            self.agsig.zero_()
-            self.agbuf_ptrs = [int(p) for p in self.h_agbuf.buffer_ptrs]
-            self.agsig_ptrs = [int(p) for p in self.h_agsig.buffer_ptrs]
-            self.ag_done = torch.zeros(1, dtype=torch.int32, device=self.device)
-            self.push_ctas = int(os.environ.get("MLB200_AG_PUSH_CTAS", "8"))
         # offsets that calls captured in a CUDA graph add to their (frozen) epoch arguments -- see replay_offsets()
         self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
         torch.cuda.synchronize()
-        dist.barrier(group=group)
+        if loopback is None:
+            dist.barrier(group=group)
         self.enabled = True
+
+    def _symmetric(self, name: str, numel: int, dtype):
+        """(this rank's buffer, every rank's device pointer to its copy)"""
+        if self.loopback is not None:
+            bufs = self.loopback.alloc(name, numel, dtype)
+            return bufs[self.rank], [int(t.data_ptr()) for t in bufs]
+        t, hdl = _alloc_symmetric(numel, dtype, self.device, self.group)
+        self._handles = getattr(self, "_handles", []) + [hdl]       # keep the peer mappings alive
+        return t, [int(p) for p in hdl.buffer_ptrs]
+
+    @classmethod
+    def loopback_group(cls, world: int, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 4,
+                       sms: Optional[int] = None):
+        """``world`` communicators that talk to each other on the current device (see :class:`LoopbackWorld`)."""
+        lw = LoopbackWorld(world, sms)
+        return [cls(None, max_rows_per_rank, max_k, max_n, num_comm_ctas, loopback=lw, loopback_rank=r)
+                for r in range(world)]
 
     # -------------------------------------------------------------------------------------------
     def supports(self, rows_per_rank: int, k: int, n: int) -> bool:
@@ -102,16 +130,14 @@ class TPCommunicator:
                 keep: bool = True):
         """x_shard [m, ..., K] (this rank's rows) -> (out [world*m*..., N], gathered [world*m, ..., K]).
 
-        ``keep=False`` says the caller consumes ``gathered`` before the next call on this communicator (the push
-        variant then returns a view of its symmetric buffer instead of a copy)."""
+        ``keep`` is accepted for interface stability (a transport that gathers into communicator-owned memory would
+        have to copy when the caller keeps ``gathered`` for backward); this one gathers into a fresh tensor."""
         lead = x_shard.shape[:-1]
         K = x_shard.size(-1)
         x2d = x_shard.reshape(-1, K)
         m = x2d.size(0)
         N = weight.size(1) if transposed_weight else weight.size(0)
         assert m <= self.max_rows and K <= self.max_k and m % 128 == 0, (m, K, self.max_rows, self.max_k)
-        if self.push and K <= self.ag_k:
-            return self._ag_gemm_push(x2d, weight, transposed_weight, out, keep, lead, m, K, N)
         # publish my shard (stream-ordered before the kernel; the previous call's kernel only retired after every
         # peer had acknowledged reading the old content)
         gathered = torch.empty((self.world * m, K), dtype=torch.bfloat16, device=self.device)
@@ -130,29 +156,8 @@ class TPCommunicator:
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
         self.mod.fused_ag_gemm(gathered, w, out, transposed_weight, self.xs_ptrs, m, self.chunk_flags,
                                self.read_counters, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
-                               self.ag_epoch, self.num_comm_ctas, 0, self._state_ptr())
+                               self.ag_epoch, self.num_comm_ctas, self.sms, self._state_ptr())
         _ext.count()
-        return out, gathered.view(self.world * lead[0], *lead[1:], K)
-
-    def _ag_gemm_push(self, x2d, weight, transposed_weight, out, keep, lead, m, K, N):
-        self.ag_epoch += 1
-        parity = self.ag_epoch % 2
-        buf_elems = self.world * self.max_rows * self.ag_k           # one parity of the gather buffer
-        sig_ints = self.agsig.numel() // 2
-        view = self.agbuf[parity * buf_elems: parity * buf_elems + self.world * m * K].view(self.world * m, K)
-        push_dst = [p + 2 * parity * buf_elems for p in self.agbuf_ptrs]
-        sig = [p + 4 * parity * sig_ints for p in self.agsig_ptrs]
-        if out is None:
-            out = torch.empty((self.world * m, N), dtype=torch.bfloat16, device=self.device)
-        x = x2d.contiguous()
-        if x.data_ptr() % 16:
-            x = x.clone()
-        w = weight if weight.stride(-1) == 1 else weight.contiguous()
-        self.mod.fused_ag_gemm_push(view, x, w, out, transposed_weight, push_dst, sig, self.ag_done, m,
-                                    self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.ag_epoch,
-                                    self.push_ctas, 0, self._state_ptr())
-        _ext.count()
-        gathered = view.clone() if keep else view
         return out, gathered.view(self.world * lead[0], *lead[1:], K)
 
     def gemm_rs(self, x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
@@ -174,8 +179,8 @@ class TPCommunicator:
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
         self.rs_arrived_total = self.mod.fused_gemm_rs(
             x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total, tiles_per_dst,
-            self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch, 0,
-            self._state_ptr())
+            self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch,
+            self.sms, self._state_ptr())
         _ext.count()
         return out
 
@@ -203,8 +208,6 @@ class TPCommunicator:
         handshake only needs monotonic epochs.)"""
         if (self.rs_epoch - before[1]) % 2:
             self.rs_epoch += 1
-        if getattr(self, "push", False) and (self.ag_epoch - before[0]) % 2:   # (push all-gather: parity is frozen too)
-            self.ag_epoch += 1
         self.mod.comm_set_state(self.state, self.ag_epoch - before[0], self.rs_epoch - before[1],
                                 self.rs_arrived_total - before[2])
         self.ag_epoch += advance[0]
@@ -213,7 +216,7 @@ class TPCommunicator:
 
     def _num_n_tiles(self, M: int, N: int) -> int:
         """Mirror of ``pick_block_n`` in csrc/gemm_sm100.cu (the arrival counters count output tiles)."""
-        sms = self.mod.num_sms()
+        sms = self.sms or self.mod.num_sms()
 
         def cost(bn):
             tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
@@ -229,25 +232,34 @@ class TPCommunicator:
 class DPCommunicator:
     """Peer-memory gradient reduction for one data-parallel group: the whole fp32 grad buffer is symmetric."""
 
-    def __init__(self, group, numel_padded: int, num_ctas: int = 32):
+    def __init__(self, group, numel_padded: int, num_ctas: int = 32, loopback: Optional[LoopbackWorld] = None,
+                 loopback_rank: int = 0):
         self.group = group
-        self.world = dist.get_world_size(group)
-        self.rank = dist.get_rank(group)
-        self.device = torch.device("cuda", torch.cuda.current_device())
+        self.loopback = loopback
+        if loopback is not None:
+            self.world, self.rank, self.device = loopback.world, loopback_rank, loopback.device
+        else:
+            self.world = dist.get_world_size(group)
+            self.rank = dist.get_rank(group)
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.mod = _ext.load()
         self.num_ctas = num_ctas
         self.enabled = False
-        self.buffer, self.h_buf = _alloc_symmetric(numel_padded, torch.float32, self.device, group)
+        self.buffer, self.buf_ptrs = TPCommunicator._symmetric(self, "dp_buffer", numel_padded, torch.float32)
         self.buffer.zero_()
-        self.pad, self.h_pad = _alloc_symmetric(_PAD_INTS, torch.int32, self.device, group)
+        self.pad, self.pad_ptrs = TPCommunicator._symmetric(self, "dp_pad", _PAD_INTS, torch.int32)
         self.pad.zero_()
-        self.buf_ptrs = [int(p) for p in self.h_buf.buffer_ptrs]
-        self.pad_ptrs = [int(p) for p in self.h_pad.buffer_ptrs]
         self.epoch = 0
         self.stream = torch.cuda.Stream(priority=-1)
         torch.cuda.synchronize()
-        dist.barrier(group=group)
+        if loopback is None:
+            dist.barrier(group=group)
         self.enabled = True
+
+    @classmethod
+    def loopback_group(cls, world: int, numel_padded: int, num_ctas: int = 16):
+        lw = LoopbackWorld(world)
+        return [cls(None, numel_padded, num_ctas, loopback=lw, loopback_rank=r) for r in range(world)]
 
     def reduce_bucket(self, view: torch.Tensor, start: int, numel_padded: int, reduce_scatter: bool):
         """``view`` = buffer[start:end] (a slice of the symmetric grad buffer).  Returns an object with ``wait()``."""
@@ -284,8 +296,7 @@ def bind_tp_communicator(args) -> Optional[TPCommunicator]:
     vocab_shard = getattr(args, "padded_vocab_size", 0) // tp
     max_n = max(args.hidden_size, ffn // tp, vocab_shard)
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), rows, max_k, max_n,
-                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")),   # upper bound: picked per shape
-                          ag_k=args.hidden_size)          # every all-gathered operand has K = hidden size
+                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")))   # upper bound: picked per shape
     fused_tp.bind(comm)
     return comm
 

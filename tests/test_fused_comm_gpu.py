@@ -1,4 +1,5 @@
-"""Fused GEMM+collective kernels and the peer-memory DP reduction vs. the unfused NCCL path (needs >= 2 B200s)."""
+"""Fused GEMM+collective kernels and the peer-memory DP reduction vs. the unfused NCCL path (needs >= 2 B200s).
+The same kernels are exercised on ONE GPU by tests/test_fused_loopback_gpu.py (virtual ranks on one device)."""
 import os
 
 import pytest
@@ -8,11 +9,6 @@ import torch.distributed as dist
 from tests.dist_utils import run_distributed
 
 pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
-
-# Variants that were written after the last hardware session of the round they were added in: they run only on request
-# (MLB200_TEST_EXPERIMENTAL=1) until they have passed on a GPU box once, then the marker is dropped.
-experimental = pytest.mark.skipif(os.environ.get("MLB200_TEST_EXPERIMENTAL", "0") != "1",
-                                  reason="not yet validated on hardware; set MLB200_TEST_EXPERIMENTAL=1")
 
 
 def _tp_kernels(rank, world):
@@ -64,39 +60,6 @@ def test_fused_tp_kernels_match_nccl():
     run_distributed(_tp_kernels, 2, backend="nccl")
 
 
-def _tp_kernels_streaming(rank, world):
-    os.environ["MLB200_AG_STREAM"] = "1"     # read once per process by the launcher
-    _tp_kernels(rank, world)
-
-
-@experimental
-def test_fused_tp_kernels_streaming_pullers_match_nccl():
-    """Same checks with the all-gather pieces dealt round-robin to all puller CTAs (MLB200_AG_STREAM)."""
-    run_distributed(_tp_kernels_streaming, 2, backend="nccl")
-
-
-def _tp_kernels_push(rank, world):
-    os.environ["MLB200_AG_PUSH"] = "1"       # read when the communicator is built
-    _tp_kernels(rank, world)
-
-
-@experimental
-def test_fused_tp_kernels_push_all_gather_match_nccl():
-    """Same checks with the push variant of the all-gather (owner stores its shard into every rank's symmetric
-    gather buffer; MLB200_AG_PUSH)."""
-    run_distributed(_tp_kernels_push, 2, backend="nccl")
-
-
-def _tp_kernels_push_in_graph(rank, world):
-    os.environ["MLB200_AG_PUSH"] = "1"
-    _tp_kernels_in_graph(rank, world)
-
-
-@experimental
-def test_fused_tp_kernels_push_replay_in_cuda_graph():
-    run_distributed(_tp_kernels_push_in_graph, 2, backend="nccl")
-
-
 def _tp_kernels_with_skew(rank, world):
     """Shake the flag protocol: every rank delays its launches by a different, changing amount (device-side spin on the
     launching stream), so the READY / ACK / ARRIVED / FREE handshakes see peers that are early, late, or a whole call
@@ -136,7 +99,6 @@ def _tp_kernels_with_skew(rank, world):
     ps.destroy_model_parallel()
 
 
-@experimental
 def test_fused_tp_kernels_tolerate_rank_skew():
     run_distributed(_tp_kernels_with_skew, 2, backend="nccl")
 

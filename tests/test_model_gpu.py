@@ -1,5 +1,7 @@
-"""Model-level parity on a B200: the same tiny Llama / Falcon / GPT step with the sm_100a kernels vs. the plain
-PyTorch operator path (MLB200_DISABLE_KERNELS=1) must agree on loss and gradient norm."""
+"""Model-level parity on a B200: the same tiny Llama / Falcon / GPT training steps with the sm_100a kernels in bf16 vs.
+the plain PyTorch operator path (MLB200_DISABLE_KERNELS=1) in FP32 must agree on loss (1 %) and gradient norm (3 %).
+Both runs build their weights from the same fp32 CPU random stream (--use_cpu_initialization), so the oracle's
+weights are the un-rounded values of the bf16 run's, and both see the same fixed batch."""
 import os
 import subprocess
 import sys
@@ -22,8 +24,10 @@ initialize_megatron(finetune.extra_args, {}, args_list=argv)
 model, opt, sched = setup_model_and_optimizer(finetune.model_provider, ModelType.encoder_or_decoder)
 def it():
     g = torch.Generator().manual_seed(0)
-    while True:
-        yield {"text": torch.randint(0, 1000, (2, %(seq)d + 1), generator=g)}
+    batches = [torch.randint(0, 1000, (2, %(seq)d + 1), generator=g) for _ in range(2)]   # one step = 2 micro-batches
+    while True:                                      # the SAME step every time: the loss must go down
+        for b in batches:
+            yield {"text": b}
 data = it()
 out = []
 for step in range(3):
@@ -33,10 +37,10 @@ print("RESULT " + json.dumps(out))
 '''
 
 COMMON = ("--num_layers 2 --hidden_size 256 --num_attention_heads 2 --seq_length 256 --max_position_embeddings 256 "
-          "--micro_batch_size 2 --global_batch_size 4 --train_iters 10 --lr 1e-3 --bf16 --hidden_dropout 0 "
+          "--micro_batch_size 2 --global_batch_size 4 --train_iters 10 --lr 3e-4 --bf16 --hidden_dropout 0 "
           "--attention_dropout 0 --tokenizer_type NullTokenizer --vocab_file 1024 --data_type synthetic "
           "--log_interval 100 --eval_iters 0 --eval_interval 1000 --num_workers 0 --lr_decay_style constant "
-          "--use_flash_attn --position_embedding_type rotary ")
+          "--use_flash_attn --position_embedding_type rotary --use_cpu_initialization --clip_grad 0 ")
 CONFIGS = {
     "llama": COMMON + "--model_name llama2 --use_rms_norm --glu_activation swiglu --no_tie_embed_logits "
                       "--ffn_hidden_size 704 --num_attention_heads_kv 1",
@@ -46,9 +50,11 @@ CONFIGS = {
 }
 
 
-def _run(argv, disable, port):
+def _run(argv, disable, port, fp32=False):
     env = dict(os.environ)
     env["MLB200_DISABLE_KERNELS"] = "1" if disable else "0"
+    if fp32:
+        argv = argv.replace("--bf16", "")
     code = SCRIPT % {"root": ROOT, "port": str(port), "argv": argv, "seq": 256}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -60,12 +66,13 @@ def _run(argv, disable, port):
 @pytest.mark.parametrize("name", list(CONFIGS))
 def test_kernels_match_torch_path(name):
     a = _run(CONFIGS[name], disable=False, port=29610)
-    b = _run(CONFIGS[name], disable=True, port=29611)
+    b = _run(CONFIGS[name], disable=True, port=29611, fp32=True)
     for (la, ga), (lb, gb) in zip(a, b):
         assert la == la and ga == ga, "nan"
-        assert abs(la - lb) < 3e-2 * max(1.0, abs(lb)), (a, b)
-        assert abs(ga - gb) < 0.15 * max(1e-3, abs(gb)), (a, b)
-    assert a[-1][0] < a[0][0] + 1e-3   # loss does not blow up over 3 steps
+        assert abs(la - lb) < 1e-2 * max(1.0, abs(lb)), (a, b)
+        assert abs(ga - gb) < 3e-2 * max(1e-3, abs(gb)), (a, b)
+    assert a[-1][0] < a[0][0]          # same batch every step: the loss goes down
+    assert b[-1][0] < b[0][0]
 
 
 def test_cuda_graph_microbatch_matches_eager():
