@@ -12,11 +12,11 @@ namespace mlb { struct GemmComm; }
 
 extern "C" {
 int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
-                  int a_mn_major, int b_mn_major, int epilogue, int block_n, const void* comm, int num_sms,
+                  int a_mn_major, int b_mn_major, int epilogue, int block_n, int fp16, int num_sms,
                   cudaStream_t stream);
 int mlb_gemm2_debug_read(unsigned long long* host, int n);
 int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
-                       int a_mn_major, int b_mn_major, int epilogue, int num_sms, cudaStream_t stream);
+                       int a_mn_major, int b_mn_major, int epilogue, int fp16, int num_sms, cudaStream_t stream);
 int mlb_norm_fwd(int dtype, const void* x, const void* res_in, const void* w, const void* b, void* y, void* res_out,
                  float* mean, float* rstd, int rows, int H, float eps, int rms, cudaStream_t st);
 int mlb_norm_bwd(int dtype, const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
@@ -94,22 +94,24 @@ static int num_sms() {
 static void gemm(const torch::Tensor& A, const torch::Tensor& B, torch::Tensor& C, int64_t M, int64_t N, int64_t K,
                  int64_t lda, int64_t ldb, int64_t ldc, bool a_mn, bool b_mn, int64_t epilogue, int64_t block_n,
                  const c10::optional<torch::Tensor>& comm, int64_t sms) {
-  TORCH_CHECK(A.scalar_type() == torch::kBFloat16 && B.scalar_type() == torch::kBFloat16, "gemm: bf16 operands");
+  const bool fp16 = A.scalar_type() == torch::kFloat16;
+  TORCH_CHECK((fp16 || A.scalar_type() == torch::kBFloat16) && B.scalar_type() == A.scalar_type(),
+              "gemm: bf16 x bf16 or fp16 x fp16 operands");
+  TORCH_CHECK(C.scalar_type() == torch::kFloat32 || C.scalar_type() == A.scalar_type(), "gemm: C is fp32 or the operand type");
   TORCH_CHECK((reinterpret_cast<uintptr_t>(A.data_ptr()) % 16) == 0 && (reinterpret_cast<uintptr_t>(B.data_ptr()) % 16) == 0 &&
                   (reinterpret_cast<uintptr_t>(C.data_ptr()) % 16) == 0, "gemm: 16-byte aligned operands");
   TORCH_CHECK(lda % 8 == 0 && ldb % 8 == 0 && ldc % 4 == 0 && N % 8 == 0, "gemm: leading dims / N must be multiples of 8");
   c10::cuda::CUDAGuard guard(A.device());
-  const void* cp = comm.has_value() ? comm->data_ptr() : nullptr;
   // 2-CTA (cta_group::2) 256x256 tiles; its TMA-store epilogue needs 16-byte multiples of the output row pitch
   const int64_t out_bytes = (epilogue == 0 || epilogue == 3) ? 2 : 4;
   if (block_n == 512 && (ldc * out_bytes) % 16 == 0) {
     CHK(mlb_gemm_bf16_2cta(A.data_ptr(), B.data_ptr(), C.data_ptr(), (int)M, (int)N, (int)K, (int)lda, (int)ldb,
-                           (int)ldc, a_mn, b_mn, (int)epilogue, sms > 0 ? (int)sms : num_sms(), cur()));
+                           (int)ldc, a_mn, b_mn, (int)epilogue, fp16, sms > 0 ? (int)sms : num_sms(), cur()));
     return;
   }
   if (block_n == 512) block_n = 0;
   CHK(mlb_gemm_bf16(A.data_ptr(), B.data_ptr(), C.data_ptr(), (int)M, (int)N, (int)K, (int)lda, (int)ldb, (int)ldc,
-                    a_mn, b_mn, (int)epilogue, (int)block_n, cp, sms > 0 ? (int)sms : num_sms(), cur()));
+                    a_mn, b_mn, (int)epilogue, (int)block_n, fp16, sms > 0 ? (int)sms : num_sms(), cur()));
 }
 
 static void norm_fwd(const torch::Tensor& x, const c10::optional<torch::Tensor>& res_in, const torch::Tensor& w,

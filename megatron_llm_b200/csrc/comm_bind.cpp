@@ -137,7 +137,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
                              const std::vector<int64_t>& rs_dst, int64_t rs_slots, int64_t rows_per_rank,
                              int64_t prev_total, int64_t tiles_1cta, torch::Tensor& reduce_counter, int64_t pad_local,
                              const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world, int64_t epoch,
-                             int64_t sms, int64_t state_ptr) {
+                             int64_t sms, int64_t state_ptr, const std::vector<int64_t>& ar_dst) {
   c10::cuda::CUDAGuard guard(x.device());
   const int M = x.size(0), K = x.size(1);
   const int N = b_mn ? weight.size(1) : weight.size(0);
@@ -156,6 +156,9 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
   c.rs_out = rs_out.data_ptr();
   c.rs_rows_per_rank = rows_per_rank;
   c.rs_reduce_counter = reduce_counter.data_ptr<int>();
+  // GEMM -> all-reduce: every rank's [M, N] output buffer of this parity (empty list = plain reduce-scatter)
+  TORCH_CHECK(ar_dst.empty() || (int64_t)ar_dst.size() == world, "ar_dst: one buffer per rank");
+  for (size_t i = 0; i < ar_dst.size(); ++i) c.ar_dst[i] = reinterpret_cast<void*>(ar_dst[i]);
   fill_pads(c, pad_local, pad_peers);
   static const bool force_1cta = getenv("MLB200_FUSED_1CTA") != nullptr;
   if (!force_1cta && rows_per_rank % 256 == 0 && N >= 256) {

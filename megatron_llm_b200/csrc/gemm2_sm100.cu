@@ -52,7 +52,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                       const __grid_constant__ CUtensorMap tmC, const __grid_constant__ RsMaps rsm,
                       const GemmParams p, const int dbg) {
   constexpr uint32_t TMEM_COLS = 2 * G2_BLOCK_N;  // two accumulator stages
-  constexpr uint32_t IDESC = make_idesc_f16(G2_BLOCK_M, G2_BLOCK_N, A_MN, B_MN, true);
+  const uint32_t IDESC = make_idesc_f16(G2_BLOCK_M, G2_BLOCK_N, A_MN, B_MN, !p.fp16);
   constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
 
   extern __shared__ uint8_t smem_raw[];
@@ -285,8 +285,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              w[i] = pack_bf16x2(__uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
-              w[16 + i] = pack_bf16x2(__uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
+              w[i] = pack_16x2(p.fp16, __uint_as_float(r0[2 * i]), __uint_as_float(r0[2 * i + 1]));
+              w[16 + i] = pack_16x2(p.fp16, __uint_as_float(r1[2 * i]), __uint_as_float(r1[2 * i + 1]));
             }
           }
           uint8_t* buf = ebase + (c & 1) * 4096;
@@ -329,17 +329,17 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                   uint4 o;
                   if constexpr (EPI == EPI_BF16_ACCUM) {
                     const uint4 old = dptr[v];
-                    float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z),
-                           a3 = unpack_bf16x2(old.w);
-                    o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) + a0.x, __uint_as_float(r[v * 8 + 1]) + a0.y);
-                    o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]) + a1.x, __uint_as_float(r[v * 8 + 3]) + a1.y);
-                    o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]) + a2.x, __uint_as_float(r[v * 8 + 5]) + a2.y);
-                    o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]) + a3.x, __uint_as_float(r[v * 8 + 7]) + a3.y);
+                    float2 a0 = unpack_16x2(p.fp16, old.x), a1 = unpack_16x2(p.fp16, old.y), a2 = unpack_16x2(p.fp16, old.z),
+                           a3 = unpack_16x2(p.fp16, old.w);
+                    o.x = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 0]) + a0.x, __uint_as_float(r[v * 8 + 1]) + a0.y);
+                    o.y = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 2]) + a1.x, __uint_as_float(r[v * 8 + 3]) + a1.y);
+                    o.z = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 4]) + a2.x, __uint_as_float(r[v * 8 + 5]) + a2.y);
+                    o.w = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 6]) + a3.x, __uint_as_float(r[v * 8 + 7]) + a3.y);
                   } else {
-                    o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-                    o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-                    o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-                    o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+                    o.x = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+                    o.y = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+                    o.z = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+                    o.w = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
                   }
                   dptr[v] = o;
                 }
@@ -494,7 +494,7 @@ extern "C" int mlb_gemm2_debug_read(unsigned long long* host, int n) {
 }
 
 extern "C" int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
-                                  int ldc, int a_mn_major, int b_mn_major, int epilogue, int num_sms,
+                                  int ldc, int a_mn_major, int b_mn_major, int epilogue, int fp16, int num_sms,
                                   cudaStream_t stream) {
   using namespace mlb;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
@@ -512,7 +512,7 @@ extern "C" int mlb_gemm_bf16_2cta(const void* A, const void* B, void* C, int M, 
   if (r) return 3000 + r;
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.fp16 = fp16;
   if (!a_mn_major && !b_mn_major) return dispatch2_epi<false, false>(epilogue, tmA, tmB, tmC, p, num_sms, stream);
   if (!a_mn_major && b_mn_major) return dispatch2_epi<false, true>(epilogue, tmA, tmB, tmC, p, num_sms, stream);
   if (a_mn_major && b_mn_major) return dispatch2_epi<true, true>(epilogue, tmA, tmB, tmC, p, num_sms, stream);

@@ -130,7 +130,7 @@ static int pick_block_n(int M, int N, int num_sms) {
 // `comm` may be null (plain GEMM).  Returns 0 on success.
 extern "C" int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
                              int ldc, int a_mn_major, int b_mn_major, int epilogue, int block_n,
-                             const void* /*unused*/, int num_sms, cudaStream_t stream) {
+                             int fp16, int num_sms, cudaStream_t stream) {
   using namespace mlb;
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   CUtensorMap tmA, tmB;
@@ -144,7 +144,7 @@ extern "C" int mlb_gemm_bf16(const void* A, const void* B, void* C, int M, int N
   if (r) return 2000 + r;
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc;
+  p.C = C; p.M = M; p.N = N; p.K = K; p.ldc = ldc; p.fp16 = fp16;
   if (block_n == 256) return dispatch_major<256>(a_mn_major, b_mn_major, epilogue, tmA, tmB, p, num_sms, stream);
   return dispatch_major<128>(a_mn_major, b_mn_major, epilogue, tmA, tmB, p, num_sms, stream);
 }

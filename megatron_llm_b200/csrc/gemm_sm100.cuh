@@ -179,6 +179,8 @@ static __device__ void rs_reduce_phase(const GemmParams& p) {
   const long long slot_vec = (long long)c.rs_rows_per_rank * p.ldc / 8;
   const uint4* slots = reinterpret_cast<const uint4*>(c.rs_slots);
   uint4* out = reinterpret_cast<uint4*>(c.rs_out);
+  const bool all_reduce = c.ar_dst[0] != nullptr;          // reduced slice goes to every rank's [M, N] output buffer
+  const long long ar_off = (long long)c.rank * slot_vec;   // my rows inside that buffer
   const long long stride = (long long)gridDim.x * blockDim.x;
   constexpr int U = 4;
   for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total_vec; i0 += U * stride) {
@@ -213,14 +215,21 @@ static __device__ void rs_reduce_phase(const GemmParams& p) {
         uint4 o;
         o.x = pack_bf16x2(acc[u][0], acc[u][1]); o.y = pack_bf16x2(acc[u][2], acc[u][3]);
         o.z = pack_bf16x2(acc[u][4], acc[u][5]); o.w = pack_bf16x2(acc[u][6], acc[u][7]);
-        out[i] = o;
+        if (!all_reduce) {
+          out[i] = o;
+        } else {
+          for (int k = 0; k < c.world; ++k) {                // own copy first, then the peers (posted NVLink stores)
+            const int d = (c.rank + k) % c.world;
+            st_v4(reinterpret_cast<uint4*>(c.ar_dst[d]) + ar_off + i, o);
+          }
+        }
       }
     }
   }
   // last CTA out tells every peer that this rank's receive slot (this parity) is free again
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();
+    if (all_reduce) __threadfence_system(); else __threadfence();     // (peer stores of this CTA precede the count)
     s_last = (atomicAdd(c.rs_reduce_counter, 1) == (int)gridDim.x - 1);
   }
   __syncthreads();
@@ -230,6 +239,13 @@ static __device__ void rs_reduce_phase(const GemmParams& p) {
     const int epoch = comm_epoch(c, STATE_RS_EPOCH);
     for (int d = 0; d < c.world; ++d)
       if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_RS_FREE + c.rank, epoch);
+    if (all_reduce) {
+      // all-gather handshake: my slice is in everybody's buffer; the launch retires once theirs are in mine
+      for (int d = 0; d < c.world; ++d)
+        if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_AR_DONE + c.rank, epoch);
+      for (int s = 0; s < c.world; ++s)
+        if (s != c.rank) spin_until_ge(c.pad_local + PAD_AR_DONE + s, epoch, c.pad_local);
+    }
   }
 }
 
@@ -243,7 +259,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   using S = GemmSmem<BLOCK_N>;
   constexpr int STAGES = S::STAGES;
   constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;  // two accumulator stages (power of two: 256 or 512)
-  constexpr uint32_t IDESC = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, A_MN, B_MN, true);
+  const uint32_t IDESC = make_idesc_f16(GEMM_BLOCK_M, BLOCK_N, A_MN, B_MN, !p.fp16);
   constexpr int OUT_ELEM = (EPI == EPI_BF16 || EPI == EPI_BF16_ACCUM) ? 2 : 4;
 
   extern __shared__ uint8_t smem_raw[];
@@ -429,17 +445,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 uint4 o;
                 if constexpr (EPI == EPI_BF16_ACCUM) {
                   const uint4 old = dptr[v];
-                  float2 a0 = unpack_bf16x2(old.x), a1 = unpack_bf16x2(old.y), a2 = unpack_bf16x2(old.z),
-                         a3 = unpack_bf16x2(old.w);
-                  o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]) + a0.x, __uint_as_float(r[v * 8 + 1]) + a0.y);
-                  o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]) + a1.x, __uint_as_float(r[v * 8 + 3]) + a1.y);
-                  o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]) + a2.x, __uint_as_float(r[v * 8 + 5]) + a2.y);
-                  o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]) + a3.x, __uint_as_float(r[v * 8 + 7]) + a3.y);
+                  float2 a0 = unpack_16x2(p.fp16, old.x), a1 = unpack_16x2(p.fp16, old.y), a2 = unpack_16x2(p.fp16, old.z),
+                         a3 = unpack_16x2(p.fp16, old.w);
+                  o.x = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 0]) + a0.x, __uint_as_float(r[v * 8 + 1]) + a0.y);
+                  o.y = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 2]) + a1.x, __uint_as_float(r[v * 8 + 3]) + a1.y);
+                  o.z = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 4]) + a2.x, __uint_as_float(r[v * 8 + 5]) + a2.y);
+                  o.w = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 6]) + a3.x, __uint_as_float(r[v * 8 + 7]) + a3.y);
                 } else {
-                  o.x = pack_bf16x2(__uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
-                  o.y = pack_bf16x2(__uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
-                  o.z = pack_bf16x2(__uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
-                  o.w = pack_bf16x2(__uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
+                  o.x = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 0]), __uint_as_float(r[v * 8 + 1]));
+                  o.y = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 2]), __uint_as_float(r[v * 8 + 3]));
+                  o.z = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 4]), __uint_as_float(r[v * 8 + 5]));
+                  o.w = pack_16x2(p.fp16, __uint_as_float(r[v * 8 + 6]), __uint_as_float(r[v * 8 + 7]));
                 }
                 dptr[v] = o;
               }

@@ -24,7 +24,8 @@ enum PadSlot : int {
   PAD_AG_ACK = 8,     // [rdr]  : rdr finished reading my shard of epoch e
   PAD_RS_ARRIVED = 16,  // [src]: cumulative number of tiles src delivered into my receive slots
   PAD_RS_FREE = 24,   // [dst]  : dst finished reducing epoch e (its receive slot of parity e may be reused)
-  PAD_ERROR = 32,     // spin-wait timeout marker (debug)
+  PAD_ERROR = 32,     // spin-wait timeout marker (checked once per training step)
+  PAD_AR_DONE = 40,   // [src]  : (GEMM -> all-reduce) src stored its reduced row slice of epoch e into my output buffer
   PAD_INTS = 64,
 };
 
@@ -48,6 +49,9 @@ struct GemmComm {
   int rs_rows_per_rank;
   int rs_expected_total;               // cumulative tiles every source will have delivered after this call
   int* rs_reduce_counter;              // local: CTAs that finished the reduction (last one frees the slot)
+  // ---- GEMM -> all-reduce (non-sequence-parallel Row forward / Column dgrad): reduce-scatter as above, then every rank
+  //      stores its reduced slice into ALL ranks' symmetric output buffers [M, N] (all-gather by posted stores)
+  void* ar_dst[GEMM_MAX_PEERS];        // rank d's output buffer of this epoch parity (nullptr = plain reduce-scatter)
   // ---- device-resident offsets added to `epoch` / `rs_expected_total` (nullptr = 0).  A kernel node of a replayed
   //      CUDA graph keeps the arguments of its capture; the host writes {ag epoch, rs epoch, rs arrivals} deltas here
   //      before every replay so the captured calls continue the live sequence.
@@ -61,6 +65,7 @@ struct GemmParams {
   void* C;
   int M, N, K;
   int ldc;  // elements
+  int fp16; // 1: A/B (and a 16-bit C) are IEEE fp16 instead of bf16 (same tiles; kind::f16 operand-format bits differ)
   GemmComm comm;
 };
 

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -333,6 +334,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t u) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&u));
+}
+// 16-bit output element type chosen at run time (warp-uniform flag): bf16 or fp16
+__device__ __forceinline__ uint32_t pack_16x2(int fp16, float a, float b);
+__device__ __forceinline__ float2 unpack_16x2(int fp16, uint32_t u);
 __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
@@ -348,4 +359,9 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+}  // namespace mlb
+
+namespace mlb {
+__device__ __forceinline__ uint32_t pack_16x2(int fp16, float a, float b) { return fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
+__device__ __forceinline__ float2 unpack_16x2(int fp16, uint32_t u) { return fp16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
 }  // namespace mlb

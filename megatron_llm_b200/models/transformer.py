@@ -311,11 +311,8 @@ class ParallelAttention(MegatronModule):
 
 
 def _bias_dropout_add(x, bias, residual, prob, training):
-    if bias is not None:
-        x = x + bias
-    if prob > 0.0 and training:
-        x = F.dropout(x, p=prob, training=True)
-    return residual + x
+    """residual + dropout(x + bias): one kernel forward, one backward (``ops.bias_dropout_add``)."""
+    return ops.bias_dropout_add(x, bias, residual, prob, training)
 
 
 class ParallelTransformerLayer(MegatronModule):

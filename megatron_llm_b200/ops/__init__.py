@@ -51,8 +51,10 @@ def _tile_cfg(M: int, N: int) -> int:
 
 
 def _gemm_ok(*ts) -> bool:
+    """bf16 x bf16 or fp16 x fp16 CUDA operands (the tcgen05 ``kind::f16`` MMA takes either; fp32 models use the
+    library)."""
     for t in ts:
-        if not (t.is_cuda and t.dtype == torch.bfloat16):
+        if not (t.is_cuda and t.dtype in (torch.bfloat16, torch.float16) and t.dtype == ts[0].dtype):
             return False
     return cuda_ops_available(ts[0])
 
@@ -79,7 +81,7 @@ def gemm_nt(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     M, K = a.shape
     N = b.size(0)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
     _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), False, False, _EPI_BF16, _tile_cfg(M, N), comm, sms)
     _count()
     return out
@@ -98,7 +100,7 @@ def gemm_nn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
     M, K = a.shape
     N = b.size(1)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
     _C().gemm(a, b, out, M, N, K, a.stride(0), b.stride(0), out.stride(0), False, True, _EPI_BF16, _tile_cfg(M, N), comm, sms)
     _count()
     return out
@@ -108,7 +110,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
             sms: int = 0) -> torch.Tensor:
     """out[M,N] (+)= a[K,M]^T @ b[K,N]   (wgrad: dY^T @ X; ``out`` may be the fp32 main_grad)."""
     M, N, K = a.size(1), b.size(1), a.size(0)
-    if not _gemm_ok(a, b) or M % 8 or N % 8 or (out is not None and out.dtype not in (torch.float32, torch.bfloat16)):
+    if not _gemm_ok(a, b) or M % 8 or N % 8 or (out is not None and out.dtype not in (torch.float32, a.dtype)):
         r = a.t().float() @ b.float() if (out is not None and out.dtype == torch.float32) else a.t() @ b
         if out is None:
             return r
@@ -119,7 +121,7 @@ def gemm_tn(a: torch.Tensor, b: torch.Tensor, out: Optional[torch.Tensor] = None
         return out
     a, b = _rowmajor2d(a), _rowmajor2d(b)
     if out is None:
-        out = torch.empty((M, N), dtype=torch.bfloat16, device=a.device)
+        out = torch.empty((M, N), dtype=a.dtype, device=a.device)
         accumulate = False
     if out.dtype == torch.float32:
         epi = _EPI_F32_ACCUM if accumulate else _EPI_F32
@@ -394,6 +396,63 @@ class _GeluFn(torch.autograd.Function):
 
 def gelu(x, bias=None, approximate=False):
     return _GeluFn.apply(x, bias, approximate)
+
+
+# =============================================================================================
+# bias + dropout + residual add (one kernel each way; the mask is a counter-based hash of (seed, element index), so
+# nothing is stored for backward -- reference: megatron/model/transformer.py:563-609 jit-scripted bias_dropout_add)
+# =============================================================================================
+
+def _dropout_seed(n_elems: int) -> int:
+    """63-bit seed drawn from (and advancing) the current CUDA generator, on the host: follows the model-parallel RNG
+    tracker's forks and is reproduced exactly when activation recompute restores the generator state."""
+    gen = torch.cuda.default_generators[torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + 4 * ((n_elems + 3) // 4))
+    return (seed * 6364136223846793005 + off * 1442695040888963407 + 1) & 0x7FFFFFFFFFFFFFFF
+
+
+def _bda_kernel_ok(x, bias, residual):
+    F_ = x.size(-1)
+    return (cuda_ops_available(x) and x.dtype in (torch.bfloat16, torch.float16, torch.float32) and F_ % 8 == 0
+            and residual.dtype == x.dtype and residual.shape == x.shape
+            and (bias is None or (bias.dtype == x.dtype and bias.numel() == F_)))
+
+
+class _BiasDropoutAddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, residual, p, seed):
+        xc, rc = x.contiguous(), residual.contiguous()
+        out = torch.empty_like(xc)
+        _C().bias_dropout_add(xc, bias.contiguous() if bias is not None else None, rc, out, p, seed, False)
+        _count()
+        ctx.p, ctx.seed, ctx.has_bias = p, seed, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = dout.contiguous()
+        if ctx.p > 0.0:
+            dx = torch.empty_like(dout)
+            _C().bias_dropout_add(dout, None, None, dx, ctx.p, ctx.seed, True)      # dx = mask * dout / (1 - p)
+            _count()
+        else:
+            dx = dout
+        dbias = dx.reshape(-1, dx.size(-1)).sum(0) if ctx.has_bias else None
+        return dx, dbias, dout, None, None
+
+
+def bias_dropout_add(x, bias, residual, p: float, training: bool):
+    """residual + dropout(x + bias, p)."""
+    p = float(p) if training else 0.0
+    if _bda_kernel_ok(x, bias, residual):
+        seed = _dropout_seed(x.numel()) if p > 0.0 else 0
+        return _BiasDropoutAddFn.apply(x, bias, residual, p, seed)
+    if bias is not None:
+        x = x + bias
+    if p > 0.0:
+        x = F.dropout(x, p=p, training=True)
+    return residual + x
 
 
 # =============================================================================================

@@ -9,10 +9,9 @@ from . import _ext
 
 
 def _head_dim_ok(hn: int) -> bool:
-    """128 always; 64 (Falcon, GPT-2 style models) is compiled in but stays opt-in (``MLB200_ATTN_HD64=1``) until its
-    instantiations have been validated on hardware with tools/profiling/attn_check.py -- until then those models use
-    the FA-2 library fallback in ops/attention.py."""
-    return hn == 128 or (hn == 64 and os.environ.get("MLB200_ATTN_HD64", "0") == "1")
+    """128 (Llama / Mistral) and 64 (Falcon-40B: 128 heads x 64, GPT-2 style models); both instantiations are
+    validated against the fp32 reference in tests/test_ops_gpu.py (``MLB200_ATTN_HD64=0`` routes 64 to the library)."""
+    return hn == 128 or (hn == 64 and os.environ.get("MLB200_ATTN_HD64", "1") == "1")
 
 
 def supported(q, k, v, causal, window, dropout_p) -> bool:

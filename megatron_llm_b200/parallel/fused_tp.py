@@ -59,3 +59,21 @@ def ag_gemm(x_shard: torch.Tensor, weight: torch.Tensor, transposed_weight: bool
 def gemm_rs(x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
     """GEMM then reduce-scatter along dim 0.  Returns out2d [rows/tp, N]."""
     return _COMM.gemm_rs(x2d, weight, transposed_weight)
+
+
+def active_all_reduce(x2d: torch.Tensor, n_out: int) -> bool:
+    """GEMM -> all-reduce (no sequence parallelism: Row-parallel forward, Column-parallel dgrad): ``x2d`` [M, K] is
+    this rank's full-length operand, the result is [M, n_out] on every rank."""
+    if not active(x2d) or getattr(_COMM, "ar_n", 0) <= 0 or x2d.dim() != 2:
+        return False
+    M, k = x2d.shape
+    if M % _COMM.world != 0:
+        return False
+    rows = M // _COMM.world
+    return (rows % 128 == 0 and rows <= _COMM.max_rows and k % 8 == 0 and n_out % 8 == 0
+            and n_out <= min(_COMM.ar_n, _COMM.max_n))
+
+
+def gemm_ar(x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, keep: bool = True):
+    """GEMM then all-reduce over the TP group.  Returns out2d [M, N]."""
+    return _COMM.gemm_ar(x2d, weight, transposed_weight, keep=keep)

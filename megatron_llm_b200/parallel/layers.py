@@ -236,6 +236,16 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                                  ctx.gradient_accumulation_fusion)
             return grad_input, grad_weight, grad_bias, None, None, None
 
+        from . import fused_tp
+        if (ctx.async_grad_allreduce and ps.get_tensor_model_parallel_world_size() > 1 and weight.dtype == g2d.dtype
+                and fused_tp.active_all_reduce(g2d, weight.size(1))):
+            # dX = all_reduce(dY @ W): one fused GEMM -> all-reduce kernel over peer memory (reference: cuBLAS GEMM +
+            # async NCCL all-reduce overlapped with wgrad, layers.py:278-283)
+            grad_input = fused_tp.gemm_ar(g2d, weight, transposed_weight=True).view(*grad_output.shape[:-1],
+                                                                                     weight.size(1))
+            grad_weight = _wgrad(g2d, total_input.reshape(-1, total_input.size(-1)), weight,
+                                 ctx.gradient_accumulation_fusion)
+            return grad_input, grad_weight, grad_bias, None, None, None
         grad_input = ops.gemm_nn(g2d, weight).view(*grad_output.shape[:-1], weight.size(1))
         if handle is not None:
             handle.wait()
@@ -354,6 +364,28 @@ class _RowLinearFusedRS(torch.autograd.Function):
         return grad_input, grad_weight, None
 
 
+class _RowLinearFusedAR(torch.autograd.Function):
+    """Row-parallel forward without sequence parallelism: GEMM -> all-reduce fused (reference: GEMM, then
+    ``reduce_from_tensor_model_parallel_region``, layers.py:694 / mappings.py:13-23); backward = plain dgrad + wgrad
+    (the incoming gradient is already replicated over the TP group)."""
+
+    @staticmethod
+    def forward(ctx, input, weight, gradient_accumulation_fusion):
+        from . import fused_tp
+        ctx.gradient_accumulation_fusion = gradient_accumulation_fusion
+        ctx.save_for_backward(input, weight)
+        out2d = fused_tp.gemm_ar(input.reshape(-1, input.size(-1)), weight, transposed_weight=False)
+        return out2d.view(*input.shape[:-1], weight.size(0))
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, weight = ctx.saved_tensors
+        g2d = grad_output.contiguous().reshape(-1, grad_output.size(-1))
+        grad_input = ops.gemm_nn(g2d, weight).view(*input.shape)
+        grad_weight = _wgrad(g2d, input.reshape(-1, input.size(-1)), weight, ctx.gradient_accumulation_fusion)
+        return grad_input, grad_weight, None
+
+
 class RowParallelLinear(torch.nn.Module):
     """Y = X A + b with A split along its input (row) dimension: weight shard is [out, in/tp].
 
@@ -401,6 +433,9 @@ class RowParallelLinear(torch.nn.Module):
         from . import fused_tp
         if self.sequence_parallel_enabled and self.world_size > 1 and fused_tp.active_row(input_parallel, self.weight):
             output_ = _RowLinearFusedRS.apply(input_parallel, self.weight, self.gradient_accumulation_fusion)
+        elif (not self.sequence_parallel_enabled and self.world_size > 1 and input_parallel.dtype == self.weight.dtype
+              and fused_tp.active_all_reduce(input_parallel.reshape(-1, input_parallel.size(-1)), self.weight.size(0))):
+            output_ = _RowLinearFusedAR.apply(input_parallel, self.weight, self.gradient_accumulation_fusion)
         else:
             output_parallel = linear_with_grad_accumulation_and_async_allreduce(
                 input_parallel, self.weight, None, self.gradient_accumulation_fusion, False, False)

@@ -71,7 +71,7 @@ class TPCommunicator:
     """
 
     def __init__(self, group, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 8,
-                 loopback: Optional[LoopbackWorld] = None, loopback_rank: int = 0):
+                 loopback: Optional[LoopbackWorld] = None, loopback_rank: int = 0, all_reduce_n: int = 0):
         self.group = group
         self.loopback = loopback
         if loopback is not None:
@@ -90,6 +90,11 @@ class TPCommunicator:
         self.rs, self.rs_ptrs = self._symmetric("rs", 2 * self.world * max_rows_per_rank * max_n, torch.bfloat16)
         self.pad, self.pad_ptrs = self._symmetric("pad", _PAD_INTS, torch.int32)
         self.pad.zero_()
+        # GEMM -> all-reduce (non-sequence-parallel layers): two parities of a [world * rows, all_reduce_n] output buffer
+        self.ar_n = all_reduce_n
+        if all_reduce_n > 0:
+            self.ar, self.ar_ptrs = self._symmetric("ar", 2 * self.world * max_rows_per_rank * all_reduce_n,
+                                                    torch.bfloat16)
         max_chunks = self.world * max_rows_per_rank // 128
         self.chunk_flags = torch.zeros(max(max_chunks, 1), dtype=torch.int32, device=self.device)
         self.read_counters = torch.zeros(8, dtype=torch.int32, device=self.device)   # pullers done per peer (self-resetting)
@@ -115,11 +120,11 @@ class TPCommunicator:
 
     @classmethod
     def loopback_group(cls, world: int, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 4,
-                       sms: Optional[int] = None):
+                       sms: Optional[int] = None, all_reduce_n: int = 0):
         """``world`` communicators that talk to each other on the current device (see :class:`LoopbackWorld`)."""
         lw = LoopbackWorld(world, sms)
-        return [cls(None, max_rows_per_rank, max_k, max_n, num_comm_ctas, loopback=lw, loopback_rank=r)
-                for r in range(world)]
+        return [cls(None, max_rows_per_rank, max_k, max_n, num_comm_ctas, loopback=lw, loopback_rank=r,
+                    all_reduce_n=all_reduce_n) for r in range(world)]
 
     # -------------------------------------------------------------------------------------------
     def supports(self, rows_per_rank: int, k: int, n: int) -> bool:
@@ -162,10 +167,20 @@ class TPCommunicator:
 
     def gemm_rs(self, x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
         """reduce_scatter_rows(x2d [M, K] @ W^T or W) -> [M/world, N]."""
+        return self._gemm_rs(x2d, weight, transposed_weight, all_reduce=False)
+
+    def gemm_ar(self, x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False, keep: bool = True):
+        """all_reduce(x2d [M, K] @ W^T or W) -> [M, N]: the reduce-scatter kernel whose reduction phase stores every
+        rank's reduced row slice into ALL ranks' symmetric output buffers (GEMM -> reduce-scatter -> all-gather in one
+        launch).  ``keep=False``: the caller consumes the result before the next-but-one call on this communicator and
+        gets a view of the communicator's buffer instead of a copy."""
+        return self._gemm_rs(x2d, weight, transposed_weight, all_reduce=True, keep=keep)
+
+    def _gemm_rs(self, x2d, weight, transposed_weight, all_reduce, keep=True):
         M, K = x2d.shape
         N = weight.size(1) if transposed_weight else weight.size(0)
         m = M // self.world
-        assert m <= self.max_rows and N <= self.max_n and m % 128 == 0, (m, N)
+        assert m <= self.max_rows and N <= self.max_n and m % 128 == 0 and m * self.world == M, (M, N)
         self.rs_epoch += 1
         parity = self.rs_epoch % 2
         slot_elems = m * N
@@ -173,15 +188,25 @@ class TPCommunicator:
         base = (parity * self.world) * self.max_rows * self.max_n
         rs_dst = [self.rs_ptrs[d] + 2 * (base + self.rank * slot_elems) for d in range(self.world)]
         rs_slots = self.rs_ptrs[self.rank] + 2 * base
-        out = torch.empty((m, N), dtype=torch.bfloat16, device=self.device)
+        ar_dst = []
+        if all_reduce:
+            assert 0 < N <= self.ar_n, "communicator was built without (large enough) all-reduce buffers"
+            ar_base = parity * self.world * self.max_rows * self.ar_n
+            ar_dst = [p + 2 * ar_base for p in self.ar_ptrs]
+            full = self.ar[ar_base: ar_base + M * N].view(M, N)
+            out = full[self.rank * m: (self.rank + 1) * m]          # (unused by the kernel in this mode)
+        else:
+            out = torch.empty((m, N), dtype=torch.bfloat16, device=self.device)
         tiles_per_dst = (m // 128) * self._num_n_tiles(M, N)      # arrivals if the 1-CTA kernel is chosen
         x = x2d if (x2d.stride(1) == 1 and x2d.stride(0) % 8 == 0) else x2d.contiguous()
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
         self.rs_arrived_total = self.mod.fused_gemm_rs(
             x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total, tiles_per_dst,
             self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch,
-            self.sms, self._state_ptr())
+            self.sms, self._state_ptr(), ar_dst)
         _ext.count()
+        if all_reduce:
+            return full.clone() if keep else full
         return out
 
     # ------------------------------------------------------------------- CUDA-graph support
@@ -296,7 +321,9 @@ def bind_tp_communicator(args) -> Optional[TPCommunicator]:
     vocab_shard = getattr(args, "padded_vocab_size", 0) // tp
     max_n = max(args.hidden_size, ffn // tp, vocab_shard)
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), rows, max_k, max_n,
-                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")))   # upper bound: picked per shape
+                          num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")),   # upper bound: picked per shape
+                          # without sequence parallelism the Row forward / Column dgrad end in an all-reduce of [s*b, h]
+                          all_reduce_n=0 if args.sequence_parallel else args.hidden_size)
     fused_tp.bind(comm)
     return comm
 

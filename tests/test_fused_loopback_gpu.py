@@ -126,3 +126,34 @@ def test_loopback_dp_reduce(world, reduce_scatter):
                                           ref[base + r * sl: base + (r + 1) * sl], atol=1e-5), f"it {it} rank {r}"
             else:
                 assert torch.allclose(comms[r].buffer, ref, atol=1e-5), f"it {it} rank {r}"
+
+
+@pytest.mark.parametrize("world,m", [(2, 256), (4, 256), (2, 128)])
+def test_loopback_gemm_all_reduce(world, m):
+    """GEMM -> all-reduce (non-sequence-parallel Row forward / Column dgrad): every rank ends with the full [M, N] sum.
+    Interleaved with plain reduce-scatter calls: both share the receive slots, parities and epochs."""
+    from megatron_llm_b200.parallel.symm import TPCommunicator
+    K, N = 512, 768
+    M = world * m
+    comms = TPCommunicator.loopback_group(world, max_rows_per_rank=512, max_k=2048, max_n=2048, num_comm_ctas=4,
+                                          all_reduce_n=1024)
+    torch.manual_seed(3)
+    for it in range(4):
+        a = [torch.randn(M, K, device=DEV, dtype=torch.bfloat16) for _ in range(world)]
+        ws = [torch.randn(N, K, device=DEV, dtype=torch.bfloat16) * 0.05 for _ in range(world)]
+        wts = [torch.randn(K, N, device=DEV, dtype=torch.bfloat16) * 0.05 for _ in range(world)]
+        got = _run_ranks(world, lambda r: comms[r].gemm_ar(a[r], ws[r], False))
+        if it % 2:
+            _run_ranks(world, lambda r: comms[r].gemm_rs(a[r], ws[r], False))       # shifts the slot parity
+        got_t = _run_ranks(world, lambda r: comms[r].gemm_ar(a[r], wts[r], True, keep=False))
+        torch.cuda.synchronize()
+        total = sum(a[r].float() @ ws[r].float().t() for r in range(world))
+        total_t = sum(a[r].float() @ wts[r].float() for r in range(world))
+        for r in range(world):
+            assert got[r].shape == (M, N)
+            assert (got[r].float() - total).abs().max() <= 3e-2 * total.abs().max(), f"it {it} rank {r}: gemm_ar"
+            assert (got_t[r].float() - total_t).abs().max() <= 3e-2 * total_t.abs().max(), f"it {it} rank {r}: gemm_ar(T)"
+        for r in range(1, world):                    # every rank holds bit-identical results
+            assert torch.equal(got[r], got[0])
+    for c in comms:
+        assert c.error_flag() == 0, "a spin-wait timed out"

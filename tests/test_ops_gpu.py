@@ -48,6 +48,28 @@ def test_gemm_nn_and_tn(M, N, K):
     _close(acc, base + at.float().t() @ b.float(), atol=1e-3, rtol=1e-5)
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 512, 320), (4096, 1536, 4096)])      # 1-CTA and 2-CTA (cta_group::2) kernels
+def test_gemm_fp16_operands(M, N, K):
+    """The same tcgen05 kernels with IEEE fp16 operands (``kind::f16`` a/b format bits, fp16 epilogue packing): NT, NN,
+    TN with fp16 / fp32 / fp32-accumulate outputs.  fp16 has 3 more mantissa bits than bf16: tighter bound."""
+    torch.manual_seed(4)
+    h = torch.float16
+    a = torch.randn(M, K, device=DEV, dtype=h)
+    b = torch.randn(N, K, device=DEV, dtype=h)
+    n0 = ops.launches()
+    out = ops.gemm_nt(a, b)
+    assert ops.launches() == n0 + 1 and out.dtype == h
+    _close(out, a.float() @ b.float().t(), atol=0.0, rtol=1.5e-3)
+    bn = torch.randn(K, N, device=DEV, dtype=h)
+    _close(ops.gemm_nn(a, bn), a.float() @ bn.float(), atol=0.0, rtol=1.5e-3)
+    at = torch.randn(K, M, device=DEV, dtype=h)
+    _close(ops.gemm_tn(at, bn), at.float().t() @ bn.float(), atol=0.0, rtol=1.5e-3)
+    base = torch.randn(M, N, device=DEV, dtype=torch.float32)
+    acc = base.clone()
+    ops.gemm_tn(at, bn, out=acc, accumulate=True)
+    _close(acc, base + at.float().t() @ bn.float(), atol=1e-3, rtol=1e-5)
+
+
 def test_gemm_strided_views():
     torch.manual_seed(2)
     big = torch.randn(512, 768, device=DEV, dtype=torch.bfloat16)
@@ -246,6 +268,41 @@ def test_flat_adamw_and_norm_match_torch():
     assert torch.equal(p, before)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_bias_dropout_add(dtype):
+    torch.manual_seed(9)
+    rows, F_ = 300, 1024
+    x = torch.randn(rows, F_, device=DEV, dtype=dtype, requires_grad=True)
+    b = torch.randn(F_, device=DEV, dtype=dtype, requires_grad=True)
+    r = torch.randn(rows, F_, device=DEV, dtype=dtype, requires_grad=True)
+    # p = 0 (and eval mode): exact bias + residual add
+    out = ops.bias_dropout_add(x, b, r, 0.3, training=False)
+    _close(out, (x.float() + b.float() + r.float()), atol=2e-2 if dtype != torch.float32 else 1e-6)
+    # p > 0: inverted dropout of (x + b); survivors scaled by 1/(1-p); the backward mask is the forward mask
+    p = 0.25
+    n0 = ops.launches()
+    out = ops.bias_dropout_add(x, b, r, p, training=True)
+    assert ops.launches() == n0 + 1
+    kept = ((out.float() - r.float()).abs() > 0)
+    frac = kept.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    want = torch.where(kept, (x.float() + b.float()) / (1 - p), torch.zeros_like(out, dtype=torch.float32)) + r.float()
+    _close(out, want, atol=3e-2 if dtype != torch.float32 else 1e-5)
+    do = torch.randn_like(out)
+    out.backward(do)
+    _close(x.grad, torch.where(kept, do.float() / (1 - p), torch.zeros_like(do, dtype=torch.float32)),
+           atol=2e-2 if dtype != torch.float32 else 1e-5)
+    _close(r.grad, do, atol=0.0)
+    _close(b.grad, x.grad.float().sum(0), atol=0.5 if dtype != torch.float32 else 1e-3)
+    # the seed follows the CUDA generator: same state -> same mask, next call -> a different one
+    st = torch.cuda.get_rng_state()
+    o1 = ops.bias_dropout_add(x, b, r, p, training=True)
+    o2 = ops.bias_dropout_add(x, b, r, p, training=True)
+    torch.cuda.set_rng_state(st)
+    o3 = ops.bias_dropout_add(x, b, r, p, training=True)
+    assert torch.equal(o1, o3) and not torch.equal(o1, o2)
+
+
 def test_accumulate_kernel():
     x = torch.randn(12345, device=DEV, dtype=torch.bfloat16)
     y = torch.randn(12345, device=DEV)
@@ -292,14 +349,11 @@ def test_attention_sm100_forward_and_all_grads_match_fp32(b, s, nq, nkv, window)
         assert err <= 2e-2 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
 
 
-@pytest.mark.skipif(os.environ.get("MLB200_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="head_dim 64 instantiations not yet validated on hardware; set MLB200_TEST_EXPERIMENTAL=1")
-@pytest.mark.parametrize("nq,nkv,window", [(4, 4, None), (8, 2, None), (8, 1, None), (4, 4, 128)])
-def test_flash_attention_head_dim_64_matches_reference(nq, nkv, window, monkeypatch):
+@pytest.mark.parametrize("nq,nkv,window", [(4, 4, None), (8, 2, None), (8, 1, None), (4, 4, 128), (16, 1, None)])
+def test_flash_attention_head_dim_64_matches_reference(nq, nkv, window):
     """Falcon / GPT-2 style heads: forward and all three input gradients against the fp32 reference."""
     from megatron_llm_b200.ops import attention_sm100
     from megatron_llm_b200.ops.attention import attention_reference
-    monkeypatch.setenv("MLB200_ATTN_HD64", "1")
     torch.manual_seed(11)
     b, s, hn = 2, 512, 64
     q, k, v = (torch.randn(b, s, n, hn, device=DEV, dtype=torch.bfloat16, requires_grad=True) for n in (nq, nkv, nkv))
