@@ -34,6 +34,10 @@ int mlb_gelu(int dtype, const void* x, const void* bias, const void* dy, void* o
              int backward, cudaStream_t st);
 int mlb_bias_dropout_add(int dtype, const void* x, const void* bias, const void* residual, void* out, long long rows,
                          int F, float p, unsigned long long seed, int backward, cudaStream_t st);
+int mlb_embedding_fwd(int dtype, const long long* ids, const void* weight, void* out, int batch, int seq, int H,
+                      long long vocab_start, long long rows_local, int sbh, cudaStream_t st);
+int mlb_embedding_bwd(int dtype, const long long* ids, const void* dout, float* dweight, int batch, int seq, int H,
+                      long long vocab_start, long long rows_local, int sbh, cudaStream_t st);
 int mlb_ce_stats(int dtype, const void* logits, const long long* target, float* stats, int rows, int Vp,
                  int vocab_start, long long row_stride, cudaStream_t st);
 int mlb_ce_bwd(int dtype, const void* logits, void* out, const long long* target, const float* M, const float* logS,
@@ -180,6 +184,28 @@ static void bias_dropout_add(const torch::Tensor& x, const c10::optional<torch::
                            (unsigned long long)seed, backward, cur()));
 }
 
+// ids [batch, seq] int64; weight [rows_local, H]; out [seq, batch, H] (sbh) or [batch, seq, H]; ids outside
+// [vocab_start, vocab_start + rows_local) give zero rows
+static void embedding_fwd(const torch::Tensor& ids, const torch::Tensor& weight, torch::Tensor& out, int64_t vocab_start,
+                          bool sbh) {
+  c10::cuda::CUDAGuard guard(weight.device());
+  TORCH_CHECK(ids.scalar_type() == torch::kInt64 && ids.dim() == 2 && ids.is_contiguous());
+  TORCH_CHECK(weight.dim() == 2 && weight.is_contiguous() && out.is_contiguous() && out.scalar_type() == weight.scalar_type());
+  TORCH_CHECK(out.numel() == ids.numel() * weight.size(1));
+  CHK(mlb_embedding_fwd(dt(weight), (const long long*)ids.data_ptr(), weight.data_ptr(), out.data_ptr(), (int)ids.size(0),
+                        (int)ids.size(1), (int)weight.size(1), vocab_start, weight.size(0), sbh, cur()));
+}
+// dweight(fp32) [rows_local, H] += scatter of dout rows by token id
+static void embedding_bwd(const torch::Tensor& ids, const torch::Tensor& dout, torch::Tensor& dweight, int64_t vocab_start,
+                          bool sbh) {
+  c10::cuda::CUDAGuard guard(dout.device());
+  TORCH_CHECK(ids.scalar_type() == torch::kInt64 && ids.dim() == 2 && ids.is_contiguous() && dout.is_contiguous());
+  TORCH_CHECK(dweight.scalar_type() == torch::kFloat32 && dweight.dim() == 2 && dweight.is_contiguous());
+  TORCH_CHECK(dout.numel() == ids.numel() * dweight.size(1));
+  CHK(mlb_embedding_bwd(dt(dout), (const long long*)ids.data_ptr(), dout.data_ptr(), dweight.data_ptr<float>(),
+                        (int)ids.size(0), (int)ids.size(1), (int)dweight.size(1), vocab_start, dweight.size(0), sbh, cur()));
+}
+
 static void ce_stats(const torch::Tensor& logits, const torch::Tensor& target, torch::Tensor& stats, int64_t vocab_start) {
   c10::cuda::CUDAGuard guard(logits.device());
   CHK(mlb_ce_stats(dt(logits), logits.data_ptr(), (const long long*)target.data_ptr(), stats.data_ptr<float>(),
@@ -278,6 +304,8 @@ PYBIND11_MODULE(_C_b200, m) {
   m.def("glu_bwd", &glu_bwd);
   m.def("gelu", &gelu);
   m.def("bias_dropout_add", &bias_dropout_add);
+  m.def("embedding_fwd", &embedding_fwd);
+  m.def("embedding_bwd", &embedding_bwd);
   m.def("ce_stats", &ce_stats);
   m.def("ce_bwd", &ce_bwd);
   m.def("adamw_flat", &adamw_flat);

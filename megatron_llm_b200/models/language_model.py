@@ -94,6 +94,7 @@ class Embedding(MegatronModule):
         args = _get_args()
         self.word_embeddings = tp_layers.VocabParallelEmbedding(
             vocab_size, hidden_size, init_method=init_method, params_dtype=args.params_dtype,
+            gradient_accumulation_fusion=args.gradient_accumulation_fusion,
             use_cpu_initialization=args.use_cpu_initialization, perform_initialization=args.perform_initialization)
         self._word_embeddings_key = "word_embeddings"
         self.position_embedding_type = args.position_embedding_type
@@ -135,6 +136,19 @@ class Embedding(MegatronModule):
         self.init_method(self.tokentype_embeddings.weight)
 
     def forward(self, input_ids, position_ids, tokentype_ids=None):
+        drop = self.training and self.embedding_dropout.p > 0.0      # p = 0: no RNG use (and CUDA-graph capturable)
+        if (self.position_embeddings is None and tokentype_ids is None and not self.fp32_residual_connection
+                and input_ids.dim() == 2):
+            # word embeddings only (Llama / Falcon / Mistral): gather straight into the [s, b, h] layout and, under
+            # sequence parallelism, reduce-scatter the partial lookups instead of all-reduce + split
+            embeddings = self.word_embeddings.forward_sbh(input_ids, self.sequence_parallel)
+            if drop:
+                if self.sequence_parallel:
+                    with get_cuda_rng_tracker().fork():
+                        embeddings = self.embedding_dropout(embeddings)
+                else:
+                    embeddings = self.embedding_dropout(embeddings)
+            return embeddings
         embeddings = self.word_embeddings(input_ids)
         if self.position_embedding_type == PositionEmbeddingType.absolute:
             assert self.position_embeddings is not None
@@ -149,7 +163,6 @@ class Embedding(MegatronModule):
         embeddings = embeddings.transpose(0, 1).contiguous()  # [b,s,h] -> [s,b,h]
         if self.fp32_residual_connection:
             embeddings = embeddings.float()
-        drop = self.training and self.embedding_dropout.p > 0.0      # p = 0: no RNG use (and CUDA-graph capturable)
         if self.sequence_parallel:
             embeddings = mappings.scatter_to_sequence_parallel_region(embeddings)
             if drop:

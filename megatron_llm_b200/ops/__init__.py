@@ -399,6 +399,66 @@ def gelu(x, bias=None, approximate=False):
 
 
 # =============================================================================================
+# Vocab-parallel embedding lookup (csrc/embedding.cu): gather with the vocab-range mask and the [s, b, h] transpose folded
+# in; backward scatter-adds straight into the fp32 main_grad of the table
+# =============================================================================================
+
+def _embedding_ref(ids, weight, vocab_start, sbh):
+    local = ids - vocab_start
+    mask = (local < 0) | (local >= weight.size(0))
+    out = F.embedding(local.masked_fill(mask, 0), weight)
+    out = out.masked_fill(mask.unsqueeze(-1), 0.0)
+    return out.transpose(0, 1).contiguous() if sbh else out
+
+
+def _embedding_kernel_ok(ids, weight):
+    return (cuda_ops_available(weight) and ids.is_cuda and ids.dim() == 2 and weight.dim() == 2
+            and weight.is_contiguous() and weight.size(1) % 8 == 0
+            and weight.dtype in (torch.bfloat16, torch.float16, torch.float32))
+
+
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, ids, weight, vocab_start, sbh, accumulate_into_main_grad):
+        idc = ids.contiguous().long()
+        b, s = idc.shape
+        out = torch.empty((s, b, weight.size(1)) if sbh else (b, s, weight.size(1)), dtype=weight.dtype,
+                          device=weight.device)
+        _C().embedding_fwd(idc, weight, out, vocab_start, sbh)
+        _count()
+        ctx.save_for_backward(idc)
+        ctx.weight, ctx.vocab_start, ctx.sbh = weight, vocab_start, sbh
+        ctx.fused = accumulate_into_main_grad
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        (idc,) = ctx.saved_tensors
+        w = ctx.weight
+        dout = dout.contiguous()
+        main_grad = getattr(w, "main_grad", None)
+        if ctx.fused and main_grad is not None and main_grad.dtype == torch.float32 and main_grad.is_contiguous():
+            _C().embedding_bwd(idc, dout, main_grad, ctx.vocab_start, ctx.sbh)
+            _count()
+            cb = getattr(w, "_grad_ready_callback", None)
+            if cb is not None:
+                cb()
+            return None, None, None, None, None
+        dw = torch.zeros(w.shape, dtype=torch.float32, device=w.device)
+        _C().embedding_bwd(idc, dout, dw, ctx.vocab_start, ctx.sbh)
+        _count()
+        return None, dw.to(w.dtype), None, None, None
+
+
+def embedding_lookup(ids, weight, vocab_start: int = 0, sbh: bool = False, accumulate_into_main_grad: bool = False):
+    """ids [b, s] -> weight[ids - vocab_start] as [b, s, h] (or [s, b, h] with ``sbh``); ids outside this rank's vocab
+    range give zero rows.  With ``accumulate_into_main_grad`` the backward adds into ``weight.main_grad`` (fp32)."""
+    if _embedding_kernel_ok(ids, weight):
+        return _EmbeddingFn.apply(ids, weight, int(vocab_start), bool(sbh), bool(accumulate_into_main_grad))
+    return _embedding_ref(ids, weight, vocab_start, sbh)
+
+
+# =============================================================================================
 # bias + dropout + residual add (one kernel each way; the mask is a counter-based hash of (seed, element index), so
 # nothing is stored for backward -- reference: megatron/model/transformer.py:563-609 jit-scripted bias_dropout_add)
 # =============================================================================================

@@ -93,8 +93,9 @@ class VocabParallelEmbedding(torch.nn.Module):
 
     def __init__(self, num_embeddings: int, embedding_dim: int, *, init_method=init.xavier_normal_,
                  params_dtype: torch.dtype = torch.float32, use_cpu_initialization: bool = False,
-                 perform_initialization: bool = True):
+                 perform_initialization: bool = True, gradient_accumulation_fusion: bool = False):
         super().__init__()
+        self.gradient_accumulation_fusion = gradient_accumulation_fusion
         self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
         self.padding_idx = None
         self.max_norm, self.norm_type, self.scale_grad_by_freq, self.sparse = None, 2.0, False, False
@@ -116,6 +117,11 @@ class VocabParallelEmbedding(torch.nn.Module):
                 _initialize_affine_weight_gpu(self.weight, init_method, partition_dim=0, stride=1)
 
     def forward(self, input_):
+        """[b, s] ids -> [b, s, h], summed over the TP group (reference contract)."""
+        if input_.dim() == 2:
+            out = ops.embedding_lookup(input_, self.weight, self.vocab_start_index, sbh=False,
+                                       accumulate_into_main_grad=self.gradient_accumulation_fusion)
+            return reduce_from_tensor_model_parallel_region(out)
         if self.tensor_model_parallel_size > 1:
             mask = (input_ < self.vocab_start_index) | (input_ >= self.vocab_end_index)
             local = input_ - self.vocab_start_index
@@ -126,6 +132,18 @@ class VocabParallelEmbedding(torch.nn.Module):
                           self.scale_grad_by_freq, self.sparse)
         if self.tensor_model_parallel_size > 1:
             out = out.masked_fill(mask.unsqueeze(-1), 0.0)
+        return reduce_from_tensor_model_parallel_region(out)
+
+    def forward_sbh(self, input_, sequence_parallel: bool):
+        """[b, s] ids -> [s, b, h] (transpose folded into the gather kernel).  Under sequence parallelism the partial
+        lookups are reduce-scattered along s (-> [s/tp, b, h]) instead of all-reduced and then split: 1/tp of the
+        traffic and no scatter copy (reference: all-reduce at layers.py:208, scatter in language_model.py)."""
+        out = ops.embedding_lookup(input_, self.weight, self.vocab_start_index, sbh=True,
+                                   accumulate_into_main_grad=self.gradient_accumulation_fusion)
+        if self.tensor_model_parallel_size == 1:
+            return out
+        if sequence_parallel:
+            return reduce_scatter_to_sequence_parallel_region(out)
         return reduce_from_tensor_model_parallel_region(out)
 
 

@@ -25,6 +25,7 @@ def _worker(rank, world, port, backend, fn, args, errq):
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                           LOCAL_RANK=str(rank), LOCAL_WORLD_SIZE=str(world))
         if backend == "nccl":
+            os.environ["MLB200_FORCE_CPU"] = "0"      # (never inherit a CPU-only switch from the parent process)
             torch.cuda.set_device(rank)
         else:
             os.environ["MLB200_FORCE_CPU"] = "1"

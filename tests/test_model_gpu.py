@@ -22,6 +22,7 @@ from megatron_llm_b200.training import setup_model_and_optimizer, train_step
 argv = %(argv)r.split()
 initialize_megatron(finetune.extra_args, {}, args_list=argv)
 model, opt, sched = setup_model_and_optimizer(finetune.model_provider, ModelType.encoder_or_decoder)
+assert next(model[0].parameters()).is_cuda, "the model must live on the GPU in this test"
 def it():
     g = torch.Generator().manual_seed(0)
     batches = [torch.randint(0, 1000, (2, %(seq)d + 1), generator=g) for _ in range(2)]   # one step = 2 micro-batches
@@ -51,7 +52,7 @@ CONFIGS = {
 
 
 def _run(argv, disable, port, fp32=False):
-    env = dict(os.environ)
+    env = dict(os.environ, MLB200_FORCE_CPU="0")
     env["MLB200_DISABLE_KERNELS"] = "1" if disable else "0"
     if fp32:
         argv = argv.replace("--bf16", "")
@@ -81,7 +82,7 @@ def test_cuda_graph_microbatch_matches_eager():
     argv = CONFIGS["llama"].replace("--train_iters 10", "--train_iters 20")
     script = SCRIPT.replace("for step in range(3):", "for step in range(6):")
     def run(extra, port):
-        env = dict(os.environ, MLB200_DISABLE_KERNELS="0")
+        env = dict(os.environ, MLB200_DISABLE_KERNELS="0", MLB200_FORCE_CPU="0")
         code = script % {"root": ROOT, "port": str(port), "argv": argv + extra, "seq": 256}
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
@@ -102,7 +103,7 @@ def test_fp16_with_dynamic_loss_scaling_trains():
     argv = CONFIGS["llama"].replace("--bf16", "--fp16 --initial_loss_scale 4096 --loss_scale_window 2")
     script = SCRIPT.replace("for step in range(3):", "for step in range(5):")
     for disable in (False, True):
-        env = dict(os.environ, MLB200_DISABLE_KERNELS="1" if disable else "0")
+        env = dict(os.environ, MLB200_DISABLE_KERNELS="1" if disable else "0", MLB200_FORCE_CPU="0")
         code = script % {"root": ROOT, "port": "29614", "argv": argv, "seq": 256}
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]

@@ -8,7 +8,13 @@ import signal
 import pytest
 import torch
 
-os.environ.setdefault("MLB200_FORCE_CPU", "1")
+
+
+@pytest.fixture(autouse=True)
+def _cpu_only(monkeypatch):
+    """These tests run the CPU paths; the switch must NOT leak into the pytest process environment (importing this
+    module during collection of ``-m gpu`` runs once forced the GPU model tests' subprocesses onto the CPU)."""
+    monkeypatch.setenv("MLB200_FORCE_CPU", "1")
 
 
 # ----------------------------------------------------------------------------------------------- micro-batches

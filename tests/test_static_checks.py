@@ -50,14 +50,14 @@ def test_every_python_file_parses_and_binds_the_names_it_reads():
     assert not problems, problems
 
 
-def test_every_args_attribute_is_a_flag_or_assigned_somewhere():
+def test_every_args_attribute_is_a_flag_or_assigned_somewhere(monkeypatch):
     """``args.<name>`` read anywhere in the package / entry points / tasks must be a destination of one of the argument
     parsers or be assigned somewhere (the reference lost ``--bert_no_binary_head`` from its parser while
     pretrain_bert.py kept reading it: this is the check that would have caught it)."""
     import re
     import sys
     sys.path.insert(0, ROOT)
-    os.environ.setdefault("MLB200_FORCE_CPU", "1")
+    monkeypatch.setenv("MLB200_FORCE_CPU", "1")
     import finetune
     from megatron_llm_b200.arguments import build_base_parser
     dests = {a.dest for a in finetune.extra_args(build_base_parser())._actions}
