@@ -305,7 +305,17 @@ def run_ours(a):
     sampler = ClockSampler(index=int(os.environ.get("LOCAL_RANK", "0")))
     if rank == 0:
         sampler.start()
+    tp_comm = fused_tp.communicator() if _fused_tp_active() else None
+    exposed0 = tp_comm.exposed_ms() if tp_comm is not None else None
     ms_dev, launches, _ = timed(it_dev, a.steps, read_loss=False)
+    exposed = None
+    if tp_comm is not None:
+        # device-side %globaltimer accounting of the fused kernels: time their GEMM tiles could not hide
+        e1 = tp_comm.exposed_ms()
+        ex = torch.tensor([(e1[0] - exposed0[0]) / a.steps, (e1[1] - exposed0[1]) / a.steps], device=dev)
+        dist.all_reduce(ex, op=dist.ReduceOp.MAX)
+        exposed = {"all_gather_wait": round(ex[0].item(), 3), "reduce_scatter_tail": round(ex[1].item(), 3),
+                   "total": round(ex.sum().item(), 3)}
     host_enqueue_ms = timed.host_enqueue_ms
     clocks = sampler.stop() if rank == 0 else None
     e2e = None
@@ -335,6 +345,7 @@ def run_ours(a):
                                        "nccl (fused kernels disabled after a handshake timeout)" if fused_fallback
                                        else "nccl"),
                            "peak_mem_gb": round(peak_gb, 2)},
+               "exposed_tp_collective_ms_per_step": exposed,
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                "host_enqueue_ms_per_step": host_enqueue_ms}
         print(json.dumps(out), flush=True)

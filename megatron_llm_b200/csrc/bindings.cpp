@@ -46,7 +46,8 @@ int mlb_ce_bwd(int dtype, const void* logits, void* out, const long long* target
 int mlb_adamw_flat(float* p, const float* g, float* m, float* v, void* p16, int p16_dtype, long long n,
                    long long global_offset, const long long* seg_start, const float* seg_wd, const float* seg_lr_mult,
                    int nseg, float lr, float beta1, float beta2, float eps, float bc1, float bc2,
-                   const float* grad_scale_ptr, const int* skip_flag, cudaStream_t st);
+                   const float* grad_scale_ptr, const int* skip_flag, const long long* p16_peers, int n_peers,
+                   cudaStream_t st);
 int mlb_sgd_flat(float* p, const float* g, float* mom, void* p16, int p16_dtype, long long n, long long global_offset,
                  const long long* seg_start, const float* seg_wd, const float* seg_lr_mult, int nseg, float lr,
                  float momentum, int first_step, const float* grad_scale_ptr, const int* skip_flag, cudaStream_t st);
@@ -224,15 +225,20 @@ static void adamw_flat(torch::Tensor& p, const torch::Tensor& g, torch::Tensor& 
                        const c10::optional<torch::Tensor>& p16, int64_t global_offset, const torch::Tensor& seg_start,
                        const torch::Tensor& seg_wd, const c10::optional<torch::Tensor>& seg_lr_mult, double lr,
                        double beta1, double beta2, double eps, double bc1, double bc2,
-                       const c10::optional<torch::Tensor>& grad_scale, const c10::optional<torch::Tensor>& skip) {
+                       const c10::optional<torch::Tensor>& grad_scale, const c10::optional<torch::Tensor>& skip,
+                       const std::vector<int64_t>& p16_peers) {
   c10::cuda::CUDAGuard guard(p.device());
+  // ZeRO-1 fused cast + parameter all-gather: device pointers of every DP peer's 16-bit buffer at this shard's start
+  TORCH_CHECK(p16_peers.empty() || (p16.has_value() && p16_peers.size() <= 8), "adamw_flat: bad peer list");
+  long long peers[8] = {0};
+  for (size_t i = 0; i < p16_peers.size(); ++i) peers[i] = p16_peers[i];
   CHK(mlb_adamw_flat(p.data_ptr<float>(), g.data_ptr<float>(), m.data_ptr<float>(), v.data_ptr<float>(),
                      const_cast<void*>(optp(p16)), p16.has_value() ? dt(*p16) : 0, p.numel(), global_offset,
                      (const long long*)seg_start.data_ptr(), seg_wd.data_ptr<float>(),
                      seg_lr_mult.has_value() ? seg_lr_mult->data_ptr<float>() : nullptr, (int)seg_wd.numel(), (float)lr,
                      (float)beta1, (float)beta2, (float)eps, (float)bc1, (float)bc2,
                      grad_scale.has_value() ? grad_scale->data_ptr<float>() : nullptr,
-                     skip.has_value() ? skip->data_ptr<int>() : nullptr, cur()));
+                     skip.has_value() ? skip->data_ptr<int>() : nullptr, peers, (int)p16_peers.size(), cur()));
 }
 static void sgd_flat(torch::Tensor& p, const torch::Tensor& g, torch::Tensor& mom, const c10::optional<torch::Tensor>& p16,
                      int64_t global_offset, const torch::Tensor& seg_start, const torch::Tensor& seg_wd,

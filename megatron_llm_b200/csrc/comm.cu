@@ -9,12 +9,26 @@
 //      writes its own slice;
 //   3. (all-reduce only) all-gather: the reduced slice is stored into every peer's bucket over NVLink;
 //   4. handshake out: a rank's kernel retires only when every peer has finished reading from / writing into its bucket.
+#include <string.h>
+
 #include "gemm_types.h"
 #include "ptx.cuh"
 
 namespace mlb {
 
-enum DpPadSlot : int { DP_READY = 0, DP_DONE = 8, DP_CTA_COUNTER = 40 };
+enum DpPadSlot : int { DP_READY = 0, DP_DONE = 8, DP_ERROR = 32 /* == PAD_ERROR */, DP_CTA_COUNTER = 40 };
+
+// bounded spin: a lost peer must not hang the box; the timeout is recorded in the pad (polled once per training step)
+__device__ __forceinline__ void dp_spin_until_ge(const int* flag, int value, int* pad_local) {
+  long long polls = 0;
+  while (ld_acquire_sys(flag) < value) {
+    __nanosleep(100);
+    if (++polls > (1LL << 25)) {
+      st_release_sys(pad_local + DP_ERROR, 1);
+      break;
+    }
+  }
+}
 
 struct DpArgs {
   float* peer[GEMM_MAX_PEERS];
@@ -34,13 +48,7 @@ __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
         if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_READY + a.rank, a.epoch);
     }
     for (int p = 0; p < a.world; ++p)
-      if (p != a.rank) {
-        long long polls = 0;
-        while (ld_acquire_sys(a.pad_local + DP_READY + p) < a.epoch) {
-          __nanosleep(100);
-          if (++polls > (1LL << 25)) break;
-        }
-      }
+      if (p != a.rank) dp_spin_until_ge(a.pad_local + DP_READY + p, a.epoch, a.pad_local);
   }
   __syncthreads();
 
@@ -86,13 +94,7 @@ __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
     for (int p = 0; p < a.world; ++p)
       if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_DONE + a.rank, a.epoch);
     for (int p = 0; p < a.world; ++p)
-      if (p != a.rank) {
-        long long polls = 0;
-        while (ld_acquire_sys(a.pad_local + DP_DONE + p) < a.epoch) {
-          __nanosleep(100);
-          if (++polls > (1LL << 25)) break;
-        }
-      }
+      if (p != a.rank) dp_spin_until_ge(a.pad_local + DP_DONE + p, a.epoch, a.pad_local);
   }
 }
 
@@ -133,6 +135,27 @@ __global__ void set_ints3_kernel(int* dst, int a, int b, int c) {
 
 extern "C" int mlb_set_ints3(int* dst, int a, int b, int c, cudaStream_t stream) {
   set_ints3_kernel<<<1, 1, 0, stream>>>(dst, a, b, c);
+  return (int)cudaGetLastError();
+}
+
+// all ranks of a group meet: used after the ZeRO-1 optimizer kernel has stored its updated 16-bit shard into every
+// peer's parameter buffer (stream order: the stores are complete when this kernel starts)
+__global__ void peer_barrier_kernel(int* pad_local, mlb::DpArgs a, int slot) {
+  __threadfence_system();
+  for (int p = 0; p < a.world; ++p)
+    if (p != a.rank) mlb::st_release_sys(a.pad_peer[p] + slot + a.rank, a.epoch);
+  for (int p = 0; p < a.world; ++p)
+    if (p != a.rank) mlb::dp_spin_until_ge(pad_local + slot + p, a.epoch, pad_local);
+}
+
+extern "C" int mlb_peer_barrier(int* pad_local, const long long* pad_peer_ptrs, int rank, int world, int epoch, int slot,
+                                cudaStream_t st) {
+  if (world > mlb::GEMM_MAX_PEERS) return -2;
+  mlb::DpArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < world; ++i) a.pad_peer[i] = reinterpret_cast<int*>(pad_peer_ptrs[i]);
+  a.pad_local = pad_local; a.rank = rank; a.world = world; a.epoch = epoch;
+  peer_barrier_kernel<<<1, 1, 0, st>>>(pad_local, a, slot);
   return (int)cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@ int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int
                           mlb::GemmComm* comm, int prev_total, int num_sms, cudaStream_t stream);
 int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
                         int ldc, int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+int mlb_peer_barrier(int* pad_local, const long long* pad_peer_ptrs, int rank, int world, int epoch, int slot,
+                     cudaStream_t st);
 int mlb_dp_reduce(int reduce_scatter, float* local, const long long* peer_ptrs, int* pad_local,
                   const long long* pad_peer_ptrs, long long n, int rank, int world, int epoch, float scale,
                   int num_ctas, cudaStream_t st);
@@ -96,7 +98,7 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
                           const std::vector<int64_t>& ag_src, int64_t rows_per_rank, torch::Tensor& chunk_flags,
                           torch::Tensor& read_counters, int64_t pad_local, const std::vector<int64_t>& pad_peers,
                           int64_t rank, int64_t world, int64_t epoch, int64_t num_comm_ctas, int64_t sms,
-                          int64_t state_ptr) {
+                          int64_t state_ptr, int64_t stats_ptr) {
   c10::cuda::CUDAGuard guard(gathered.device());
   const int M = gathered.size(0), K = gathered.size(1);
   const int N = b_mn ? weight.size(1) : weight.size(0);
@@ -110,6 +112,7 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
   num_comm_ctas = c.num_comm_ctas;
   c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
   c.state = reinterpret_cast<const int*>(state_ptr);
+  c.stats = reinterpret_cast<unsigned long long*>(stats_ptr);
   c.m_rotate_blocks = (int)(rank * rows_per_rank / mlb::GEMM_BLOCK_M);
   for (int i = 0; i < world; ++i) c.ag_src[i] = reinterpret_cast<const void*>(ag_src[i]);
   c.ag_dst = gathered.data_ptr();
@@ -137,7 +140,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
                              const std::vector<int64_t>& rs_dst, int64_t rs_slots, int64_t rows_per_rank,
                              int64_t prev_total, int64_t tiles_1cta, torch::Tensor& reduce_counter, int64_t pad_local,
                              const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world, int64_t epoch,
-                             int64_t sms, int64_t state_ptr, const std::vector<int64_t>& ar_dst) {
+                             int64_t sms, int64_t state_ptr, const std::vector<int64_t>& ar_dst, int64_t stats_ptr) {
   c10::cuda::CUDAGuard guard(x.device());
   const int M = x.size(0), K = x.size(1);
   const int N = b_mn ? weight.size(1) : weight.size(0);
@@ -148,6 +151,7 @@ static int64_t fused_gemm_rs(const torch::Tensor& x, const torch::Tensor& weight
   memset(&c, 0, sizeof(c));
   c.rank = rank; c.world = world; c.epoch = epoch;
   c.state = reinterpret_cast<const int*>(state_ptr);
+  c.stats = reinterpret_cast<unsigned long long*>(stats_ptr);
   c.m_rotate_blocks = (int)(((rank + 1) % world) * rows_per_rank / mlb::GEMM_BLOCK_M);  // remote chunks first
   c.m_group_blocks = pick_group_blocks(rows_per_rank, (int64_t)N * K * 2);
   c.m_interleave = (world == 2 && (M / 256) % (2 * c.m_group_blocks) == 0) ? 1 : 0;
@@ -189,6 +193,15 @@ static void dp_reduce(torch::Tensor& local, const std::vector<int64_t>& peer_ptr
                     local.numel(), (int)rank, (int)world, (int)epoch, (float)scale, (int)num_ctas, cur()));
 }
 
+// all ranks of the group meet on the current stream (flags in pad slots [slot, slot + world))
+static void peer_barrier(int64_t pad_local, const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world,
+                         int64_t epoch, int64_t slot) {
+  long long pads[mlb::GEMM_MAX_PEERS] = {0};
+  TORCH_CHECK(world <= mlb::GEMM_MAX_PEERS && (int64_t)pad_peers.size() >= world);
+  for (int i = 0; i < world; ++i) pads[i] = pad_peers[i];
+  CHK(mlb_peer_barrier(reinterpret_cast<int*>(pad_local), pads, (int)rank, (int)world, (int)epoch, (int)slot, cur()));
+}
+
 // state[0..2] = {a, b, c} on the current stream (the offsets a replayed graph's fused kernels add to their epochs)
 static void comm_set_state(torch::Tensor& state, int64_t a, int64_t b, int64_t c) {
   c10::cuda::CUDAGuard guard(state.device());
@@ -224,4 +237,5 @@ void register_comm(pybind11::module_& m) {
   m.def("fused_ag_gemm", &fused_ag_gemm);
   m.def("fused_gemm_rs", &fused_gemm_rs);
   m.def("dp_reduce", &dp_reduce);
+  m.def("peer_barrier", &peer_barrier);
 }

@@ -144,7 +144,7 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      unsigned long long w_empty = 0, t_begin = dbg ? g2_clock() : 0;
+      unsigned long long w_empty = 0, t_begin = dbg ? g2_clock() : 0, ag_wait_ns = 0;
       for (int tile = pair; tile < total_tiles; tile += num_pairs) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
@@ -152,7 +152,8 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
         if constexpr (MODE == MODE_AG_GEMM) {
           if (m0 / p.comm.ag_rows_per_rank != p.comm.rank) {   // (the own shard was placed before the launch)
-            spin_until_ge(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
+            ag_wait_ns += spin_until_ge_timed(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH),
+                                              p.comm.pad_local);
             fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
           }
         }
@@ -182,6 +183,9 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
       }
       if (dbg) { g2_dbg[blockIdx.x * 8 + 3] = w_empty; g2_dbg[blockIdx.x * 8 + 4] = g2_clock() - t_begin; }
+      if constexpr (MODE == MODE_AG_GEMM) {
+        if (p.comm.stats) atomicAdd(p.comm.stats + 0, ag_wait_ns / (unsigned long long)(2 * num_pairs));
+      }
     }
   } else if (warp == 1 && leader) {
     // ================================ MMA issuer (leader CTA only) ================================

@@ -49,6 +49,14 @@ __device__ __forceinline__ void spin_until_ge(const int* flag, int value, int* p
   }
 }
 
+// spin_until_ge that also returns how long it blocked (0 if the flag was already there)
+__device__ __forceinline__ unsigned long long spin_until_ge_timed(const int* flag, int value, int* pad_local) {
+  if (ld_acquire_sys(flag) >= value) return 0;
+  const unsigned long long t0 = globaltimer_ns();
+  spin_until_ge(flag, value, pad_local);
+  return globaltimer_ns() - t0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // puller CTA: all-gather peer shards into the local gathered buffer with bulk async copies
 // ------------------------------------------------------------------------------------------------
@@ -167,6 +175,7 @@ static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) 
 static __device__ void rs_reduce_phase(const GemmParams& p) {
   const GemmComm& c = p.comm;
   __shared__ int s_last;
+  const unsigned long long t_tail = (c.stats && threadIdx.x == 0) ? globaltimer_ns() : 0;
   if (threadIdx.x == 0) {
     const int expected = comm_rs_expected(c);
     for (int s = 0; s < c.world; ++s) spin_until_ge(c.pad_local + PAD_RS_ARRIVED + s, expected, c.pad_local);
@@ -247,6 +256,7 @@ static __device__ void rs_reduce_phase(const GemmParams& p) {
         if (s != c.rank) spin_until_ge(c.pad_local + PAD_AR_DONE + s, epoch, c.pad_local);
     }
   }
+  if (c.stats && threadIdx.x == 0) atomicAdd(c.stats + 1, (globaltimer_ns() - t_tail) / gridDim.x);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -334,13 +344,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      unsigned long long ag_wait_ns = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += num_compute_ctas) {
         int m_blk, n_blk;
         tile_coords(tile, m_blk, n_blk);
         const int m0 = m_blk * GEMM_BLOCK_M, n0 = n_blk * BLOCK_N;
         if constexpr (MODE == MODE_AG_GEMM) {
           if (m0 / p.comm.ag_rows_per_rank != p.comm.rank)     // (the own shard was placed before the launch)
-            spin_until_ge(p.comm.ag_chunk_flags + m_blk, comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
+            ag_wait_ns += spin_until_ge_timed(p.comm.ag_chunk_flags + m_blk, comm_epoch(p.comm, STATE_AG_EPOCH),
+                                              p.comm.pad_local);
           fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
         }
         for (int kb = 0; kb < num_k; ++kb) {
@@ -365,6 +377,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+      }
+      if constexpr (MODE == MODE_AG_GEMM) {
+        if (p.comm.stats) atomicAdd(p.comm.stats + 0, ag_wait_ns / (unsigned long long)num_compute_ctas);
       }
     }
   } else if (warp == 1) {

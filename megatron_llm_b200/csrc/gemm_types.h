@@ -56,6 +56,10 @@ struct GemmComm {
   //      CUDA graph keeps the arguments of its capture; the host writes {ag epoch, rs epoch, rs arrivals} deltas here
   //      before every replay so the captured calls continue the live sequence.
   const int* state;
+  // ---- exposed-communication accounting (nullptr = off), %globaltimer nanoseconds averaged over the CTAs of a launch:
+  //      [0] all-gather: time the TMA producers spent blocked on chunk flags (data not there yet)
+  //      [1] reduce-scatter / all-reduce: time from a CTA's last tile to the end of the slot reduction + handshakes
+  unsigned long long* stats;
   // ---- signal pads
   int* pad_local;
   int* pad_peer[GEMM_MAX_PEERS];

@@ -24,13 +24,22 @@ __device__ __forceinline__ int find_segment(const long long* __restrict__ seg_st
 
 constexpr int OPT_CHUNK = 2048;  // elements per CTA iteration (256 threads x 8)
 
+// ZeRO-1: the updated 16-bit weights of this rank's shard are stored into EVERY data-parallel peer's parameter buffer
+// (NVLink-mapped symmetric memory) by the optimizer kernel itself: the fp32 -> bf16 cast and the parameter all-gather
+// (reference: optimizer/distrib_optimizer.py:592-608, one NCCL all-gather + per-tensor copies) are the same pass.
+struct P16Peers {
+  void* ptr[8];   // peer d's buffer at the start of this shard (own buffer included)
+  int n;          // 0: write only `p16`
+};
+
 template <typename TP16>
 __global__ void __launch_bounds__(256)
 adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                   TP16* __restrict__ p16, long long n, long long global_offset,
                   const long long* __restrict__ seg_start, const float* __restrict__ seg_wd,
                   const float* __restrict__ seg_lr_mult, int nseg, float lr, float beta1, float beta2, float eps,
-                  float bc1, float bc2, const float* __restrict__ grad_scale_ptr, const int* __restrict__ skip_flag) {
+                  float bc1, float bc2, const float* __restrict__ grad_scale_ptr, const int* __restrict__ skip_flag,
+                  const P16Peers peers) {
   if (skip_flag != nullptr && *skip_flag != 0) return;
   const float gscale = grad_scale_ptr ? *grad_scale_ptr : 1.f;
   const long long nchunks = (n + OPT_CHUNK - 1) / OPT_CHUNK;
@@ -82,7 +91,11 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
       *reinterpret_cast<float4*>(m + base + 4) = *reinterpret_cast<float4*>(mv + 4);
       *reinterpret_cast<float4*>(v + base) = *reinterpret_cast<float4*>(vv);
       *reinterpret_cast<float4*>(v + base + 4) = *reinterpret_cast<float4*>(vv + 4);
-      if (p16 != nullptr) {
+      if (peers.n > 0) {
+        Vec<TP16> o;
+        o.from_float(pv);
+        for (int d = 0; d < peers.n; ++d) o.store(reinterpret_cast<TP16*>(peers.ptr[d]) + base);
+      } else if (p16 != nullptr) {
         Vec<TP16> o;
         o.from_float(pv);
         o.store(p16 + base);
@@ -92,7 +105,11 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
       for (int j = 0; j < 8; ++j)
         if (base + j < n) {
           p[base + j] = pv[j]; m[base + j] = mv[j]; v[base + j] = vv[j];
-          if (p16 != nullptr) p16[base + j] = from_f<TP16>(pv[j]);
+          if (peers.n > 0) {
+            for (int d = 0; d < peers.n; ++d) reinterpret_cast<TP16*>(peers.ptr[d])[base + j] = from_f<TP16>(pv[j]);
+          } else if (p16 != nullptr) {
+            p16[base + j] = from_f<TP16>(pv[j]);
+          }
         }
     }
   }
@@ -217,13 +234,17 @@ extern "C" int mlb_adamw_flat(float* p, const float* g, float* m, float* v, void
                               long long global_offset, const long long* seg_start, const float* seg_wd,
                               const float* seg_lr_mult, int nseg, float lr, float beta1, float beta2, float eps,
                               float bc1, float bc2, const float* grad_scale_ptr, const int* skip_flag,
-                              cudaStream_t st) {
+                              const long long* p16_peers, int n_peers, cudaStream_t st) {
   if (n <= 0) return 0;
+  if (n_peers > 8) return -2;
+  mlb::P16Peers peers;
+  peers.n = n_peers;
+  for (int i = 0; i < 8; ++i) peers.ptr[i] = i < n_peers ? reinterpret_cast<void*>(p16_peers[i]) : nullptr;
   const int grid = mlb::opt_grid(n);
   if (p16 == nullptr || p16_dtype == mlb::DT_BF16)
-    mlb::adamw_flat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p16, n, global_offset, seg_start, seg_wd, seg_lr_mult, nseg, lr, beta1, beta2, eps, bc1, bc2, grad_scale_ptr, skip_flag);
+    mlb::adamw_flat_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(p, g, m, v, (__nv_bfloat16*)p16, n, global_offset, seg_start, seg_wd, seg_lr_mult, nseg, lr, beta1, beta2, eps, bc1, bc2, grad_scale_ptr, skip_flag, peers);
   else if (p16_dtype == mlb::DT_F16)
-    mlb::adamw_flat_kernel<__half><<<grid, 256, 0, st>>>(p, g, m, v, (__half*)p16, n, global_offset, seg_start, seg_wd, seg_lr_mult, nseg, lr, beta1, beta2, eps, bc1, bc2, grad_scale_ptr, skip_flag);
+    mlb::adamw_flat_kernel<__half><<<grid, 256, 0, st>>>(p, g, m, v, (__half*)p16, n, global_offset, seg_start, seg_wd, seg_lr_mult, nseg, lr, beta1, beta2, eps, bc1, bc2, grad_scale_ptr, skip_flag, peers);
   else return -100;
   return (int)cudaGetLastError();
 }

@@ -285,6 +285,12 @@ __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
 // ---------------------------------------------------------------- system-scope flags (cross-GPU)
 __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   int v;

@@ -24,6 +24,17 @@ class DistributedOptimizer(FlatOptimizer):
         super().__init__(optimizer_config, clip_grad, log_num_zeros_in_grad, params_have_main_grad,
                          use_contiguous_buffers_in_local_ddp, fp16, bf16, params_dtype, grad_scaler, models,
                          shard_over_dp=True)
+        # fused cast + all-gather: when the DDP wrapper's 16-bit parameter buffer lives in symmetric memory, the AdamW
+        # kernel stores the updated shard into every DP peer's buffer and gather_model_params() is a barrier
+        self._fused_gather = []
+        for g in self.groups:
+            comm = getattr(g.ddp, "_symm", None)
+            if (comm is not None and getattr(comm, "pbuf", None) is not None and g.model_param_buffer is not None
+                    and g.model_param_buffer.data_ptr() == comm.pbuf.data_ptr() and not g.is_fp32_model
+                    and self.config["name"] == "adam"):
+                g.p16_peer_ptrs = comm.param_peer_ptrs(g.shard[0])
+                if comm not in self._fused_gather:
+                    self._fused_gather.append(comm)
 
     def _norm_reduce_group(self):
         """Every (tp, pp, dp) rank holds a distinct slice of the gradients: reduce over the whole world."""
@@ -50,9 +61,13 @@ class DistributedOptimizer(FlatOptimizer):
         """All-gather the updated weight slices in place (bf16 buffer; fp32 buffer for fp32 models)."""
         timers("params-all-gather", log_level=1).start(barrier=args.barrier_with_L1_time)
         w = ps.get_data_parallel_world_size()
+        for comm in self._fused_gather:
+            comm.params_barrier()
         if w > 1:
             group = ps.get_data_parallel_group()
             for g in self.groups:
+                if g.p16_peer_ptrs:
+                    continue              # already stored into every peer's buffer by the optimizer kernel
                 buf = g.model_param_buffer
                 s, e = g.shard
                 n = e - s

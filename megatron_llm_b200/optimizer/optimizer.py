@@ -40,13 +40,14 @@ class _FlatGroup:
     """One (model chunk, grad dtype) buffer: segment table + fp32 state, for the full buffer or a DP shard."""
 
     def __init__(self, ddp, gdt, param_group_of, shard=None):
+        self.ddp, self.gdt = ddp, gdt
         self.grad_buffer = ddp.grad_buffers()[gdt]
         self.index_map = ddp.param_index_maps()[gdt]
         pbufs = ddp.param_buffers()[gdt]
         # params sorted by offset
         self.params = sorted(self.index_map.keys(), key=lambda p: self.index_map[p][0])
         assert len(pbufs) <= 1, "mixed parameter dtypes inside one grad buffer are not supported"
-        self.model_param_buffer = next(iter(pbufs.values())) if pbufs else None
+        self.param_dtype = next(iter(pbufs.keys())) if pbufs else None
         self.numel = self.grad_buffer.numel_padded
         self.shard = shard if shard is not None else (0, self.numel)   # [start, end) owned by this rank
         dev = self.grad_buffer.data.device
@@ -67,6 +68,7 @@ class _FlatGroup:
         s, e = self.shard
         n = e - s
         self.is_fp32_model = self.model_param_buffer is not None and self.model_param_buffer.dtype == torch.float32
+        self.p16_peer_ptrs = []      # ZeRO-1 fused param gather: every DP peer's 16-bit buffer at this shard (optional)
         if self.is_fp32_model:
             self.main_param = self.model_param_buffer[s:e]            # optimise the weights in place
         else:
@@ -75,6 +77,11 @@ class _FlatGroup:
         self.exp_avg = torch.zeros(n, dtype=torch.float32, device=dev)
         self.exp_avg_sq = torch.zeros(n, dtype=torch.float32, device=dev)
         self.workspace = torch.zeros(148 * 8, dtype=torch.float32, device=dev)
+
+    @property
+    def model_param_buffer(self):
+        """The DDP wrapper's flat parameter buffer (looked up on use: it may be re-homed into symmetric memory)."""
+        return self.ddp.param_buffers()[self.gdt].get(self.param_dtype) if self.param_dtype is not None else None
 
     def main_grad(self):
         s, e = self.shard
@@ -380,7 +387,8 @@ class FlatOptimizer(MegatronOptimizer):
                 bc2 = 1.0 - b2 ** self.step_count
                 if ops.cuda_ops_available(grad):
                     ops._C().adamw_flat(g.main_param, grad, g.exp_avg, g.exp_avg_sq, p16, off, g.seg_start, seg_wd,
-                                        g.seg_lr_mult, lr, b1, b2, eps, bc1, bc2, self._clip_coef, self.found_inf)
+                                        g.seg_lr_mult, lr, b1, b2, eps, bc1, bc2, self._clip_coef, self.found_inf,
+                                        g.p16_peer_ptrs if p16 is not None else [])
                     ops._count()
                 else:
                     skip = bool(self.found_inf.item())

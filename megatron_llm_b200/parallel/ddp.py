@@ -201,6 +201,19 @@ class DistributedDataParallel(DistributedDataParallelBase):
         for p, (s, e) in self._grad_buffer_param_index_map[gdt].items():
             p.main_grad = buf.get(p.data.shape, s)
 
+    def rehome_param_buffer(self, gdt, pdtype, new_storage: torch.Tensor):
+        """Move the flat parameter buffer of dtype ``pdtype`` (grad dtype ``gdt``) into ``new_storage`` (symmetric
+        memory: the ZeRO-1 optimizer kernel stores updated weights straight into every DP peer's copy) and re-point
+        every ``param.data`` view at it."""
+        old = self._param_buffers[gdt][pdtype]
+        assert new_storage.numel() >= old.numel() and new_storage.dtype == pdtype
+        new = new_storage[:old.numel()]
+        new.copy_(old)
+        self._param_buffers[gdt][pdtype] = new
+        for p, (s, e) in self._grad_buffer_param_index_map[gdt].items():
+            if p.dtype == pdtype:
+                p.data = new[s:e].view(p.data.shape)
+
     def _make_param_hook(self, param):
         def hook(*unused):
             if param.grad is not None:

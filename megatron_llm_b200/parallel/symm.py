@@ -61,6 +61,35 @@ class LoopbackWorld:
         return self._bufs[name]
 
 
+_COMMUNICATORS = []      # every live TP / DP communicator of this process (polled by check_timeouts)
+_POLL = {"buf": None, "event": None}
+
+
+def check_timeouts() -> None:
+    """Called once per training step: a bounded spin-wait inside a fused kernel that gave up (lost / hung peer) leaves
+    ``PAD_ERROR`` in the communicator's signal pad and the kernel's results are garbage.  The flags are fetched with an
+    asynchronous copy and examined when it has landed (no host sync on the step path), so the failure surfaces at most
+    one step late -- as an exception, never as silently wrong training."""
+    if not _COMMUNICATORS or torch.cuda.is_current_stream_capturing():
+        return
+    ev = _POLL["event"]
+    if ev is not None and ev.query():
+        bad = [i for i, v in enumerate(_POLL["buf"][:len(_COMMUNICATORS)].tolist()) if v != 0]
+        _POLL["event"] = None
+        if bad:
+            names = ", ".join(type(_COMMUNICATORS[i]).__name__ for i in bad)
+            raise RuntimeError(f"peer-memory collective timed out waiting for a peer ({names}): a rank is lost or hung; "
+                               "results of the affected kernels are invalid")
+    if _POLL["event"] is None:
+        if _POLL["buf"] is None or _POLL["buf"].numel() < len(_COMMUNICATORS):
+            _POLL["buf"] = torch.zeros(max(8, len(_COMMUNICATORS)), dtype=torch.int32).pin_memory()
+        for i, c in enumerate(_COMMUNICATORS):
+            _POLL["buf"][i:i + 1].copy_(c.pad[32:33], non_blocking=True)
+        e = torch.cuda.Event()
+        e.record()
+        _POLL["event"] = e
+
+
 class TPCommunicator:
     """Fused GEMM+collective for one tensor-parallel group.
 
@@ -104,9 +133,12 @@ class TPCommunicator:
         self.rs_arrived_total = 0
         # offsets that calls captured in a CUDA graph add to their (frozen) epoch arguments -- see replay_offsets()
         self.state = torch.zeros(4, dtype=torch.int32, device=self.device)
+        # exposed-communication accounting written by the kernels (ns, averaged over the CTAs of each launch)
+        self.stats = torch.zeros(2, dtype=torch.int64, device=self.device)
         torch.cuda.synchronize()
         if loopback is None:
             dist.barrier(group=group)
+            _COMMUNICATORS.append(self)
         self.enabled = True
 
     def _symmetric(self, name: str, numel: int, dtype):
@@ -161,7 +193,7 @@ class TPCommunicator:
         w = weight if weight.stride(-1) == 1 else weight.contiguous()
         self.mod.fused_ag_gemm(gathered, w, out, transposed_weight, self.xs_ptrs, m, self.chunk_flags,
                                self.read_counters, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
-                               self.ag_epoch, self.num_comm_ctas, self.sms, self._state_ptr())
+                               self.ag_epoch, self.num_comm_ctas, self.sms, self._state_ptr(), self.stats.data_ptr())
         _ext.count()
         return out, gathered.view(self.world * lead[0], *lead[1:], K)
 
@@ -203,7 +235,7 @@ class TPCommunicator:
         self.rs_arrived_total = self.mod.fused_gemm_rs(
             x, w, out, transposed_weight, rs_dst, rs_slots, m, self.rs_arrived_total, tiles_per_dst,
             self.reduce_counter, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.rs_epoch,
-            self.sms, self._state_ptr(), ar_dst)
+            self.sms, self._state_ptr(), ar_dst, self.stats.data_ptr())
         _ext.count()
         if all_reduce:
             return full.clone() if keep else full
@@ -253,6 +285,12 @@ class TPCommunicator:
     def error_flag(self) -> int:
         return int(self.pad[32].item())
 
+    def exposed_ms(self):
+        """(all-gather wait, reduce-scatter tail) in ms accumulated since the communicator was built: time the fused
+        kernels could not hide behind their GEMM tiles (device ``%globaltimer`` stamps; host sync)."""
+        ag, rs = self.stats.tolist()
+        return ag / 1e6, rs / 1e6
+
 
 class DPCommunicator:
     """Peer-memory gradient reduction for one data-parallel group: the whole fp32 grad buffer is symmetric."""
@@ -279,7 +317,31 @@ class DPCommunicator:
         torch.cuda.synchronize()
         if loopback is None:
             dist.barrier(group=group)
+            _COMMUNICATORS.append(self)
         self.enabled = True
+
+    def error_flag(self) -> int:
+        return int(self.pad[32].item())
+
+    # ---- ZeRO-1 parameter all-gather fused into the optimizer kernel -----------------------------------------------
+    def attach_param_buffer(self, numel: int, dtype):
+        """Symmetric twin of the DDP wrapper's flat 16-bit parameter buffer: every rank's AdamW kernel stores its
+        updated shard into all of them (``adamw_flat(..., p16_peers)``), :meth:`params_barrier` closes the step."""
+        self.pbuf, self.pbuf_ptrs = TPCommunicator._symmetric(self, "dp_params", numel, dtype)
+        self.param_epoch = 0
+        return self.pbuf
+
+    def param_peer_ptrs(self, start_elem: int):
+        """Device pointers of element ``start_elem`` of every rank's parameter buffer (own rank first)."""
+        es = self.pbuf.element_size()
+        order = [(self.rank + k) % self.world for k in range(self.world)]
+        return [self.pbuf_ptrs[d] + es * start_elem for d in order]
+
+    def params_barrier(self):
+        """All ranks' optimizer kernels have finished storing into everybody's parameter buffer."""
+        self.param_epoch += 1
+        self.mod.peer_barrier(self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, self.param_epoch, 16)
+        _ext.count()
 
     @classmethod
     def loopback_group(cls, world: int, numel_padded: int, num_ctas: int = 16):
@@ -342,4 +404,10 @@ def bind_dp_communicator(ddp_module, group=None) -> Optional[DPCommunicator]:
     comm = DPCommunicator(group, mb.numel_padded)
     ddp_module.rehome_grad_buffer(torch.float32, comm.buffer)
     ddp_module.bind_symmetric_communicator(comm)
+    # ZeRO-1: the 16-bit weights live in symmetric memory too, so the optimizer kernel can all-gather them as it casts
+    if getattr(ddp_module, "use_distributed_optimizer", False) and os.environ.get("MLB200_FUSED_PARAM_GATHER", "1") == "1":
+        pbufs = ddp_module.param_buffers().get(torch.float32, {})
+        for pdtype, pb in list(pbufs.items()):
+            if pdtype in (torch.bfloat16, torch.float16):
+                ddp_module.rehome_param_buffer(torch.float32, pdtype, comm.attach_param_buffer(pb.numel(), pdtype))
     return comm

@@ -273,6 +273,9 @@ def train_step(forward_step_func, data_iterator, model, optimizer, opt_param_sch
         skipped_iter = 0
     else:
         skipped_iter = 1
+    if use_cuda():
+        from .parallel import symm
+        symm.check_timeouts()      # a timed-out peer-memory handshake is fatal, not a silent fallback
     if args.empty_unused_memory_level >= 2 and use_cuda():
         torch.cuda.empty_cache()
 

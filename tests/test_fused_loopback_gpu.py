@@ -157,3 +157,39 @@ def test_loopback_gemm_all_reduce(world, m):
             assert torch.equal(got[r], got[0])
     for c in comms:
         assert c.error_flag() == 0, "a spin-wait timed out"
+
+
+def test_loopback_zero1_param_gather_barrier():
+    """ZeRO-1 fused cast + parameter all-gather: every virtual rank's AdamW kernel stores its shard of the updated
+    16-bit weights into all ranks' parameter buffers, then the ranks meet in the peer barrier."""
+    from megatron_llm_b200.ops import _ext
+    from megatron_llm_b200.parallel.symm import DPCommunicator
+    world, n = 4, 1 << 16
+    comms = DPCommunicator.loopback_group(world, n)
+    for c in comms:
+        c.attach_param_buffer(n, torch.bfloat16)
+    mod = _ext.load()
+    shard = n // world
+    torch.manual_seed(21)
+    master = torch.randn(n, device=DEV)
+    grads = torch.randn(n, device=DEV)
+    seg_start = torch.tensor([0, n], device=DEV, dtype=torch.int64)
+    seg_wd = torch.zeros(1, device=DEV)
+    coef = torch.ones(1, device=DEV)
+    inf = torch.zeros(1, device=DEV, dtype=torch.int32)
+    state = [(master[r * shard:(r + 1) * shard].clone(), torch.zeros(shard, device=DEV), torch.zeros(shard, device=DEV))
+             for r in range(world)]
+
+    def step(r):
+        p, m, v = state[r]
+        mod.adamw_flat(p, grads[r * shard:(r + 1) * shard].contiguous(), m, v, comms[r].pbuf[r * shard:(r + 1) * shard],
+                       r * shard, seg_start, seg_wd, None, 1e-2, 0.9, 0.95, 1e-8, 0.1, 0.05, coef, inf,
+                       comms[r].param_peer_ptrs(r * shard))
+        comms[r].params_barrier()
+    for _ in range(2):
+        _run_ranks(world, step)
+    torch.cuda.synchronize()
+    want = torch.cat([state[r][0] for r in range(world)]).to(torch.bfloat16)
+    for r in range(world):
+        assert torch.equal(comms[r].pbuf, want), f"rank {r}"
+        assert comms[r].error_flag() == 0

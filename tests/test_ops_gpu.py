@@ -253,7 +253,7 @@ def test_flat_adamw_and_norm_match_torch():
     lr, b1, b2, eps = 1e-2, 0.9, 0.95, 1e-8
     for step in (1, 2, 3):
         mod.adamw_flat(p, g, m, v, p16, 0, seg_start, seg_wd, None, lr, b1, b2, eps, 1 - b1 ** step, 1 - b2 ** step,
-                       coef, inf)
+                       coef, inf, [])
         gg = g * coef
         mr = b1 * mr + (1 - b1) * gg
         vr = b2 * vr + (1 - b2) * gg * gg
@@ -264,8 +264,17 @@ def test_flat_adamw_and_norm_match_torch():
     # skip flag turns the step into a no-op
     inf.fill_(1)
     before = p.clone()
-    mod.adamw_flat(p, g, m, v, p16, 0, seg_start, seg_wd, None, lr, b1, b2, eps, 0.5, 0.5, coef, inf)
+    mod.adamw_flat(p, g, m, v, p16, 0, seg_start, seg_wd, None, lr, b1, b2, eps, 0.5, 0.5, coef, inf, [])
     assert torch.equal(p, before)
+    # ZeRO-1 fused cast + all-gather: the 16-bit result goes to every listed buffer instead of `p16`
+    inf.fill_(0)
+    peers = [torch.zeros_like(p16) for _ in range(3)]
+    p16.zero_()
+    mod.adamw_flat(p, g, m, v, p16, 0, seg_start, seg_wd, None, lr, b1, b2, eps, 0.5, 0.5, coef, inf,
+                   [t.data_ptr() for t in peers])
+    for t in peers:
+        assert torch.equal(t, p.to(p16.dtype))
+    assert not p16.any()
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
