@@ -33,6 +33,8 @@ MODELS = {
     "llama2-70b": (80, 8192, 64, 8, 28672, 32000),
     "mistral-7b": (32, 4096, 32, 8, 14336, 32000),
     "llama2-tiny": (4, 1024, 8, 8, 2816, 32000),
+    "mistral-tiny": (4, 1024, 8, 2, 3584, 32000),
+    "falcon-tiny": (4, 1024, 16, 2, 4096, 65024),     # head_dim 64, GQA, parallel attention + MLP (Falcon-40B shape, small)
     "falcon-40b": (60, 8192, 128, 8, 32768, 65024),
 }
 
@@ -351,12 +353,22 @@ def run_ours(a):
         print(json.dumps(out), flush=True)
     torch.cuda.synchronize()
     dist.barrier()
-    if getattr(args, "cuda_graph_microbatch", False):
-        # tearing down NCCL communicators that are referenced by live CUDA graphs can block: leave without it
-        sys.stdout.flush()
-        sys.stderr.flush()
-        os._exit(0)
+    # orderly shutdown: the captured micro-batch graphs hold the NCCL communicators' kernels and the symmetric buffers,
+    # so they go first; then the model / optimizer, then the process group.  A watchdog ends the process if the
+    # teardown still blocks (seen with NCCL 2.28 when a graph outlives its communicator) -- the result is already out.
+    import gc
+    sys.stdout.flush()
+    sys.stderr.flush()
+    watchdog = threading.Timer(30.0, lambda: (sys.stderr.write("bench: teardown timed out, leaving\n"), os._exit(0)))
+    watchdog.daemon = True
+    watchdog.start()
+    schedules._GRAPH_RUNNERS.clear()
+    del model, optimizer, scheduler
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
     dist.destroy_process_group()
+    watchdog.cancel()
 
 
 def run_reference(a):

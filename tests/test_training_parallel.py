@@ -56,6 +56,12 @@ def _train_worker(rank, world, argv, out_path, n_steps, save_first, save_last):
     if losses and ps.get_tensor_model_parallel_rank() == 0 and ps.get_data_parallel_rank() == 0:
         with open(out_path, "w") as f:
             json.dump(losses, f)
+    if getattr(args, "cuda_graph_microbatch", False) and torch.cuda.is_available():
+        # (GPU runs from tests/test_tp_model_gpu.py) NCCL teardown under live CUDA graphs can block: result is on disk
+        import torch.distributed as dist
+        torch.cuda.synchronize()
+        dist.barrier()
+        os._exit(0)
 
 
 def _run(world, extra, out_path, n_steps=3, save_first=False, save_last=False):

@@ -20,3 +20,18 @@ cap gemm_2cta_wgrad   gemm_bf16_2cta_kernel  2 $G tn_acc 22016 4096 4096 t
 cap attn_fwd2         attn_fwd2_kernel       1 $A 1 4096 32 32 none t
 cap attn_bwd_dkdv     attn_bwd_dkdv_kernel   1 $A 1 4096 32 32 none t
 cap attn_bwd_dq       attn_bwd_dq_kernel     1 $A 1 4096 32 32 none t
+E="python tools/profiling/ew_drive.py"
+cap rmsnorm_fwd       norm_fwd_kernel        2 $E
+cap rmsnorm_bwd       norm_bwd_kernel        1 $E
+cap swiglu_fwd        glu_fwd_kernel         2 $E
+cap swiglu_bwd        glu_bwd_kernel         1 $E
+cap rope_qkv          rope_qkv_kernel        1 $E
+cap ce_stats          ce_stats_kernel        1 $E
+cap adamw_flat        adamw_flat_kernel      1 $E
+cap embedding_bwd     embedding_bwd_kernel   1 $E
+cap bias_dropout_add  bias_dropout_add_kernel 1 $E
+# the fused GEMM+collective kernels with ONE virtual rank (ncu serialises kernels, so peers cannot answer): instruction
+# mix / tensor pipe of the same code that moves tiles through peer pointers
+L="python tools/profiling/fused_loopback_drive.py"
+cap fused_ag_gemm     gemm_bf16_2cta_kernel  1 $L ag
+cap fused_gemm_rs     gemm_bf16_2cta_kernel  1 $L rs

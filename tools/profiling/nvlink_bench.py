@@ -44,6 +44,8 @@ def main():
         """direction 'pull': src = peer, dst = local; 'push': src = local, dst = peer."""
         peers = [(rank + 1) % world] if pattern == "ring" else [(rank + i) % world for i in range(1, world)]
         nbytes = total if pattern == "ring" else per_peer
+        if mode == 2:          # rows are `stride` apart at the destination: stay inside the buffer
+            nbytes = (nbytes * row // stride) // piece * piece
         share = max(ctas // len(peers), 1)
 
         def once():
@@ -89,8 +91,8 @@ def main():
             run(direction, pattern, 1, 16, piece=16384, stages=12)
             run(direction, pattern, 1, 16, piece=65536, stages=3)
         for row in (128, 256, 512, 1024, 4096):
-            run("push", pattern, 2, 16, piece=32768, stages=6, row=row, stride=8192 if row <= 8192 else row)
-            run("push", pattern, 2, 32, piece=32768, stages=6, row=row, stride=8192 if row <= 8192 else row)
+            run("push", pattern, 2, 16, piece=32768, stages=6, row=row, stride=2 * row)
+            run("push", pattern, 2, 32, piece=32768, stages=6, row=row, stride=2 * row)
     if mc_dst:
         # one multicast store reaches every rank's dst: per-GPU egress = bytes, ingress = world x bytes
         for ctas in (8, 16, 32, 64):

@@ -9,7 +9,7 @@ out=gpurun_out/sanitize; mkdir -p $out
 tools=${@:-memcheck synccheck}
 for t in $tools; do
   timeout 1500 compute-sanitizer --tool $t --error-exitcode 3 --launch-timeout 120 \
-    python -m pytest tests/test_ops_gpu.py tests/test_gemm_gpu.py tests/test_attention_gpu.py -m gpu -x -q -k "not 4096 and not large" \
+    python -m pytest tests/test_ops_gpu.py tests/test_fused_loopback_gpu.py -m gpu -q -k "not 4096 and not 2048 and not world8 and not 8-256" \
     > $out/$t.log 2>&1
   echo "$t: exit $? ($(grep -c 'ERROR SUMMARY' $out/$t.log) summaries; $(grep -h 'ERROR SUMMARY' $out/$t.log | tail -1))"
 done
