@@ -98,6 +98,78 @@ __global__ void __launch_bounds__(512) dp_reduce_kernel(const DpArgs a) {
   }
 }
 
+// NVLS variant: the bucket is mapped through an NVSwitch multicast object.  ``multimem.ld_reduce`` returns the SUM of the
+// element over every rank's copy -- the addition happens inside the switch, so a rank pulls 1 x its slice instead of
+// (world - 1) x -- and ``multimem.st`` writes the scaled result into every rank's copy at once (all-reduce form).
+struct DpNvlsArgs {
+  float* mc;                 // multicast address of the bucket start
+  float* local;              // this rank's unicast address of the bucket start
+  int* pad_peer[GEMM_MAX_PEERS];
+  int* pad_local;
+  long long n;
+  int rank, world, epoch;
+  float scale;
+  int reduce_scatter;
+};
+
+__global__ void __launch_bounds__(512) dp_reduce_nvls_kernel(const DpNvlsArgs a) {
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      for (int p = 0; p < a.world; ++p)
+        if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_READY + a.rank, a.epoch);
+    }
+    for (int p = 0; p < a.world; ++p)
+      if (p != a.rank) dp_spin_until_ge(a.pad_local + DP_READY + p, a.epoch, a.pad_local);
+  }
+  __syncthreads();
+  const long long slice = a.n / a.world;
+  const long long begin = slice * a.rank;
+  const long long nvec = slice / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr int U = 4;       // independent 16-byte in-switch reductions in flight per thread
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < nvec; i0 += U * stride) {
+    float4 v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < nvec)
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                     : "l"(a.mc + begin + i * 4)
+                     : "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= nvec) continue;
+      const float4 o = make_float4(v[u].x * a.scale, v[u].y * a.scale, v[u].z * a.scale, v[u].w * a.scale);
+      if (a.reduce_scatter) {
+        *reinterpret_cast<float4*>(a.local + begin + i * 4) = o;
+      } else {
+        asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a.mc + begin + i * 4),
+                     "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w)
+                     : "memory");
+      }
+    }
+  }
+  __shared__ int s_last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    s_last = (atomicAdd(a.pad_local + DP_CTA_COUNTER, 1) == (int)gridDim.x - 1);
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    a.pad_local[DP_CTA_COUNTER] = 0;
+    __threadfence_system();
+    for (int p = 0; p < a.world; ++p)
+      if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_DONE + a.rank, a.epoch);
+    for (int p = 0; p < a.world; ++p)
+      if (p != a.rank) dp_spin_until_ge(a.pad_local + DP_DONE + p, a.epoch, a.pad_local);
+  }
+}
+
 }  // namespace mlb
 
 // dst1[i] = dst2[i] = src[i] (16-byte vectors): publishes a shard to the symmetric buffer and places it into the local
@@ -156,6 +228,20 @@ extern "C" int mlb_peer_barrier(int* pad_local, const long long* pad_peer_ptrs, 
   for (int i = 0; i < world; ++i) a.pad_peer[i] = reinterpret_cast<int*>(pad_peer_ptrs[i]);
   a.pad_local = pad_local; a.rank = rank; a.world = world; a.epoch = epoch;
   peer_barrier_kernel<<<1, 1, 0, st>>>(pad_local, a, slot);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int mlb_dp_reduce_nvls(int reduce_scatter, float* local, float* mc, int* pad_local,
+                                  const long long* pad_peer_ptrs, long long n, int rank, int world, int epoch,
+                                  float scale, int num_ctas, cudaStream_t st) {
+  using namespace mlb;
+  if (world > GEMM_MAX_PEERS || n % (world * 4) != 0) return -2;
+  DpNvlsArgs a;
+  memset(&a, 0, sizeof(a));
+  for (int i = 0; i < world; ++i) a.pad_peer[i] = reinterpret_cast<int*>(pad_peer_ptrs[i]);
+  a.mc = mc; a.local = local; a.pad_local = pad_local;
+  a.n = n; a.rank = rank; a.world = world; a.epoch = epoch; a.scale = scale; a.reduce_scatter = reduce_scatter;
+  dp_reduce_nvls_kernel<<<num_ctas > 0 ? num_ctas : 16, 512, 0, st>>>(a);
   return (int)cudaGetLastError();
 }
 

@@ -26,6 +26,8 @@ int mlb_gemm_bf16_2cta_rs(const void* A, const void* B, int M, int N, int K, int
                           mlb::GemmComm* comm, int prev_total, int num_sms, cudaStream_t stream);
 int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
                         int ldc, int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+int mlb_dp_reduce_nvls(int reduce_scatter, float* local, float* mc, int* pad_local, const long long* pad_peer_ptrs,
+                       long long n, int rank, int world, int epoch, float scale, int num_ctas, cudaStream_t st);
 int mlb_peer_barrier(int* pad_local, const long long* pad_peer_ptrs, int rank, int world, int epoch, int slot,
                      cudaStream_t st);
 int mlb_dp_reduce(int reduce_scatter, float* local, const long long* peer_ptrs, int* pad_local,
@@ -64,6 +66,8 @@ static void fill_pads(mlb::GemmComm& c, int64_t pad_local, const std::vector<int
 // the B traffic; but its first tiles need all of its rows, so it should not reach past the rows that are available
 // first (one rank's shard) unless B is too large to be re-read from L2 for every shard.
 static int pick_group_blocks(int64_t rows_per_rank, int64_t b_bytes) {
+  static const char* forced = getenv("MLB200_FUSED_GROUP");      // (tuning aid)
+  if (forced) return atoi(forced);
   const int per_rank = (int)(rows_per_rank / 256);
   if (b_bytes > (24LL << 20) || per_rank >= 4) return 4;
   return per_rank >= 2 ? 2 : 1;
@@ -193,6 +197,19 @@ static void dp_reduce(torch::Tensor& local, const std::vector<int64_t>& peer_ptr
                     local.numel(), (int)rank, (int)world, (int)epoch, (float)scale, (int)num_ctas, cur()));
 }
 
+// NVLS form of dp_reduce: ``mc_ptr`` = multicast address of ``local`` (in-switch fp32 reduction, multicast write-back)
+static void dp_reduce_nvls(torch::Tensor& local, int64_t mc_ptr, int64_t pad_local, const std::vector<int64_t>& pad_peers,
+                           int64_t rank, int64_t world, int64_t epoch, double scale, bool reduce_scatter,
+                           int64_t num_ctas) {
+  c10::cuda::CUDAGuard guard(local.device());
+  TORCH_CHECK(local.scalar_type() == torch::kFloat32 && local.is_contiguous() && mc_ptr != 0 && mc_ptr % 16 == 0);
+  long long pads[mlb::GEMM_MAX_PEERS] = {0};
+  for (int i = 0; i < world; ++i) pads[i] = pad_peers[i];
+  CHK(mlb_dp_reduce_nvls(reduce_scatter, local.data_ptr<float>(), reinterpret_cast<float*>(mc_ptr),
+                         reinterpret_cast<int*>(pad_local), pads, local.numel(), (int)rank, (int)world, (int)epoch,
+                         (float)scale, (int)num_ctas, cur()));
+}
+
 // all ranks of the group meet on the current stream (flags in pad slots [slot, slot + world))
 static void peer_barrier(int64_t pad_local, const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world,
                          int64_t epoch, int64_t slot) {
@@ -238,4 +255,5 @@ void register_comm(pybind11::module_& m) {
   m.def("fused_gemm_rs", &fused_gemm_rs);
   m.def("dp_reduce", &dp_reduce);
   m.def("peer_barrier", &peer_barrier);
+  m.def("dp_reduce_nvls", &dp_reduce_nvls);
 }

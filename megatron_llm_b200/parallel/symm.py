@@ -148,6 +148,9 @@ class TPCommunicator:
             return bufs[self.rank], [int(t.data_ptr()) for t in bufs]
         t, hdl = _alloc_symmetric(numel, dtype, self.device, self.group)
         self._handles = getattr(self, "_handles", []) + [hdl]       # keep the peer mappings alive
+        # NVSwitch multicast address of the same allocation (0 when the platform has no NVLS)
+        self._mc = getattr(self, "_mc", {})
+        self._mc[name] = int(getattr(hdl, "multicast_ptr", 0) or 0)
         return t, [int(p) for p in hdl.buffer_ptrs]
 
     @classmethod
@@ -314,6 +317,10 @@ class DPCommunicator:
         self.pad.zero_()
         self.epoch = 0
         self.stream = torch.cuda.Stream(priority=-1)
+        # NVLS: reduce inside the switch (multimem.ld_reduce) and write back by multicast when the grad buffer has a
+        # multicast mapping; MLB200_DP_NVLS=0 keeps the peer-pointer kernel
+        self.buf_mc = getattr(self, "_mc", {}).get("dp_buffer", 0) if loopback is None else 0
+        self.use_nvls = self.buf_mc != 0 and os.environ.get("MLB200_DP_NVLS", "1") == "1"
         torch.cuda.synchronize()
         if loopback is None:
             dist.barrier(group=group)
@@ -357,9 +364,14 @@ class DPCommunicator:
         ev.record()                       # the bucket's last gradient was produced on the current stream
         with torch.cuda.stream(self.stream):
             self.stream.wait_event(ev)
-            peers = [p + 4 * start for p in self.buf_ptrs]
-            self.mod.dp_reduce(view, peers, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
-                               self.epoch, 1.0 / self.world, reduce_scatter, self.num_ctas)
+            if self.use_nvls:
+                self.mod.dp_reduce_nvls(view, self.buf_mc + 4 * start, self.pad_ptrs[self.rank], self.pad_ptrs,
+                                        self.rank, self.world, self.epoch, 1.0 / self.world, reduce_scatter,
+                                        self.num_ctas)
+            else:
+                peers = [p + 4 * start for p in self.buf_ptrs]
+                self.mod.dp_reduce(view, peers, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
+                                   self.epoch, 1.0 / self.world, reduce_scatter, self.num_ctas)
             done = torch.cuda.Event()
             done.record()
         _ext.count()

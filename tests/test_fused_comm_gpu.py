@@ -158,27 +158,44 @@ def test_fused_tp_kernels_replay_in_cuda_graph():
     run_distributed(_tp_kernels_in_graph, 2, backend="nccl")
 
 
-def _dp_reduce(rank, world):
+def _dp_reduce(rank, world, nvls):
+    os.environ["MLB200_DP_NVLS"] = "1" if nvls else "0"
     from megatron_llm_b200.parallel import state as ps
     from megatron_llm_b200.parallel.symm import DPCommunicator
     ps.initialize_model_parallel(1, 1)
     dev = torch.device("cuda", rank)
     n = 1 << 20
     comm = DPCommunicator(ps.get_data_parallel_group(), n)
-    for it in range(3):
+    if nvls and not comm.use_nvls:
+        ps.destroy_model_parallel()
+        return                               # no multicast mapping on this box: nothing to test
+    half = n // 2
+    for it in range(4):
+        reduce_scatter = it % 2 == 1
         torch.manual_seed(rank * 10 + it)
         g = torch.randn(n, device=dev)
         ref = g.clone()
         dist.all_reduce(ref, group=ps.get_data_parallel_group())
         ref /= world
         comm.buffer.copy_(g)
-        h = comm.reduce_bucket(comm.buffer[: n // 2], 0, n, reduce_scatter=False)
-        h2 = comm.reduce_bucket(comm.buffer[n // 2:], n // 2, n, reduce_scatter=False)
+        h = comm.reduce_bucket(comm.buffer[:half], 0, n, reduce_scatter=reduce_scatter)
+        h2 = comm.reduce_bucket(comm.buffer[half:], half, n, reduce_scatter=reduce_scatter)
         h.wait(); h2.wait()
         torch.cuda.synchronize()
-        assert torch.allclose(comm.buffer, ref, atol=1e-5), f"dp all-reduce it={it}"
+        if reduce_scatter:                   # rank r owns slice r of each bucket
+            sl = half // world
+            for base in (0, half):
+                a, b = base + rank * sl, base + (rank + 1) * sl
+                assert torch.allclose(comm.buffer[a:b], ref[a:b], atol=1e-5), f"dp reduce-scatter it={it}"
+        else:
+            assert torch.allclose(comm.buffer, ref, atol=1e-5), f"dp all-reduce it={it}"
+        dist.barrier()
+    assert comm.error_flag() == 0
     ps.destroy_model_parallel()
 
 
-def test_dp_peer_memory_allreduce():
-    run_distributed(_dp_reduce, 2, backend="nccl")
+@pytest.mark.parametrize("nvls", [False, True], ids=["peer_pointers", "nvls_multimem"])
+def test_dp_peer_memory_reduction(nvls):
+    """Bucket all-reduce / reduce-scatter fused with the 1/DP scale: peer-pointer kernel and the NVLS kernel
+    (multimem.ld_reduce in-switch sum + multimem.st write-back)."""
+    run_distributed(_dp_reduce, min(torch.cuda.device_count(), 4), nvls, backend="nccl")
