@@ -73,27 +73,27 @@ static int pick_group_blocks(int64_t rows_per_rank, int64_t b_bytes) {
   return per_rank >= 2 ? 2 : 1;
 }
 
-// Number of puller CTAs for all-gather -> GEMM.  Measured pairwise on B200 (profiles/nvlink_n2_r2.jsonl): a bulk-copy
-// puller CTA moves ~44 GB/s and the link saturates near 470 GB/s (16 CTAs) for 16 MB messages.  Every puller costs the
-// GEMM one SM, so small GEMMs behind a big gather want many pullers and big GEMMs few:
-// minimise  max(gemm(c), pull(c) + one tile group of gemm(c))  over even c <= max_ctas.
+// Number of puller CTAs for all-gather -> GEMM.  Measured on B200 (profiles/nvlink_n2_r2.jsonl): a bulk-copy puller CTA
+// moves ~44 GB/s alone and ~29 GB/s when 16 share the link, which saturates near 470 GB/s per direction for 16 MB
+// messages.  The GEMM consumes its own rows first (1/world of the time), then the remote rows in arrival order, so the
+// pullers must (a) sustain the consumption rate of the remote rows and (b) have the first tile group's chunks there
+// when the own rows are done; every puller costs the GEMM one SM.  The first version of this model minimised
+// max(gemm, pull + one group) with an optimistic per-puller rate and left no slack: at TP=2 the producers were blocked
+// ~70 us per call (exposed_tp_collective in bench.py).  Now: the rate requirement with 1.4x headroom, at least 4.
 static int pick_comm_ctas(int64_t M, int64_t N, int64_t K, int64_t rows_per_rank, int world, int max_ctas, int sms) {
   static const char* fixed = getenv("MLB200_AG_CTAS_FIXED");
   if (fixed) return std::min(max_ctas, atoi(fixed));
-  constexpr double PULL_GBPS = 40.0, LINK_GBPS = 470.0, GEMM_TFLOPS = 1350.0;
-  const double chunk_bytes = 128.0 * K * 2;
-  const int remote_chunks = (int)((world - 1) * rows_per_rank / 128);
-  const int groups = std::max<int>(1, (int)(M / 256 / pick_group_blocks(rows_per_rank, N * K * 2)));
-  int best = 2;
-  double best_t = 1e30;
-  for (int c = 2; c <= max_ctas; c += 2) {
-    const double gemm_us = 2.0 * M * N * K / (GEMM_TFLOPS * 1e6) * sms / (double)(sms - c) + 4.0;
-    const double rate = std::min(PULL_GBPS * c, LINK_GBPS) / c;                       // GB/s per puller
-    const double pull_us = ((remote_chunks + c - 1) / c) * chunk_bytes / (rate * 1e3);  // whole chunks per puller
-    const double t = std::max(gemm_us, pull_us + gemm_us / groups);
-    if (t < best_t * 0.995) { best_t = t; best = c; }
-  }
-  return best;
+  constexpr double PULL_GBPS = 28.0, GEMM_TFLOPS = 1350.0, HEADROOM = 1.4;
+  const double gemm_us = 2.0 * M * N * K / (GEMM_TFLOPS * 1e6) + 4.0;
+  const double remote_bytes = (double)(world - 1) * rows_per_rank * K * 2;
+  const double remote_window_us = gemm_us * (world - 1) / world;                       // time spent on remote rows
+  const double own_us = gemm_us / world;                                                // ... and before them
+  const double group_bytes = 256.0 * pick_group_blocks(rows_per_rank, N * K * 2) * K * 2;
+  const double need_gbps = std::max(remote_bytes / (remote_window_us * 1e3), group_bytes / (own_us * 1e3));
+  int c = (int)(need_gbps * HEADROOM / PULL_GBPS + 0.999);
+  c = (c + 1) & ~1;
+  (void)sms;
+  return std::max(4, std::min(c, max_ctas & ~1));
 }
 
 // out[M, N] = all_gather(shards)[M, K] @ W^T (b_mn=false, W [N, K]) or @ W (b_mn=true, W [K, N]).

@@ -116,21 +116,35 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
       wv.to_float(wf[it]);
     }
   }
+  // software pipeline over the rows of this CTA: the 16-byte loads of row r+1 (x, dy, dres) are in flight while row r
+  // goes through its block reductions, so a CTA always has a full row of requests outstanding (the single-row version
+  // was latency bound: ~2 TB/s, tools/profiling/ew_drive.py)
+  Vec<T> xa[NORM_BWD_MAXV], da[NORM_BWD_MAXV], ra[NORM_BWD_MAXV];
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int it = 0; it < NORM_BWD_MAXV; ++it) {
+      const int vi = threadIdx.x + it * blockDim.x;
+      if (vi < nvec) {
+        xa[it].load(x + (size_t)row * H + vi * 8);
+        da[it].load(dy + (size_t)row * H + vi * 8);
+        if constexpr (ADD_DRES) ra[it].load(dres + (size_t)row * H + vi * 8);
+      }
+    }
+  };
+  if ((int)blockIdx.x < rows) fetch(blockIdx.x);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const float rstd = rstd_in[row];
     const float mean = RMS ? 0.f : mean_in[row];
-    float g[NORM_BWD_MAXV][8], xh[NORM_BWD_MAXV][8];
+    float g[NORM_BWD_MAXV][8], xh[NORM_BWD_MAXV][8], rf[NORM_BWD_MAXV][8];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int it = 0; it < NORM_BWD_MAXV; ++it) {
       const int vi = threadIdx.x + it * blockDim.x;
       if (vi < nvec) {
-        Vec<T> a, d;
         float xf[8], df[8];
-        a.load(x + (size_t)row * H + vi * 8);
-        d.load(dy + (size_t)row * H + vi * 8);
-        a.to_float(xf);
-        d.to_float(df);
+        xa[it].to_float(xf);
+        da[it].to_float(df);
+        if constexpr (ADD_DRES) ra[it].to_float(rf[it]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[it][j] = (xf[j] - mean) * rstd;
@@ -142,6 +156,7 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
         }
       }
     }
+    if (row + (int)gridDim.x < rows) fetch(row + gridDim.x);      // next row's loads fly during the reductions
     const float c2 = block_reduce_sum(s2, scratch) / H;
     float c1 = 0.f;
     if constexpr (!RMS) c1 = block_reduce_sum(s1, scratch) / H;
@@ -151,14 +166,9 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
       if (vi < nvec) {
         float o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = rstd * (g[it][j] - c1 - xh[it][j] * c2);
-        if constexpr (ADD_DRES) {
-          Vec<T> r;
-          float rf[8];
-          r.load(dres + (size_t)row * H + vi * 8);
-          r.to_float(rf);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) o[j] += rf[j];
+        for (int j = 0; j < 8; ++j) {
+          o[j] = rstd * (g[it][j] - c1 - xh[it][j] * c2);
+          if constexpr (ADD_DRES) o[j] += rf[it][j];
         }
         Vec<T> ov;
         ov.from_float(o);
