@@ -19,7 +19,7 @@ def _tp_kernels(rank, world):
     torch.manual_seed(100 + rank)
     K, N = 512, 768
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), max_rows_per_rank=512, max_k=2048, max_n=2048,
-                          num_comm_ctas=4)
+                          num_comm_ctas=4, all_reduce_n=1024)
     group = ps.get_tensor_model_parallel_group()
     # m = 256 takes the 2-CTA (cta_group::2) kernels, m = 128 the 1-CTA ones; alternating them on one communicator
     # also checks that the arrival / epoch accounting is shared correctly between the two variants
@@ -52,6 +52,13 @@ def _tp_kernels(rank, world):
         dist.reduce_scatter_tensor(refs, part2, group=group)
         got2 = comm.gemm_rs(a, wt, True)
         assert (got2.float() - refs).abs().max() <= 3e-2 * refs.abs().max(), f"gemm_rs(T) it={it}"
+        # ---- GEMM -> all-reduce (non-sequence-parallel form)
+        full_sum = part.clone()
+        dist.all_reduce(full_sum, group=group)
+        got3 = comm.gemm_ar(a, w, False)
+        torch.cuda.synchronize()
+        assert got3.shape == (M, N)
+        assert (got3.float() - full_sum).abs().max() <= 3e-2 * full_sum.abs().max(), f"gemm_ar it={it}"
     assert comm.error_flag() == 0, "a spin-wait timed out"
     ps.destroy_model_parallel()
 

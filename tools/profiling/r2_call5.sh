@@ -18,3 +18,7 @@ MLB200_FUSED_TP=1 run mistral_tiny_tp2dp2_zero1_fusedtp --model mistral-tiny --t
 run falcon_tiny_tp2pp2 --model falcon-tiny --tp 2 --pp 2 --global_batch 16
 run llama_tiny_tp4_recompute --model llama2-tiny --recompute
 grep -l "Traceback" $O/*.err | head
+echo "== multi-GPU tests (fused TP kernels incl. all-reduce, DP kernels peer / NVLS, TP invariance 1/2/4)"
+MLB200_TEST_RECORD=$O/tp_invariance.json timeout 900 python -m pytest tests/test_fused_comm_gpu.py tests/test_tp_model_gpu.py -m gpu -q --timeout 600 > $O/pytest_multigpu.log 2>&1; echo "rc=$?"; tail -8 $O/pytest_multigpu.log; cat $O/tp_invariance.json 2>/dev/null; echo
+echo "== DP reduction kernels vs NCCL (1 GB fp32 bucket, 4 GPUs)"
+timeout 300 $TR --master-port 29561 tools/profiling/dp_bench.py 1024 > $O/dp_bench_n4.jsonl 2> $O/dp_bench.err; cat $O/dp_bench_n4.jsonl; tail -3 $O/dp_bench.err
