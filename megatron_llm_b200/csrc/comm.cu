@@ -116,8 +116,9 @@ __global__ void __launch_bounds__(512) dp_reduce_nvls_kernel(const DpNvlsArgs a)
   if (threadIdx.x == 0) {
     if (blockIdx.x == 0) {
       __threadfence_system();
-      for (int p = 0; p < a.world; ++p)
-        if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_READY + a.rank, a.epoch);
+#pragma unroll
+      for (int p = 0; p < GEMM_MAX_PEERS; ++p)
+        if (p < a.world && p != a.rank) st_release_sys(a.pad_peer[p] + DP_READY + a.rank, a.epoch);
     }
     for (int p = 0; p < a.world; ++p)
       if (p != a.rank) dp_spin_until_ge(a.pad_local + DP_READY + p, a.epoch, a.pad_local);
@@ -163,8 +164,9 @@ __global__ void __launch_bounds__(512) dp_reduce_nvls_kernel(const DpNvlsArgs a)
   if (s_last && threadIdx.x == 0) {
     a.pad_local[DP_CTA_COUNTER] = 0;
     __threadfence_system();
-    for (int p = 0; p < a.world; ++p)
-      if (p != a.rank) st_release_sys(a.pad_peer[p] + DP_DONE + a.rank, a.epoch);
+#pragma unroll
+    for (int p = 0; p < GEMM_MAX_PEERS; ++p)
+      if (p < a.world && p != a.rank) st_release_sys(a.pad_peer[p] + DP_DONE + a.rank, a.epoch);
     for (int p = 0; p < a.world; ++p)
       if (p != a.rank) dp_spin_until_ge(a.pad_local + DP_DONE + p, a.epoch, a.pad_local);
   }

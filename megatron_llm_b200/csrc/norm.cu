@@ -119,19 +119,24 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
   // software pipeline over the rows of this CTA: the 16-byte loads of row r+1 (x, dy, dres) are in flight while row r
   // goes through its block reductions, so a CTA always has a full row of requests outstanding (the single-row version
   // was latency bound: ~2 TB/s, tools/profiling/ew_drive.py)
+  // (the incoming residual gradient is prefetched too where the register budget allows: 16-bit RMSNorm, the hot case;
+  // the other instantiations load it at its use so that nothing spills under the 128-register cap of 512 threads)
+  constexpr bool PREFETCH_DRES = ADD_DRES && RMS && sizeof(T) == 2;
+  constexpr bool PREFETCH = sizeof(T) == 2;
   Vec<T> xa[NORM_BWD_MAXV], da[NORM_BWD_MAXV], ra[NORM_BWD_MAXV];
-  auto fetch = [&](int row) {
-#pragma unroll
-    for (int it = 0; it < NORM_BWD_MAXV; ++it) {
-      const int vi = threadIdx.x + it * blockDim.x;
-      if (vi < nvec) {
-        xa[it].load(x + (size_t)row * H + vi * 8);
-        da[it].load(dy + (size_t)row * H + vi * 8);
-        if constexpr (ADD_DRES) ra[it].load(dres + (size_t)row * H + vi * 8);
-      }
+  auto fetch_one = [&](int row, int it) {
+    const int vi = threadIdx.x + it * blockDim.x;
+    if (vi < nvec) {
+      xa[it].load(x + (size_t)row * H + vi * 8);
+      da[it].load(dy + (size_t)row * H + vi * 8);
+      if constexpr (PREFETCH_DRES) ra[it].load(dres + (size_t)row * H + vi * 8);
     }
   };
-  if ((int)blockIdx.x < rows) fetch(blockIdx.x);
+  auto fetch = [&](int row) {
+#pragma unroll
+    for (int it = 0; it < NORM_BWD_MAXV; ++it) fetch_one(row, it);
+  };
+  if (PREFETCH && (int)blockIdx.x < rows) fetch(blockIdx.x);
   for (int row = blockIdx.x; row < rows; row += gridDim.x) {
     const float rstd = rstd_in[row];
     const float mean = RMS ? 0.f : mean_in[row];
@@ -140,11 +145,12 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
 #pragma unroll
     for (int it = 0; it < NORM_BWD_MAXV; ++it) {
       const int vi = threadIdx.x + it * blockDim.x;
+      if constexpr (!PREFETCH) fetch_one(row, it);
       if (vi < nvec) {
         float xf[8], df[8];
         xa[it].to_float(xf);
         da[it].to_float(df);
-        if constexpr (ADD_DRES) ra[it].to_float(rf[it]);
+        if constexpr (PREFETCH_DRES) ra[it].to_float(rf[it]);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           xh[it][j] = (xf[j] - mean) * rstd;
@@ -156,7 +162,7 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
         }
       }
     }
-    if (row + (int)gridDim.x < rows) fetch(row + gridDim.x);      // next row's loads fly during the reductions
+    if (PREFETCH && row + (int)gridDim.x < rows) fetch(row + gridDim.x);   // next row's loads fly during the reductions
     const float c2 = block_reduce_sum(s2, scratch) / H;
     float c1 = 0.f;
     if constexpr (!RMS) c1 = block_reduce_sum(s1, scratch) / H;
@@ -165,6 +171,11 @@ norm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __re
       const int vi = threadIdx.x + it * blockDim.x;
       if (vi < nvec) {
         float o[8];
+        if constexpr (ADD_DRES && !PREFETCH_DRES) {
+          Vec<T> r;
+          r.load(dres + (size_t)row * H + vi * 8);
+          r.to_float(rf[it]);
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           o[j] = rstd * (g[it][j] - c1 - xh[it][j] * c2);

@@ -94,7 +94,9 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
       if (peers.n > 0) {
         Vec<TP16> o;
         o.from_float(pv);
-        for (int d = 0; d < peers.n; ++d) o.store(reinterpret_cast<TP16*>(peers.ptr[d]) + base);
+#pragma unroll
+        for (int d = 0; d < 8; ++d)          // (constant indices: the by-value table stays in the parameter bank)
+          if (d < peers.n) o.store(reinterpret_cast<TP16*>(peers.ptr[d]) + base);
       } else if (p16 != nullptr) {
         Vec<TP16> o;
         o.from_float(pv);
@@ -106,7 +108,9 @@ adamw_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __r
         if (base + j < n) {
           p[base + j] = pv[j]; m[base + j] = mv[j]; v[base + j] = vv[j];
           if (peers.n > 0) {
-            for (int d = 0; d < peers.n; ++d) reinterpret_cast<TP16*>(peers.ptr[d])[base + j] = from_f<TP16>(pv[j]);
+#pragma unroll
+            for (int d = 0; d < 8; ++d)
+              if (d < peers.n) reinterpret_cast<TP16*>(peers.ptr[d])[base + j] = from_f<TP16>(pv[j]);
           } else if (p16 != nullptr) {
             p16[base + j] = from_f<TP16>(pv[j]);
           }
