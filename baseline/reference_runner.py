@@ -4,7 +4,8 @@ same metric and config, and prints the same JSON line with ``"impl": "reference"
 
 None of this repo's models, kernels or engine are on that path.  The only shims are environmental:
   * ``apex`` is not installed      -> stub modules: FusedAdam/FusedSGD = torch.optim.AdamW(fused=True)/SGD,
-                                      amp_C.multi_tensor_l2norm/scale = torch._foreach_* ; run with
+                                      amp_C.multi_tensor_l2norm/scale = torch._foreach_* ; fused_layer_norm_cuda =
+                                      ATen native_layer_norm (fwd/bwd); run with
                                       ``--no_gradient_accumulation_fusion`` (apex wgrad extension absent)
   * nvFuser flags removed in torch -> ``set_jit_fusion_options`` is a no-op
   * no tokenizer / dataset files   -> synthetic tokenizer object + synthetic dataset via the data_provider hook
@@ -59,6 +60,21 @@ def _install_apex_stub():
                 d.mul_(scale)
             else:
                 d.copy_(s.to(d.dtype) * scale if scale != 1.0 else s)
+
+    # apex's ``fused_layer_norm_cuda`` extension (imported by the reference's MixedFusedLayerNorm: Falcon / GPT / BERT):
+    # same contract on ATen's native LayerNorm kernels
+    fln = types.ModuleType("fused_layer_norm_cuda")
+
+    def forward_affine(input_, normalized_shape, weight, bias, eps):
+        out, mean, rstd = torch.native_layer_norm(input_, list(normalized_shape), weight, bias, eps)
+        return out, mean, rstd
+
+    def backward_affine(grad_output, mean, invvar, input_, normalized_shape, weight, bias, eps):
+        return torch.ops.aten.native_layer_norm_backward(grad_output, input_, list(normalized_shape), mean, invvar,
+                                                         weight, bias, [True, True, True])
+
+    fln.forward_affine, fln.backward_affine = forward_affine, backward_affine
+    sys.modules["fused_layer_norm_cuda"] = fln
 
     optimizers.FusedAdam, optimizers.FusedSGD = FusedAdam, FusedSGD
     mta.multi_tensor_applier = multi_tensor_applier

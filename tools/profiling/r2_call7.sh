@@ -3,6 +3,10 @@
 mkdir -p gpurun_out/r2c7
 O=gpurun_out/r2c7
 export MASTER_ADDR=127.0.0.1
+echo "== bench N=1 (micro-batch graph on, pipelined norm backward)"
+timeout 400 python bench.py --gpus 1 --steps 3 --warmup 3 > $O/bench_n1.json 2> $O/bench_n1.err; echo "rc=$?"; tail -c 1600 $O/bench_n1.json
+echo "== elementwise kernels"
+timeout 200 python tools/profiling/ew_drive.py --time > $O/ew_times.jsonl 2> $O/ew_times.err; cat $O/ew_times.jsonl
 echo "== step breakdown (8 layers, torch profiler)"
 timeout 300 python tools/profiling/profile_step.py 8 $O/step_breakdown_8layers_r2.txt > /dev/null 2> $O/step_breakdown.err; head -30 $O/step_breakdown_8layers_r2.txt
 echo "== ncu captures"

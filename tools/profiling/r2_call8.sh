@@ -13,8 +13,12 @@ one() {  # name, timeout, impl, args...
 }
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/smi_before.txt 2>&1
 one llama7b_tp8          240 ours      --steps 4 --warmup 3
-one mistral7b_tp2dp4     240 ours      --model mistral-7b --tp 2 --dist_opt --steps 3 --warmup 3
-one falcon40b_tp4pp2     300 ours      --model falcon-40b --tp 4 --pp 2 --global_batch 16 --steps 2 --warmup 3 --no_e2e
+MLB200_FUSED_TP=1 one mistral7b_tp2dp4     240 ours      --model mistral-7b --tp 2 --dist_opt --steps 3 --warmup 3
+MLB200_FUSED_TP=1 one falcon40b_tp4pp2     300 ours      --model falcon-40b --tp 4 --pp 2 --global_batch 16 --steps 2 --warmup 3 --no_e2e
+if ! grep -q '"value"' $O/falcon40b_tp4pp2_ours.json; then
+  mv $O/falcon40b_tp4pp2_ours.err $O/falcon40b_tp4pp2_ours_fused_failed.err
+  MLB200_FUSED_TP=0 one falcon40b_tp4pp2   300 ours      --model falcon-40b --tp 4 --pp 2 --global_batch 16 --steps 2 --warmup 3 --no_e2e
+fi
 one llama70b_tp8_recomp  300 ours      --model llama2-70b --recompute --micro_batch 4 --steps 2 --warmup 3 --no_e2e
 one llama7b_tp8          300 reference --steps 4 --warmup 3
 one mistral7b_tp2dp4     300 reference --model mistral-7b --tp 2 --dist_opt --steps 3 --warmup 3
