@@ -298,7 +298,7 @@ class TPCommunicator:
 class DPCommunicator:
     """Peer-memory gradient reduction for one data-parallel group: the whole fp32 grad buffer is symmetric."""
 
-    def __init__(self, group, numel_padded: int, num_ctas: int = 32, loopback: Optional[LoopbackWorld] = None,
+    def __init__(self, group, numel_padded: int, num_ctas: int = 16, loopback: Optional[LoopbackWorld] = None,
                  loopback_rank: int = 0):
         self.group = group
         self.loopback = loopback
@@ -321,6 +321,11 @@ class DPCommunicator:
         # multicast mapping; MLB200_DP_NVLS=0 keeps the peer-pointer kernel
         self.buf_mc = getattr(self, "_mc", {}).get("dp_buffer", 0) if loopback is None else 0
         self.use_nvls = self.buf_mc != 0 and os.environ.get("MLB200_DP_NVLS", "1") == "1"
+        # measured on 4 x B200, 1 GB fp32 bucket (profiles/dp_reduce_n4_r2.jsonl): the NVLS kernel is link-bound with
+        # 16 CTAs (all-reduce 2.35 ms vs NCCL 2.57 ms); the peer-pointer kernel scales with its CTA count (16: 14.9 ms,
+        # 64: 4.0 ms) -- give it 64 when it has to be used
+        if loopback is None and not self.use_nvls:
+            self.num_ctas = max(self.num_ctas, 64)
         torch.cuda.synchronize()
         if loopback is None:
             dist.barrier(group=group)
