@@ -7,7 +7,8 @@ Parity target: megatron/data/indexed_dataset.py.  Both on-disk formats of the re
 * ``lazy`` / ``cached`` (``TNTIDX\\0\\0``): magic(8) | version u64=1 | dtype code u64 | element size u64 | n u64 |
   s u64 | doc_count u64 | dim_offsets i64[n+1] | data_offsets i64[n+1] | sizes i64[s] | doc_idx i64[doc_count]
 
-The implementation is organised around one ``_IndexHeader`` parser/writer per format and numpy memory maps.
+The class and function names, their order and the on-disk layout follow the reference (the formats are a compatibility
+contract with existing preprocessed corpora); reads go through numpy memory maps.
 """
 from __future__ import annotations
 
