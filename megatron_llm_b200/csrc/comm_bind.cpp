@@ -137,6 +137,46 @@ static void fused_ag_gemm(torch::Tensor& gathered, const torch::Tensor& weight, 
                           (int)weight.stride(0), (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
 }
 
+// NVLS form of the all-gather -> GEMM (2-CTA kernel only): `gathered` = this rank's symmetric gather buffer of the call's
+// parity viewed as [M, K]; the pusher CTAs multimem.st `x_shard` into everybody's buffer (`mc_dst`) and release the
+// chunk flags `flags[d]`; the GEMM reads A from `gathered`.  Returns false if the shape needs the pull kernel.
+static bool fused_ag_gemm_nvls(torch::Tensor& gathered, const torch::Tensor& x_shard, const torch::Tensor& weight,
+                               torch::Tensor& out, bool b_mn, int64_t mc_dst, const std::vector<int64_t>& flags,
+                               torch::Tensor& done_counter, int64_t rows_per_rank, int64_t pad_local,
+                               const std::vector<int64_t>& pad_peers, int64_t rank, int64_t world, int64_t epoch,
+                               int64_t num_push_ctas, int64_t sms, int64_t state_ptr, int64_t stats_ptr) {
+  c10::cuda::CUDAGuard guard(gathered.device());
+  const int M = gathered.size(0), K = gathered.size(1);
+  const int N = b_mn ? weight.size(1) : weight.size(0);
+  TORCH_CHECK(gathered.is_contiguous() && x_shard.is_contiguous() && out.stride(1) == 1 && weight.stride(1) == 1);
+  TORCH_CHECK(x_shard.size(0) == rows_per_rank && x_shard.size(1) == K && M == rows_per_rank * world);
+  TORCH_CHECK((uintptr_t)x_shard.data_ptr() % 16 == 0 && mc_dst % 16 == 0 && K % 8 == 0 && N % 8 == 0);
+  if (rows_per_rank % 256 != 0 || N < 256 || (out.stride(0) * 2) % 16 != 0 || num_push_ctas < 2 || (num_push_ctas & 1))
+    return false;
+  const int per_rank = (int)(rows_per_rank / 256);
+  const int G = per_rank % 4 == 0 ? 4 : (per_rank % 2 == 0 ? 2 : 1);      // whole tile groups per source rank
+  mlb::GemmComm c;
+  memset(&c, 0, sizeof(c));
+  c.rank = rank; c.world = world; c.epoch = epoch;
+  c.num_comm_ctas = (int)num_push_ctas;
+  c.m_group_blocks = G;
+  c.m_stripe = 1;
+  c.state = reinterpret_cast<const int*>(state_ptr);
+  c.stats = reinterpret_cast<unsigned long long*>(stats_ptr);
+  c.ag_nvls = 1;
+  c.ag_local_src = x_shard.data_ptr();
+  c.ag_mc_dst = reinterpret_cast<void*>(mc_dst);
+  for (int i = 0; i < world; ++i) c.ag_flag_peer[i] = reinterpret_cast<int*>(flags[i]);
+  c.ag_dst = gathered.data_ptr();
+  c.ag_rows_per_rank = rows_per_rank;
+  c.ag_row_bytes = K * 2;
+  c.ag_done_counter = done_counter.data_ptr<int>();
+  fill_pads(c, pad_local, pad_peers);
+  CHK(mlb_gemm_bf16_2cta_ag(gathered.data_ptr(), weight.data_ptr(), out.data_ptr(), M, N, K, K, (int)weight.stride(0),
+                            (int)out.stride(0), b_mn, &c, sms > 0 ? (int)sms : sm_count(), cur()));
+  return true;
+}
+
 // rs_out[M/world, N] = reduce_scatter(x[M, K] @ W^T or @ W) over the group; tiles travel through rs_dst[] (peer slots).
 // ``prev_total``: cumulative arrivals every source had delivered per destination before this call; returns the new
 // cumulative count (the tile granularity depends on the kernel variant that is chosen here).
@@ -252,6 +292,7 @@ void register_comm(pybind11::module_& m) {
   m.def("comm_copy2", &comm_copy2);
   m.def("comm_set_state", &comm_set_state);
   m.def("fused_ag_gemm", &fused_ag_gemm);
+  m.def("fused_ag_gemm_nvls", &fused_ag_gemm_nvls);
   m.def("fused_gemm_rs", &fused_gemm_rs);
   m.def("dp_reduce", &dp_reduce);
   m.def("peer_barrier", &peer_barrier);

@@ -121,6 +121,16 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const int per_group = G * num_n;
       int group = tile / per_group;
       const int in_group = tile - group * per_group;
+      if (p.comm.m_stripe) {
+        // NVLS all-gather: every source pushes its shard front to back at the same time, so the j-th tile group of ALL
+        // sources arrives together: visit (j, source) with the own rank's group first in every round
+        const int gpr = (num_m / G) / p.comm.world;          // tile groups per source rank
+        const int j = group / p.comm.world, s_idx = group - j * p.comm.world;
+        const int src = (p.comm.rank + s_idx) % p.comm.world;
+        m_blk = (src * gpr + j) * G + in_group % G;
+        n_blk = in_group / G;
+        return;
+      }
       if (p.comm.m_interleave) {          // rotated order is [remote groups | own groups]: take them alternately
         const int half = (num_m / G) >> 1;
         group = (group & 1) ? half + (group >> 1) : (group >> 1);
@@ -151,7 +161,11 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         const int m0 = m_blk * G2_BLOCK_M + cta_rank * G2_HALF;   // this CTA's rows of A
         const int n0 = n_blk * G2_BLOCK_N + cta_rank * G2_HALF;   // this CTA's half of B
         if constexpr (MODE == MODE_AG_GEMM) {
-          if (m0 / p.comm.ag_rows_per_rank != p.comm.rank) {   // (the own shard was placed before the launch)
+          if (p.comm.ag_nvls) {                                 // every chunk (the own rows too) arrives by multicast
+            ag_wait_ns += spin_until_ge_timed(p.comm.ag_flag_peer[p.comm.rank] + (m0 >> 7),
+                                              comm_epoch(p.comm, STATE_AG_EPOCH), p.comm.pad_local);
+            fence_proxy_async_global();
+          } else if (m0 / p.comm.ag_rows_per_rank != p.comm.rank) {   // (the own shard was placed before the launch)
             ag_wait_ns += spin_until_ge_timed(p.comm.ag_chunk_flags + (m0 >> 7), comm_epoch(p.comm, STATE_AG_EPOCH),
                                               p.comm.pad_local);
             fence_proxy_async_global();  // generic-proxy acquire -> async-proxy (TMA) reads
@@ -395,6 +409,10 @@ gemm_bf16_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   }
 
   if constexpr (MODE == MODE_GEMM_RS) rs_reduce_phase(p);
+  if constexpr (MODE == MODE_AG_GEMM) {
+    // (after the cluster barrier: every TMA load of this CTA has been consumed) tell the pushers of call e+2
+    if (p.comm.ag_nvls && threadIdx.x == 0) ag_nvls_finish(p.comm);
+  }
 }
 
 template <bool A_MN, bool B_MN, int EPI, int MODE = MODE_PLAIN>

@@ -84,7 +84,72 @@ __device__ __forceinline__ int comm_rs_expected(const GemmComm& c) {
   return c.rs_expected_total + (c.state ? *reinterpret_cast<const volatile int*>(c.state + STATE_RS_TOTAL) : 0);
 }
 
+// ------------------------------------------------------------------------------------------------
+// NVLS pusher CTA (all 256 threads): local 16-byte loads -> multimem.st into every rank's gather buffer; one flag per
+// 128-row chunk, released at every destination (unicast) after a system fence.  The buffer of this parity was last
+// read two calls ago: wait until every rank's GEMM of that call retired (PAD_AG_ACK).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void multimem_st_v4(void* mc_addr, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc_addr),
+               "f"(__uint_as_float(v.x)), "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)),
+               "f"(__uint_as_float(v.w))
+               : "memory");
+}
+
+// called by one thread of every CTA of the launch when it no longer reads the gather buffer
+static __device__ void ag_nvls_finish(const GemmComm& c) {
+  __threadfence();
+  if (atomicAdd(c.ag_done_counter, 1) + 1 != (int)gridDim.x) return;
+  *c.ag_done_counter = 0;
+  __threadfence_system();
+  const int epoch = comm_epoch(c, STATE_AG_EPOCH);
+  for (int d = 0; d < c.world; ++d)
+    if (d != c.rank) st_release_sys(c.pad_peer[d] + PAD_AG_ACK + c.rank, epoch);
+}
+
+static __device__ void ag_pusher_nvls(const GemmComm& c, int comm_id) {
+  const int epoch = comm_epoch(c, STATE_AG_EPOCH);
+  if (threadIdx.x == 0) {
+    for (int p = 0; p < c.world; ++p)
+      if (p != c.rank) spin_until_ge(c.pad_local + PAD_AG_ACK + p, epoch - 2, c.pad_local);
+  }
+  __syncthreads();
+  const int cpr = c.ag_rows_per_rank / GEMM_BLOCK_M;
+  const long long chunk_vec = (long long)GEMM_BLOCK_M * c.ag_row_bytes / 16;
+  constexpr int U = 8;
+  for (int chunk = comm_id; chunk < cpr; chunk += c.num_comm_ctas) {
+    const uint4* src = reinterpret_cast<const uint4*>(c.ag_local_src) + (long long)chunk * chunk_vec;
+    uint4* dst = reinterpret_cast<uint4*>(c.ag_mc_dst) + ((long long)c.rank * cpr + chunk) * chunk_vec;
+    for (long long i0 = threadIdx.x; i0 < chunk_vec; i0 += (long long)U * blockDim.x) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        if (i < chunk_vec) v[u] = __ldg(src + i);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + (long long)u * blockDim.x;
+        if (i < chunk_vec) multimem_st_v4(dst + i, v[u]);
+      }
+    }
+    __syncthreads();                       // every thread's stores of this chunk are issued ...
+    if (threadIdx.x == 0) {
+      __threadfence_system();              // ... and ordered before the flags at system scope
+      for (int k = 0; k < c.world; ++k) {
+        const int d = (c.rank + 1 + k) % c.world;                  // own flag last
+        st_release_sys(c.ag_flag_peer[d] + c.rank * cpr + chunk, epoch);
+      }
+    }
+  }
+  if (threadIdx.x == 0) ag_nvls_finish(c);
+}
+
 static __device__ void ag_puller(const GemmComm& c, uint8_t* smem, int comm_id) {
+  if (c.ag_nvls) {
+    ag_pusher_nvls(c, comm_id);
+    return;
+  }
   // one thread drives the whole copy pipeline (bulk copies are issued by a single thread anyway)
   if (threadIdx.x != 0) return;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AG_STAGES * AG_PIECE_BYTES);

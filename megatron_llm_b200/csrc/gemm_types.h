@@ -42,6 +42,15 @@ struct GemmComm {
   int ag_row_bytes;                    // K * 2
   int* ag_chunk_flags;                 // local, one per 128-row chunk of the gathered buffer: set to epoch
   int* ag_read_counters;               // local, [world]: puller CTAs done with peer p (for the ack)
+  // ---- NVLS all-gather (2-CTA kernel): the owner's pusher CTAs ``multimem.st`` their shard into the symmetric gather
+  //      buffer of every rank at once (egress 1x instead of (world-1)x pulled, posted writes, 4-8 SIMT CTAs instead of
+  //      16-32 bulk-copy pullers) and release one flag per 128-row chunk at every destination; A is read from that buffer
+  int ag_nvls;
+  int m_stripe;                        // tile groups visit the sources round-robin (chunks of ALL sources arrive together)
+  const void* ag_local_src;            // this rank's shard [rows_per_rank, K] (any local tensor)
+  void* ag_mc_dst;                     // multicast address of the gather buffer of this epoch parity
+  int* ag_flag_peer[GEMM_MAX_PEERS];   // rank d's chunk flags of this parity ([rank] = local): set to the epoch
+  int* ag_done_counter;                // local: CTAs of this launch done with the buffer (last one acks to the pushers)
   // ---- reduce-scatter side
   void* rs_dst[GEMM_MAX_PEERS];        // rs_dst[d]: my receive slot on rank d: [rows_per_rank, N] bf16
   const void* rs_slots;                // local receive buffer of this epoch parity: [world][rows_per_rank, N]

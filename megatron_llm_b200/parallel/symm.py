@@ -100,7 +100,8 @@ class TPCommunicator:
     """
 
     def __init__(self, group, max_rows_per_rank: int, max_k: int, max_n: int, num_comm_ctas: int = 8,
-                 loopback: Optional[LoopbackWorld] = None, loopback_rank: int = 0, all_reduce_n: int = 0):
+                 loopback: Optional[LoopbackWorld] = None, loopback_rank: int = 0, all_reduce_n: int = 0,
+                 nvls_ag_k: int = 0):
         self.group = group
         self.loopback = loopback
         if loopback is not None:
@@ -124,6 +125,20 @@ class TPCommunicator:
         if all_reduce_n > 0:
             self.ar, self.ar_ptrs = self._symmetric("ar", 2 * self.world * max_rows_per_rank * all_reduce_n,
                                                     torch.bfloat16)
+        # NVLS all-gather (MLB200_AG_NVLS=1): two parities of a multicast-mapped gather buffer [world * rows, nvls_ag_k]
+        # + per-chunk arrival flags; used by the 2-CTA fused kernel for operands with K <= nvls_ag_k
+        self.nvls_ag = False
+        self.ag_k = nvls_ag_k
+        if nvls_ag_k > 0 and loopback is None and os.environ.get("MLB200_AG_NVLS", "0") == "1":
+            chunks = max(self.world * max_rows_per_rank // 128, 1)
+            self.agbuf, self.agbuf_ptrs = self._symmetric("agbuf", 2 * self.world * max_rows_per_rank * nvls_ag_k,
+                                                          torch.bfloat16)
+            self.agflag, self.agflag_ptrs = self._symmetric("agflag", 2 * chunks, torch.int32)
+            self.agflag.zero_()
+            self.agbuf_mc = self._mc.get("agbuf", 0)
+            self.ag_done = torch.zeros(1, dtype=torch.int32, device=self.device)
+            self.push_ctas = int(os.environ.get("MLB200_AG_PUSH_CTAS", "8"))
+            self.nvls_ag = self.agbuf_mc != 0
         max_chunks = self.world * max_rows_per_rank // 128
         self.chunk_flags = torch.zeros(max(max_chunks, 1), dtype=torch.int32, device=self.device)
         self.read_counters = torch.zeros(8, dtype=torch.int32, device=self.device)   # pullers done per peer (self-resetting)
@@ -178,6 +193,10 @@ class TPCommunicator:
         m = x2d.size(0)
         N = weight.size(1) if transposed_weight else weight.size(0)
         assert m <= self.max_rows and K <= self.max_k and m % 128 == 0, (m, K, self.max_rows, self.max_k)
+        if self.nvls_ag and K <= self.ag_k and m % 256 == 0 and N >= 256:
+            res = self._ag_gemm_nvls(x2d, weight, transposed_weight, out, keep, lead, m, K, N)
+            if res is not None:
+                return res
         # publish my shard (stream-ordered before the kernel; the previous call's kernel only retired after every
         # peer had acknowledged reading the old content)
         gathered = torch.empty((self.world * m, K), dtype=torch.bfloat16, device=self.device)
@@ -198,6 +217,32 @@ class TPCommunicator:
                                self.read_counters, self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world,
                                self.ag_epoch, self.num_comm_ctas, self.sms, self._state_ptr(), self.stats.data_ptr())
         _ext.count()
+        return out, gathered.view(self.world * lead[0], *lead[1:], K)
+
+    def _ag_gemm_nvls(self, x2d, weight, transposed_weight, out, keep, lead, m, K, N):
+        """NVLS transport: pusher CTAs multicast this rank's shard into every rank's gather buffer (see
+        ``ag_pusher_nvls`` in csrc/gemm_sm100.cuh); ``gathered`` is a view of that buffer unless the caller keeps it."""
+        epoch = self.ag_epoch + 1
+        parity = epoch % 2
+        buf_elems = self.world * self.max_rows * self.ag_k           # one parity of the gather buffer
+        flag_ints = self.agflag.numel() // 2
+        view = self.agbuf[parity * buf_elems: parity * buf_elems + self.world * m * K].view(self.world * m, K)
+        mc_dst = self.agbuf_mc + 2 * parity * buf_elems
+        flags = [p + 4 * parity * flag_ints for p in self.agflag_ptrs]
+        if out is None:
+            out = torch.empty((self.world * m, N), dtype=torch.bfloat16, device=self.device)
+        x = x2d.contiguous()
+        if x.data_ptr() % 16:
+            x = x.clone()
+        w = weight if weight.stride(-1) == 1 else weight.contiguous()
+        ok = self.mod.fused_ag_gemm_nvls(view, x, w, out, transposed_weight, mc_dst, flags, self.ag_done, m,
+                                         self.pad_ptrs[self.rank], self.pad_ptrs, self.rank, self.world, epoch,
+                                         self.push_ctas, self.sms, self._state_ptr(), self.stats.data_ptr())
+        if not ok:
+            return None
+        self.ag_epoch = epoch
+        _ext.count()
+        gathered = view.clone() if keep else view
         return out, gathered.view(self.world * lead[0], *lead[1:], K)
 
     def gemm_rs(self, x2d: torch.Tensor, weight: torch.Tensor, transposed_weight: bool = False):
@@ -268,6 +313,8 @@ class TPCommunicator:
         handshake only needs monotonic epochs.)"""
         if (self.rs_epoch - before[1]) % 2:
             self.rs_epoch += 1
+        if self.nvls_ag and (self.ag_epoch - before[0]) % 2:     # (the NVLS gather buffer parity is frozen too)
+            self.ag_epoch += 1
         self.mod.comm_set_state(self.state, self.ag_epoch - before[0], self.rs_epoch - before[1],
                                 self.rs_arrived_total - before[2])
         self.ag_epoch += advance[0]
@@ -402,7 +449,8 @@ def bind_tp_communicator(args) -> Optional[TPCommunicator]:
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), rows, max_k, max_n,
                           num_comm_ctas=int(os.environ.get("MLB200_AG_CTAS", "32")),   # upper bound: picked per shape
                           # without sequence parallelism the Row forward / Column dgrad end in an all-reduce of [s*b, h]
-                          all_reduce_n=0 if args.sequence_parallel else args.hidden_size)
+                          all_reduce_n=0 if args.sequence_parallel else args.hidden_size,
+                          nvls_ag_k=args.hidden_size)       # every all-gathered operand has K = hidden size
     fused_tp.bind(comm)
     return comm
 

@@ -43,6 +43,7 @@ def test_bindings_accept_the_python_call_sites(ext):
     _accepts(ext.fused_ag_gemm, a, w, out, False, ptrs, 128, i32, i32, 0, ptrs, 0, 2, 1, 8, 0, 0, 0)
     _accepts(ext.fused_gemm_rs, a, w, out[:128], False, ptrs, 0, 128, 0, 4, i32, 0, ptrs, 0, 2, 1, 0, 0, [], 0)
     _accepts(ext.fused_gemm_rs, a, w, out[:128], False, ptrs, 0, 128, 0, 4, i32, 0, ptrs, 0, 2, 1, 0, 0, ptrs, 0)
+    _accepts(ext.fused_ag_gemm_nvls, a, a[:128], w, out, False, 0, ptrs, i32, 128, 0, ptrs, 0, 2, 1, 8, 0, 0, 0)
     _accepts(ext.comm_copy2, a, a.clone(), a.clone())
     _accepts(ext.comm_set_state, i32, 0, 0, 0)
     _accepts(ext.dp_reduce, torch.zeros(64), ptrs, 0, ptrs, 0, 2, 1, 0.5, False, 8)

@@ -19,7 +19,7 @@ def _tp_kernels(rank, world):
     torch.manual_seed(100 + rank)
     K, N = 512, 768
     comm = TPCommunicator(ps.get_tensor_model_parallel_group(), max_rows_per_rank=512, max_k=2048, max_n=2048,
-                          num_comm_ctas=4, all_reduce_n=1024)
+                          num_comm_ctas=4, all_reduce_n=1024, nvls_ag_k=2048)   # (NVLS gather only with MLB200_AG_NVLS=1)
     group = ps.get_tensor_model_parallel_group()
     # m = 256 takes the 2-CTA (cta_group::2) kernels, m = 128 the 1-CTA ones; alternating them on one communicator
     # also checks that the arrival / epoch accounting is shared correctly between the two variants
@@ -65,6 +65,27 @@ def _tp_kernels(rank, world):
 
 def test_fused_tp_kernels_match_nccl():
     run_distributed(_tp_kernels, 2, backend="nccl")
+
+
+def _tp_kernels_nvls(rank, world):
+    os.environ["MLB200_AG_NVLS"] = "1"       # read when the communicator is built
+    _tp_kernels(rank, world)
+
+
+def test_fused_tp_kernels_nvls_all_gather_match_nccl():
+    """Same checks with the NVLS transport of the all-gather (pusher CTAs multimem.st the shard into every rank's gather
+    buffer); m = 128 calls still take the pull kernel, so both transports alternate on one communicator.  (Falls back
+    to the pull kernel, i.e. repeats the test above, on a box without multicast support.)"""
+    run_distributed(_tp_kernels_nvls, min(torch.cuda.device_count(), 4), backend="nccl")
+
+
+def _tp_kernels_nvls_in_graph(rank, world):
+    os.environ["MLB200_AG_NVLS"] = "1"
+    _tp_kernels_in_graph(rank, world)
+
+
+def test_fused_tp_kernels_nvls_replay_in_cuda_graph():
+    run_distributed(_tp_kernels_nvls_in_graph, 2, backend="nccl")
 
 
 def _tp_kernels_with_skew(rank, world):
@@ -119,7 +140,7 @@ def _tp_kernels_in_graph(rank, world):
     dev = torch.device("cuda", rank)
     group = ps.get_tensor_model_parallel_group()
     m, K, N = 256, 512, 768
-    comm = TPCommunicator(group, max_rows_per_rank=512, max_k=2048, max_n=2048, num_comm_ctas=4)
+    comm = TPCommunicator(group, max_rows_per_rank=512, max_k=2048, max_n=2048, num_comm_ctas=4, nvls_ag_k=2048)
     torch.manual_seed(5)
     w = torch.randn(N, K, device=dev, dtype=torch.bfloat16) * 0.05
     x = torch.randn(m, K, device=dev, dtype=torch.bfloat16)
