@@ -243,8 +243,8 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
             total_input = saved_input
         grad_bias = g2d.sum(dim=0) if ctx.use_bias else None
 
-        if ctx.sequence_parallel and ctx.fused:
-            from . import fused_tp
+        from . import fused_tp
+        if ctx.sequence_parallel and ctx.fused and fused_tp.column_backward_fused():
             grad_input = fused_tp.gemm_rs(g2d, weight, transposed_weight=True).view(
                 grad_output.size(0) // ps.get_tensor_model_parallel_world_size(), *grad_output.shape[1:-1],
                 weight.size(1))
@@ -254,7 +254,6 @@ class LinearWithGradAccumulationAndAsyncCommunication(torch.autograd.Function):
                                  ctx.gradient_accumulation_fusion)
             return grad_input, grad_weight, grad_bias, None, None, None
 
-        from . import fused_tp
         if (ctx.async_grad_allreduce and ps.get_tensor_model_parallel_world_size() > 1 and weight.dtype == g2d.dtype
                 and fused_tp.active_all_reduce(g2d, weight.size(1))):
             # dX = all_reduce(dY @ W): one fused GEMM -> all-reduce kernel over peer memory (reference: cuBLAS GEMM +
