@@ -13,7 +13,7 @@ echo "== ncu captures"
 bash tools/profiling/ncu_kernels.sh $O 2>&1 | tail -25
 echo "== compute-sanitizer memcheck + synccheck (small cases)"
 out=$O/sanitize; mkdir -p $out
-for t in memcheck synccheck; do
+for t in memcheck; do
   timeout 700 compute-sanitizer --tool $t --error-exitcode 3 --launch-timeout 120 \
     python -m pytest tests/test_ops_gpu.py tests/test_fused_loopback_gpu.py -m gpu -q -x \
       -k "not 4096 and not 2048 and not 8192 and not world8 and not 8-256 and not fp16_operands and not norm_fwd_bwd" \
