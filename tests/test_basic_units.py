@@ -139,6 +139,10 @@ def test_bench_presets_build_valid_arguments(monkeypatch):
         (ns(model="falcon-40b", tp=4, pp=2, global_batch=16), 8, "tp4+sp+pp2", (4, 2, 1)),
         (ns(model="llama2-70b", recompute=True), 8, "tp8+sp+recompute", (8, 1, 1)),
     ]
+    assert [bench.resolve_micro_batch(ns(micro_batch=0), n) for n in (1, 2, 4, 8)] == [1, 2, 4, 8]
+    assert bench.resolve_micro_batch(ns(micro_batch=0, model="mistral-7b", tp=2, dist_opt=True), 8) == 2
+    assert bench.resolve_micro_batch(ns(micro_batch=0, model="falcon-40b", tp=4, pp=2, global_batch=16), 8) == 1
+    assert bench.resolve_micro_batch(ns(micro_batch=3), 8) == 3
     for a, gpus, name, layout in cases:
         assert bench.parallel_layout(a, gpus) == layout
         assert bench.parallelism_string(a, gpus) == name
@@ -152,5 +156,6 @@ def test_bench_presets_build_valid_arguments(monkeypatch):
             args = validate_args(args, {})
         assert args.tensor_model_parallel_size == layout[0] and args.pipeline_model_parallel_size == layout[1]
         assert args.data_parallel_size == layout[2]
-        assert bool(getattr(args, "cuda_graph_microbatch", False)) == (layout[0] > 1 and layout[0] == gpus
+        # the micro-batch graph is requested whenever one TP group spans the job (N = 1 included), no pipeline, no recompute
+        assert bool(getattr(args, "cuda_graph_microbatch", False)) == (layout[0] == gpus and layout[1] == 1
                                                                         and not a.recompute)
