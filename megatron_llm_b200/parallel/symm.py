@@ -313,7 +313,7 @@ class TPCommunicator:
         handshake only needs monotonic epochs.)"""
         if (self.rs_epoch - before[1]) % 2:
             self.rs_epoch += 1
-        if self.nvls_ag and (self.ag_epoch - before[0]) % 2:     # (the NVLS gather buffer parity is frozen too)
+        if getattr(self, "nvls_ag", False) and (self.ag_epoch - before[0]) % 2:     # (NVLS gather buffer parity: frozen too)
             self.ag_epoch += 1
         self.mod.comm_set_state(self.state, self.ag_epoch - before[0], self.rs_epoch - before[1],
                                 self.rs_arrived_total - before[2])

@@ -156,6 +156,6 @@ def test_bench_presets_build_valid_arguments(monkeypatch):
             args = validate_args(args, {})
         assert args.tensor_model_parallel_size == layout[0] and args.pipeline_model_parallel_size == layout[1]
         assert args.data_parallel_size == layout[2]
-        # the micro-batch graph is requested whenever one TP group spans the job (N = 1 included), no pipeline, no recompute
-        assert bool(getattr(args, "cuda_graph_microbatch", False)) == (layout[0] == gpus and layout[1] == 1
-                                                                        and not a.recompute)
+        # the micro-batch graph is requested when one TP group of > 1 GPUs spans the job, no pipeline, no recompute
+        assert bool(getattr(args, "cuda_graph_microbatch", False)) == (layout[0] > 1 and layout[0] == gpus
+                                                                        and layout[1] == 1 and not a.recompute)
