@@ -8,11 +8,13 @@ from __future__ import annotations
 import torch
 
 _COMM = None  # bound by parallel.symm.bind_tp_communicator()
+_PREFER = {}  # (kind, M, N, K) -> take the fused kernel?  (see prefer_fused)
 
 
 def bind(comm) -> None:
     global _COMM
     _COMM = comm
+    _PREFER.clear()          # the fused-vs-library decisions depend on the communicator (world size, transports)
 
 
 def communicator():
@@ -39,7 +41,6 @@ _R_FUSED = {2: 450.0, 4: 400.0, 8: 350.0}
 _R_FUSED_NVLS_AG = {2: 450.0, 4: 480.0, 8: 520.0}
 _R_NCCL = {2: 320.0, 4: 450.0, 8: 560.0}
 _GEMM_TFLOPS = 1700.0
-_PREFER = {}
 
 
 def prefer_fused(kind: str, M: int, N: int, K: int) -> bool:

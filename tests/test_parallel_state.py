@@ -105,3 +105,31 @@ def test_fused_tp_graph_replay_bookkeeping():
     comm.begin_replay(before, advance)
     a, b, c = comm.mod.calls[-1]
     assert b % 2 == 0 and (a, c) == (8, 672) and comm.rs_epoch == before[1] + b + 3
+
+
+def test_fused_vs_library_selector_follows_the_measured_rates():
+    """parallel/fused_tp.py::prefer_fused: at TP=2 the fused kernel on every layer shape of Llama-2-7B; at TP=8 (7 peers:
+    350 GB/s in-kernel vs 560 GB/s NCCL-NVLS, measured) only behind the large GEMMs -- the choices the per-pair table
+    profiles/fused_tp_n8_r2_graph_mb8.jsonl shows to be the faster ones; the NVLS gather flips the gather pairs back."""
+    from megatron_llm_b200.parallel import fused_tp
+
+    class Comm:
+        world, nvls_ag, enabled = 8, False, True
+    old = fused_tp.communicator()
+    try:
+        fused_tp.bind(Comm())
+        M = 32768                                             # micro-batch 8 x 4096 tokens
+        got = {name: fused_tp.prefer_fused(kind, M, n, k) for name, kind, n, k in [
+            ("qkv", "ag", 1536, 4096), ("mlp_up", "ag", 2752, 4096), ("attn_dense", "rs", 4096, 512),
+            ("dgrad_mlp_down", "ag", 1376, 4096), ("dgrad_attn_dense", "ag", 512, 4096)]}
+        assert got == {"qkv": False, "mlp_up": True, "attn_dense": False, "dgrad_mlp_down": False,
+                       "dgrad_attn_dense": False}
+        Comm.nvls_ag = True
+        fused_tp.bind(Comm())                                 # (re-binding clears the decision cache)
+        assert all(fused_tp.prefer_fused("ag", M, n, 4096) for n in (1536, 2752, 1376, 512))
+        Comm.world, Comm.nvls_ag = 2, False
+        fused_tp.bind(Comm())
+        assert all(fused_tp.prefer_fused(kind, 8192, n, k) for kind, n, k in [
+            ("ag", 6144, 4096), ("ag", 11008, 4096), ("rs", 4096, 2048), ("rs", 4096, 5504), ("ag", 2048, 4096)])
+    finally:
+        fused_tp.bind(old)

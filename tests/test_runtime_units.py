@@ -448,3 +448,41 @@ def test_local_ddp_flat_buffers_buckets_and_accumulation():
     finally:
         ps.destroy_model_parallel()
         dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------------- DDP bucket layout
+def test_ddp_lays_deferred_params_out_last_and_never_reduces_them_from_the_hooks():
+    """parallel/ddp.py: sequence-parallel params and embedding tables (further gradient contributions / reductions after
+    their own backward) live in trailing buckets marked ``deferred``; only the other buckets may be launched from the
+    gradient-ready hooks."""
+    import torch
+    from megatron_llm_b200.parallel.ddp import DistributedDataParallel
+
+    class M(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.emb = torch.nn.Embedding(16, 8)
+            self.l1 = torch.nn.Linear(8, 8, bias=False)
+            self.norm_w = torch.nn.Parameter(torch.ones(8))
+            self.norm_w.sequence_parallel = True
+            self.l2 = torch.nn.Linear(8, 8, bias=False)
+
+        def forward(self, ids):
+            return self.l2(self.l1(self.emb(ids)) * self.norm_w)
+
+    ddp = DistributedDataParallel(M(), accumulate_allreduce_grads_in_fp32=True, bucket_size_mb=1)
+    buckets = ddp.buckets()[torch.float32]
+    deferred = [p for b in buckets if b.deferred for p in b.params]
+    early = [p for b in buckets if not b.deferred for p in b.params]
+    m = ddp.module
+    assert {id(p) for p in deferred} == {id(m.emb.weight), id(m.norm_w)}
+    assert {id(p) for p in early} == {id(m.l1.weight), id(m.l2.weight)}
+    assert max(b.end for b in buckets if not b.deferred) <= min(b.start for b in buckets if b.deferred)
+    # with grad sync enabled a complete early bucket is "launched" (DP world 1: marked only), a deferred one is not
+    ddp._dp_world = 2                       # pretend: exercise the bookkeeping without a process group
+    launched = []
+    ddp._launch_bucket = lambda gdt, b, async_op: (launched.append(b.index), setattr(b, "launched", True))
+    ddp.enable_grad_sync(True)
+    for p in m.parameters():
+        ddp._on_param_ready(p)
+    assert launched == [b.index for b in buckets if not b.deferred]
