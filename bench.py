@@ -312,7 +312,28 @@ def run_ours(a):
         sampler.start()
     tp_comm = fused_tp.communicator() if _fused_tp_active() else None
     exposed0 = tp_comm.exposed_ms() if tp_comm is not None else None
+    # exposed DP-reduction / PP-p2p time (CUDA events on the compute stream; BASELINE configs 3 and 4)
+    from megatron_llm_b200.parallel import p2p
+    tp_, pp_, dp_ = parallel_layout(a, a.gpus)
+    if pp_ > 1:
+        p2p.enable_accounting(True)
+    if dp_ > 1:
+        for m in model:
+            m.account_exposed = True
+            m.exposed_reduce_ms()
     ms_dev, launches, _ = timed(it_dev, a.steps, read_loss=False)
+    exposed_dp = exposed_pp = None
+    if dp_ > 1:
+        t = torch.tensor([sum(m.exposed_reduce_ms() for m in model) / a.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exposed_dp = round(t.item(), 3)
+        for m in model:
+            m.account_exposed = False
+    if pp_ > 1:
+        t = torch.tensor([p2p.exposed_recv_ms() / a.steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        exposed_pp = round(t.item(), 3)
+        p2p.enable_accounting(False)
     exposed = None
     if tp_comm is not None:
         # device-side %globaltimer accounting of the fused kernels: time their GEMM tiles could not hide
@@ -351,6 +372,7 @@ def run_ours(a):
                                        else "nccl"),
                            "peak_mem_gb": round(peak_gb, 2)},
                "exposed_tp_collective_ms_per_step": exposed,
+               "exposed_dp_reduce_ms_per_step": exposed_dp, "exposed_pp_p2p_ms_per_step": exposed_pp,
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
                "host_enqueue_ms_per_step": host_enqueue_ms}
         print(json.dumps(out), flush=True)

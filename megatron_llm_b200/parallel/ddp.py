@@ -283,8 +283,31 @@ class DistributedDataParallel(DistributedDataParallelBase):
         for param in self.module.parameters():
             dist.broadcast(param.data, src=ps.get_data_parallel_src_rank(), group=ps.get_data_parallel_group())
 
+    def exposed_reduce_ms(self, reset: bool = True) -> float:
+        """Device time the compute stream spent in :meth:`allreduce_gradients` since the last reset (launching the
+        deferred buckets and waiting for every bucket): the part of the DP reduction that backward did not hide."""
+        pairs = getattr(self, "_exposed_pairs", [])
+        if not pairs:
+            return 0.0
+        torch.cuda.synchronize()
+        total = sum(a.elapsed_time(b) for a, b in pairs)
+        if reset:
+            self._exposed_pairs = []
+        return total
+
     def allreduce_gradients(self):
         """Finish the data-parallel reduction: launch whatever was not overlapped, then wait."""
+        account = getattr(self, "account_exposed", False) and self._dp_world > 1 and torch.cuda.is_available()
+        if account:
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
+        self._finish_reduction()
+        if account:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()
+            self._exposed_pairs = getattr(self, "_exposed_pairs", []) + [(ev0, ev1)]
+
+    def _finish_reduction(self):
         if self._dp_world > 1:
             for gdt, buckets in self._buckets.items():
                 for b in buckets:

@@ -26,6 +26,27 @@ Shape = Union[List[int], torch.Size]
 
 _PENDING_SENDS = []  # (requests, tensors kept alive)
 
+# Exposed pipeline-p2p accounting (bench.py: ``exposed_pp_p2p_ms_per_step``): the compute stream waits for every
+# receive right where it is posted, so the device time between "posted" and "received" is time this stage did nothing
+# else -- pipeline bubble + transfer.  CUDA-event pairs, summed on request (one sync), off by default.
+_ACCOUNT = {"on": False, "pairs": []}
+
+
+def enable_accounting(flag: bool = True) -> None:
+    _ACCOUNT["on"] = bool(flag) and torch.cuda.is_available()
+    _ACCOUNT["pairs"] = []
+
+
+def exposed_recv_ms(reset: bool = True) -> float:
+    """Sum over the receives since the last reset of (receive complete - receive posted) on the compute stream, ms."""
+    if not _ACCOUNT["pairs"]:
+        return 0.0
+    torch.cuda.synchronize()
+    total = sum(a.elapsed_time(b) for a, b in _ACCOUNT["pairs"])
+    if reset:
+        _ACCOUNT["pairs"] = []
+    return total
+
 
 def _args():
     from ..global_vars import get_args
@@ -132,6 +153,10 @@ def _communicate(tensor_send_next: Optional[torch.Tensor], tensor_send_prev: Opt
         ops.append(dist.P2POp(dist.irecv, tensor_recv_next, ps.get_pipeline_model_parallel_next_rank()))
         kinds.append("r")
     if ops:
+        ev0 = None
+        if _ACCOUNT["on"] and "r" in kinds and dev.type == "cuda":
+            ev0 = torch.cuda.Event(enable_timing=True)
+            ev0.record()
         reqs = dist.batch_isend_irecv(ops)
         if len(reqs) == len(ops) and "r" in kinds and "s" in kinds:
             # per-op requests: wait receives now, retire sends lazily
@@ -145,6 +170,10 @@ def _communicate(tensor_send_next: Optional[torch.Tensor], tensor_send_prev: Opt
                 r.wait()
         else:
             _PENDING_SENDS.append((reqs, [o.tensor for o in ops]))
+        if ev0 is not None:
+            ev1 = torch.cuda.Event(enable_timing=True)
+            ev1.record()                       # (after the receives' stream-waits)
+            _ACCOUNT["pairs"].append((ev0, ev1))
         if len(_PENDING_SENDS) > 8:
             drain_pending_sends()
 
