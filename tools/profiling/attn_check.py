@@ -65,5 +65,5 @@ def run(b, s, nq, nkv, window, timing, hn=128):
 args = sys.argv[1:]
 hn = int(args[6]) if len(args) > 6 else 128
 if hn == 64:
-    os.environ["MLB200_ATTN_HD64"] = "1"      # the head_dim-64 instantiations are opt-in until validated
+    os.environ["MLB200_ATTN_HD64"] = "1"      # (default since round 2)
 run(int(args[0]), int(args[1]), int(args[2]), int(args[3]), None if args[4] == "none" else int(args[4]), args[5] == "t", hn)

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Validation of the head_dim-64 attention instantiations (opt-in via MLB200_ATTN_HD64=1 until this passes on a B200):
+# Validation of the head_dim-64 attention instantiations (passed on a B200 in round 2; the kernels are on by default):
 # numerics of fwd / dQ / dK / dV vs the fp32 reference for MHA, GQA, MQA, sliding window, separate and packed QKV, and
 # timing vs the FA-2 library on the Falcon-7B / GPT shapes.  Each case in its own process under a timeout.
 mkdir -p gpurun_out; out=gpurun_out/attn_hd64_checks.jsonl; : > $out

@@ -1,4 +1,5 @@
 #!/bin/bash
+# (record of the first round-2 GPU session: the stream / push all-gather variants it measured were deleted afterwards)
 # round-2 call 1 (2 GPUs): NVLink instruction-path rates + the opt-in all-gather transports
 mkdir -p gpurun_out/r2c1
 export MASTER_ADDR=127.0.0.1
