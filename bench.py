@@ -226,6 +226,9 @@ def run_ours(a):
 
     argv, vocab = megatron_argv(a, a.gpus)
     argv += ["--tokenizer_type", "NullTokenizer", "--vocab_file", str(vocab), "--data_type", "synthetic"]
+    # a timed-out peer-memory handshake is fatal in training (symm.check_timeouts); here the flags are examined after
+    # the warm-up (fall back to the NCCL path and say so) and after the timed region (reported in `details`)
+    os.environ.setdefault("MLB200_TIMEOUT_FATAL", "0")
     devnull = open(os.devnull, "w")
     real_stdout = sys.stdout
     sys.stdout = devnull if rank == 0 else sys.stdout      # keep the JSON line the only rank-0 output
@@ -352,6 +355,11 @@ def run_ours(a):
         e2e = {"value": tokens / (ms_e2e / 1e3), "unit": "tokens/s",
                "h2d_bytes_per_step": a.global_batch * (a.seq + 1) * 8, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / a.steps, "last_loss": last_loss}
+    timed_out = False
+    if fused_tp.communicator() is not None and not fused_fallback:
+        err = torch.tensor([fused_tp.communicator().error_flag()], device=dev, dtype=torch.int32)
+        dist.all_reduce(err, op=dist.ReduceOp.MAX)
+        timed_out = bool(err.item())
     peak = torch.tensor([torch.cuda.max_memory_allocated() / 2 ** 30], device=dev)
     dist.all_reduce(peak, op=dist.ReduceOp.MAX)
     peak_gb = peak.item()
@@ -370,7 +378,8 @@ def run_ours(a):
                                        if _fused_tp_active() else
                                        "nccl (fused kernels disabled after a handshake timeout)" if fused_fallback
                                        else "nccl"),
-                           "peak_mem_gb": round(peak_gb, 2)},
+                           "peak_mem_gb": round(peak_gb, 2),
+                           "handshake_timeout_in_timed_region": timed_out},
                "exposed_tp_collective_ms_per_step": exposed,
                "exposed_dp_reduce_ms_per_step": exposed_dp, "exposed_pp_p2p_ms_per_step": exposed_pp,
                "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
