@@ -113,6 +113,28 @@ def test_layout_matches_baseline(baseline, tmp_path, name, world, tp, pp, extra)
     assert losses == pytest.approx(ref, rel=2e-4, abs=2e-4), (name, losses, ref)
 
 
+def test_tied_embeddings_pipeline_and_zero(tmp_path):
+    """Tied embeddings with PP=2 x DP=2 and ZeRO-1: the last stage owns a ``shared`` copy of the word embedding whose
+    gradient is all-reduced over the embedding group after backward -- its bucket must be a deferred one, and the
+    reduce-scatter must come after that all-reduce."""
+    tied = [("gpt" if a == "llama2" else a) for a in MODEL if a != "--no_tie_embed_logits"]
+
+    def run(world, more, out, save_first=False):
+        run_distributed(_train_worker, world, tied + more, str(out), 3, save_first, False)
+        with open(out) as f:
+            return json.load(f)
+    ref = run(1, ["--save", str(tmp_path / "ckpt")], tmp_path / "ref.json", True)
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from tools import checkpoint_util
+    load = tmp_path / "pp2"
+    checkpoint_util.main(["--model_type", "GPT", "--load_dir", str(tmp_path / "ckpt"), "--save_dir", str(load),
+                          "--target_tensor_parallel_size", "1", "--target_pipeline_parallel_size", "2",
+                          "--true_vocab_size", "64"])
+    got = run(4, ["--pipeline_model_parallel_size", "2", "--use_distributed_optimizer", "--load", str(load),
+                  "--finetune", "--no_load_optim", "--no_load_rng"], tmp_path / "pp2_dp2_zero.json")
+    assert got == pytest.approx(ref, rel=2e-4, abs=2e-4), (got, ref)
+
+
 @pytest.mark.parametrize("extra", [[], ["--use_distributed_optimizer"]], ids=["dp2", "dp2_distopt"])
 def test_tied_embeddings_data_parallel(tmp_path, extra):
     """Tied embedding + fused wgrad accumulation: the word-embedding weight gets the LM-head wgrad (GEMM epilogue,
