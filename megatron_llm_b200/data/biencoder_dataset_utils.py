@@ -101,8 +101,8 @@ def get_block_samples_mapping(block_dataset, title_dataset, data_prefix, num_epo
                                                use_one_sent_docs)
         np.save(fname, mapping, allow_pickle=True)
         print_rank_0(f" > saved the index mapping in {fname} ({time.time() - t0:4f} s)")
-    if dist.is_initialized():
-        dist.barrier()
+    from .dataset_utils import _sync_after_index_build
+    _sync_after_index_build()          # (not a world barrier: only TP-rank-0 ranks build datasets)
     mapping = np.load(fname, allow_pickle=True, mmap_mode="r")
     print_rank_0(f"    total number of samples: {mapping.shape[0]}")
     return BlockSamplesMapping(mapping)

@@ -229,10 +229,21 @@ def get_indexed_dataset_(data_prefix, data_impl, skip_warmup):
 
 
 def _sync_after_index_build():
-    """All ranks wait until rank 0 has written the index file (the reference all-reduces a counter over the DP and
-    PP groups for the same effect)."""
-    if dist.is_available() and dist.is_initialized():
+    """Every rank that builds datasets waits until rank 0 has written the index file.  Only the tensor-parallel rank 0
+    of every (DP, PP) coordinate calls the dataset providers (training.py broadcasts the result flags over TP), so a
+    world barrier would dead-lock under TP > 1: like the reference (dataset_utils.py:709-717) all-reduce a counter over
+    the data-parallel and the pipeline-parallel group, which together connect exactly those ranks."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return
+    from ..parallel import state as ps
+    from ..utils.device import current_device
+    if not ps.model_parallel_is_initialized():
         dist.barrier()
+        return
+    counts = torch.ones(1, dtype=torch.long, device=current_device())
+    dist.all_reduce(counts, group=ps.get_data_parallel_group())
+    dist.all_reduce(counts, group=ps.get_pipeline_model_parallel_group())
+    assert counts[0].item() == dist.get_world_size() // dist.get_world_size(group=ps.get_tensor_model_parallel_group())
 
 
 def _rank():

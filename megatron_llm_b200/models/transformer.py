@@ -446,6 +446,8 @@ class NoopTransformerLayer(MegatronModule):
 def _get_num_layers(args, is_encoder_and_decoder_model, is_decoder=False):
     """Number of layers owned by this pipeline rank."""
     pp = ps.get_pipeline_model_parallel_world_size()
+    # (the reference leaves decoder_num_layers unset when only --num_layers is given and then fails on it; default it)
+    dec_layers = args.decoder_num_layers if args.decoder_num_layers is not None else args.num_layers
     if pp > 1:
         if is_encoder_and_decoder_model:
             assert args.pipeline_model_parallel_split_rank is not None
@@ -453,12 +455,12 @@ def _get_num_layers(args, is_encoder_and_decoder_model, is_decoder=False):
                                     else args.pipeline_model_parallel_split_rank)
             num_ranks_in_decoder = args.transformer_pipeline_model_parallel_size - num_ranks_in_encoder
             assert args.encoder_num_layers % num_ranks_in_encoder == 0
-            assert args.decoder_num_layers % num_ranks_in_decoder == 0
+            assert dec_layers % num_ranks_in_decoder == 0
             if ps.is_pipeline_stage_before_split():
                 num_layers = (0 if args.standalone_embedding_stage and ps.get_pipeline_model_parallel_rank() == 0
                               else args.encoder_num_layers // num_ranks_in_encoder)
             else:
-                num_layers = args.decoder_num_layers // num_ranks_in_decoder
+                num_layers = dec_layers // num_ranks_in_decoder
         else:
             assert args.num_layers == args.encoder_num_layers
             assert args.num_layers % args.transformer_pipeline_model_parallel_size == 0, \
@@ -466,9 +468,7 @@ def _get_num_layers(args, is_encoder_and_decoder_model, is_decoder=False):
             num_layers = (0 if args.standalone_embedding_stage and ps.get_pipeline_model_parallel_rank() == 0
                           else args.num_layers // args.transformer_pipeline_model_parallel_size)
     else:
-        # (the reference leaves decoder_num_layers unset when only --num_layers is given; default it)
-        dec = args.decoder_num_layers if args.decoder_num_layers is not None else args.num_layers
-        num_layers = dec if is_decoder else args.encoder_num_layers
+        num_layers = dec_layers if is_decoder else args.encoder_num_layers
     return num_layers
 
 

@@ -38,6 +38,28 @@ def _run(script, argv, timeout=900):
     return r.stdout
 
 
+def _run_ranks(script, argv, world, timeout=600):
+    """``world`` CPU/gloo ranks of an entry point (what torchrun would start); returns rank 0's stdout."""
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, MLB200_FORCE_CPU="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r),
+                   WORLD_SIZE=str(world), LOCAL_RANK=str(r), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, script)] + argv, env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, cwd=ROOT))
+    outs = []
+    try:
+        for p in procs:
+            outs.append(p.communicate(timeout=timeout))
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, o[-2000:] + "\n" + e[-3000:]
+    return "".join(o for o, _ in outs)
+
+
 def _preprocess(tmp, keys=("text",), extra=()):
     vocab, corpus = _make_corpus(tmp)
     _run("tools/preprocess_data.py", ["--input", str(corpus), "--output_prefix", str(tmp / "data"), "--json_keys",
@@ -84,3 +106,28 @@ def test_pretrain_ict(tmp_path):
                                             "--query_in_block_prob", "0.1", "--retriever_report_topk_accuracies", "1",
                                             "2", "--use_one_sent_docs"])
     assert "top1_acc" in out and "iteration        2/" in out
+
+
+def test_pretrain_bert_tensor_parallel(tmp_path):
+    """BERT with TP=2 + sequence parallelism: only the TP-rank-0 of every (DP, PP) coordinate builds datasets, so the
+    wait for rank 0's index map must not be a world barrier (it once was: TP > 1 dead-locked in the dataset build)."""
+    vocab = _preprocess(tmp_path)
+    out = _run_ranks("pretrain_bert.py", COMMON + ["--seq_length", "48", "--max_position_embeddings", "48",
+                                                   "--vocab_file", str(vocab), "--data_path",
+                                                   str(tmp_path / "data_text_sentence"), "--make_vocab_size_divisible_by",
+                                                   "8", "--tensor_model_parallel_size", "2", "--sequence_parallel"], 2)
+    assert "lm loss" in out and "iteration        2/" in out
+
+
+def test_pretrain_t5_pipeline_parallel(tmp_path):
+    """T5 with the encoder on stage 0 and the decoder on stage 1 (``--pipeline_model_parallel_split_rank 1``);
+    ``--decoder_num_layers`` is left to default to ``--num_layers`` (the reference fails on the unset value)."""
+    vocab = _preprocess(tmp_path)
+    out = _run_ranks("pretrain_t5.py", COMMON + ["--encoder_seq_length", "48", "--decoder_seq_length", "32",
+                                                 "--max_position_embeddings", "48", "--vocab_file", str(vocab),
+                                                 "--vocab_extra_ids", "100", "--data_path",
+                                                 str(tmp_path / "data_text_sentence"), "--make_vocab_size_divisible_by",
+                                                 "8", "--kv_channels", "8", "--ffn_hidden_size", "64",
+                                                 "--pipeline_model_parallel_size", "2",
+                                                 "--pipeline_model_parallel_split_rank", "1"], 2)
+    assert "lm loss" in out and "iteration        2/" in out
