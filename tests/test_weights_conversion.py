@@ -138,3 +138,90 @@ def test_verify_correctness_script(tmp_path):
     lines = [l for l in r.stdout.splitlines() if l.startswith("Max absoulute error")]
     assert len(lines) == 10
     assert all(float(l.split("max=")[1].split(",")[0]) < 1e-3 for l in lines), lines
+
+
+def _load_falcon_and_forward(rank, world, path, tokens, ref):
+    from megatron_llm_b200.checkpointing import load_checkpoint
+    from megatron_llm_b200.initialize import initialize_megatron
+    from megatron_llm_b200.models import FalconModel
+    from megatron_llm_b200.models.enums import ModelType
+    initialize_megatron(args_list=["--load", path, "--use_checkpoint_args", "--micro_batch_size", "2",
+                                   "--tokenizer_type", "NullTokenizer", "--vocab_file", "128", "--no_load_optim",
+                                   "--no_load_rng", "--finetune", "--train_iters", "1", "--lr", "1e-4"])
+    model = FalconModel(num_tokentypes=0, parallel_output=False, pre_process=True, post_process=True,
+                        model_type=ModelType.encoder_or_decoder)
+    load_checkpoint([model], None, None)
+    model.eval()
+    pos = torch.arange(tokens.size(1)).unsqueeze(0).expand_as(tokens).contiguous()
+    mask = torch.tril(torch.ones(1, 1, tokens.size(1), tokens.size(1))) < 0.5
+    with torch.no_grad():
+        out = model(tokens, pos, mask).float()
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+@pytest.mark.parametrize("size,new_arch,heads,kv", [(40, True, 16, 8), (7, False, 4, 1)], ids=["falcon40b_style", "falcon7b_style"])
+def test_converted_falcon_matches_hf_logits(size, new_arch, heads, kv, tmp_path, monkeypatch):
+    """Falcon: parallel attention + MLP, tied embeddings, LayerNorm; 40B style = GQA with separate attention / MLP norms,
+    7B style = MQA with one norm.  A tiny random HF Falcon converted with ``falcon_to_megatron`` must give the same
+    logits in this repo's FalconModel (fp32, CPU)."""
+    import weights_conversion.hf_to_megatron as C
+    from transformers import FalconConfig, FalconForCausalLM
+    from tests.dist_utils import run_distributed
+    torch.manual_seed(0)
+    cfg = FalconConfig(vocab_size=128, hidden_size=128, num_hidden_layers=2, num_attention_heads=heads, num_kv_heads=kv,
+                       new_decoder_architecture=new_arch, multi_query=not new_arch, parallel_attn=True, bias=False,
+                       alibi=False, max_position_embeddings=64, tie_word_embeddings=True)
+    hf = FalconForCausalLM(cfg).float().eval()
+    monkeypatch.setitem(C.falcon_s2layer, size, 2)
+    monkeypatch.setitem(C.falcon_s2heads, size, heads)
+    monkeypatch.setitem(C.falcon_s2hidden, size, 128)
+    sd = dict(hf.state_dict())
+    sd.setdefault("lm_head.weight", sd["transformer.word_embeddings.weight"])
+    mw = C.falcon_to_megatron(sd, size)
+    a = C.architecture_args("falcon", size, vocab=128)
+    a.update(max_position_embeddings=64, seq_length=32, make_vocab_size_divisible_by=1, tokenizer_type="NullTokenizer")
+    C.save_megatron(tmp_path, mw, a, torch.float32)
+    tokens = torch.randint(0, 128, (2, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = hf(tokens).logits
+    run_distributed(_load_falcon_and_forward, 1, str(tmp_path), tokens, ref, backend="gloo")
+
+
+def _load_mistral_and_forward(rank, world, path, tokens, ref):
+    from megatron_llm_b200.checkpointing import load_checkpoint
+    from megatron_llm_b200.initialize import initialize_megatron
+    from megatron_llm_b200.models import MistralModel
+    from megatron_llm_b200.models.enums import ModelType
+    initialize_megatron(args_list=["--load", path, "--use_checkpoint_args", "--micro_batch_size", "2",
+                                   "--tokenizer_type", "NullTokenizer", "--vocab_file", "96", "--no_load_optim",
+                                   "--no_load_rng", "--finetune", "--train_iters", "1", "--lr", "1e-4",
+                                   "--use_flash_attn"])
+    model = MistralModel(num_tokentypes=0, parallel_output=False, pre_process=True, post_process=True,
+                         model_type=ModelType.encoder_or_decoder)
+    load_checkpoint([model], None, None)
+    model.eval()
+    pos = torch.arange(tokens.size(1)).unsqueeze(0).expand_as(tokens).contiguous()
+    mask = torch.tril(torch.ones(1, 1, tokens.size(1), tokens.size(1))) < 0.5
+    with torch.no_grad():
+        out = model(tokens, pos, mask).float()
+    assert torch.allclose(out, ref, atol=2e-4, rtol=1e-4), (out - ref).abs().max()
+
+
+def test_converted_mistral_matches_hf_logits(tmp_path):
+    """Mistral (GQA, sliding window 4096) through the HF -> Megatron converter and this repo's MistralModel."""
+    import weights_conversion.hf_to_megatron as C
+    from transformers import MistralConfig, MistralForCausalLM
+    from tests.dist_utils import run_distributed
+    torch.manual_seed(0)
+    cfg = MistralConfig(vocab_size=96, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                        num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64, sliding_window=4096,
+                        rms_norm_eps=1e-5, tie_word_embeddings=False, attn_implementation="eager")
+    hf = MistralForCausalLM(cfg).float().eval()
+    mw = C.llama_like_to_megatron(C.hf_llama_state_to_meta_names(dict(hf.state_dict())), 2, 64, 4, 2, "hf")
+    a = C.architecture_args("mistral", 7, 2, 64, 4, 2, 176, 96)
+    a.update(max_position_embeddings=64, seq_length=32)
+    C.save_megatron(tmp_path, mw, a, torch.float32)
+    tokens = torch.randint(0, 96, (2, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        ref = hf(tokens).logits
+    run_distributed(_load_mistral_and_forward, 1, str(tmp_path), tokens, ref, backend="gloo")
