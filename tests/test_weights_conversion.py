@@ -225,3 +225,44 @@ def test_converted_mistral_matches_hf_logits(tmp_path):
     with torch.no_grad():
         ref = hf(tokens).logits
     run_distributed(_load_mistral_and_forward, 1, str(tmp_path), tokens, ref, backend="gloo")
+
+
+@pytest.mark.parametrize("name", ["falcon40b_style", "falcon7b_style", "mistral"])
+def test_hf_megatron_hf_round_trip(name, tmp_path, monkeypatch):
+    """HF -> Megatron (hf_to_megatron) -> HF (megatron_to_hf.main, incl. the generated HF config) gives back a model with
+    bit-identical logits."""
+    import weights_conversion.hf_to_megatron as C
+    import weights_conversion.megatron_to_hf as R
+    from transformers import AutoModelForCausalLM, FalconConfig, FalconForCausalLM, MistralConfig, MistralForCausalLM
+    torch.manual_seed(0)
+    if name.startswith("falcon"):
+        size, new_arch, heads, kv = (40, True, 16, 8) if name == "falcon40b_style" else (7, False, 4, 1)
+        cfg = FalconConfig(vocab_size=128, hidden_size=128, num_hidden_layers=2, num_attention_heads=heads,
+                           num_kv_heads=kv, new_decoder_architecture=new_arch, multi_query=not new_arch,
+                           parallel_attn=True, bias=False, alibi=False, max_position_embeddings=64,
+                           tie_word_embeddings=True)
+        hf = FalconForCausalLM(cfg).float().eval()
+        monkeypatch.setitem(C.falcon_s2layer, size, 2)
+        monkeypatch.setitem(C.falcon_s2heads, size, heads)
+        monkeypatch.setitem(C.falcon_s2hidden, size, 128)
+        sd = dict(hf.state_dict())
+        sd.setdefault("lm_head.weight", sd["transformer.word_embeddings.weight"])
+        mw = C.falcon_to_megatron(sd, size)
+        a = C.architecture_args("falcon", size, vocab=128)
+        a.update(max_position_embeddings=64, seq_length=32, make_vocab_size_divisible_by=1)
+        model, vocab = "falcon", 128
+    else:
+        cfg = MistralConfig(vocab_size=96, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                            num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64,
+                            sliding_window=4096, rms_norm_eps=1e-5, tie_word_embeddings=False)
+        hf = MistralForCausalLM(cfg).float().eval()
+        mw = C.llama_like_to_megatron(C.hf_llama_state_to_meta_names(dict(hf.state_dict())), 2, 64, 4, 2, "hf")
+        a = C.architecture_args("mistral", 7, 2, 64, 4, 2, 176, 96)
+        a.update(max_position_embeddings=64, seq_length=32)
+        model, vocab = "mistral", 96
+    C.save_megatron(tmp_path / "meg", mw, a, torch.float32)
+    R.main(model, tmp_path / "meg", tmp_path / "hf", dtype=torch.float32)
+    back = AutoModelForCausalLM.from_pretrained(tmp_path / "hf").float().eval()
+    tokens = torch.randint(0, vocab, (2, 32), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert torch.equal(back(tokens).logits, hf(tokens).logits)
