@@ -177,10 +177,13 @@ class _NormFn(torch.autograd.Function):
         else:
             xin = xc if residual is None else (xc + residual)
             xf = xin.float()
+            # fp32 residual stream with half-precision parameters (--fp32_residual_connection): the normed
+            # activation feeds the GEMMs, so it takes the parameter dtype (apex's "mixed" norm does the same)
+            ydt = weight.dtype if (xc.dtype == torch.float32 and weight.dtype != torch.float32) else xc.dtype
             if rms:
                 mean = None
                 rstd = torch.rsqrt(xf.pow(2).mean(-1) + eps).reshape(-1)
-                y = (xf * rstd.view(*xf.shape[:-1], 1) * weight.float()).to(xc.dtype)
+                y = (xf * rstd.view(*xf.shape[:-1], 1) * weight.float()).to(ydt)
             else:
                 mean = xf.mean(-1).reshape(-1)
                 var = xf.var(-1, unbiased=False).reshape(-1)
@@ -188,7 +191,7 @@ class _NormFn(torch.autograd.Function):
                 y = ((xf - mean.view(*xf.shape[:-1], 1)) * rstd.view(*xf.shape[:-1], 1) * weight.float())
                 if bias is not None:
                     y = y + bias.float()
-                y = y.to(xc.dtype)
+                y = y.to(ydt)
             ctx.kernel = False
         ctx.save_for_backward(xin, weight, mean, rstd)
         if residual is not None:

@@ -152,6 +152,26 @@ def test_tied_embeddings_data_parallel(tmp_path, extra):
     assert got == pytest.approx(ref, rel=2e-4, abs=2e-4), (got, ref)
 
 
+def test_fp32_residual_connection_with_bf16_params(tmp_path):
+    """--fp32_residual_connection + --bf16: the residual stream (and the pipeline p2p tensors) are fp32, the norms hand
+    parameter-dtype activations to the GEMMs.  Must train, stay close to the plain bf16 run, and agree between PP=1 and
+    PP=2 (the p2p buffers take the fp32 dtype)."""
+    def run(world, more, out, save_first=False):
+        run_distributed(_train_worker, world, MODEL + ["--bf16"] + more, str(out), 3, save_first, False)
+        with open(out) as f:
+            return json.load(f)
+    plain = run(1, ["--save", str(tmp_path / "ckpt")], tmp_path / "plain.json", True)
+    load = ["--load", str(tmp_path / "ckpt"), "--finetune", "--no_load_optim", "--no_load_rng"]
+    fp32res = run(1, ["--fp32_residual_connection"] + load, tmp_path / "fp32res.json")
+    assert fp32res == pytest.approx(plain, rel=2e-2), (fp32res, plain)
+    assert fp32res != plain                                   # the flag does something
+    pp2 = tmp_path / "pp2"
+    _reshard(tmp_path / "ckpt", pp2, 1, 2)
+    got = run(2, ["--fp32_residual_connection", "--pipeline_model_parallel_size", "2", "--load", str(pp2), "--finetune",
+                  "--no_load_optim", "--no_load_rng"], tmp_path / "pp2.json")
+    assert got == pytest.approx(fp32res, rel=5e-3), (got, fp32res)
+
+
 def test_interleaved_schedule_matches_baseline(baseline, tmp_path):
     """pp=4 with 2 virtual chunks per stage (8 layers, 1 layer per chunk): the resharder has no interleaved layout
     (like the reference), so the pp=8-style per-layer files are regrouped into model0/model1 here."""
