@@ -84,6 +84,64 @@ def test_kv_cache_decode_matches_full_forward(name, args, world):
     run_distributed(_generation_worker, world, args)
 
 
+def _layout_generation_worker(rank, world, tp, pp, ckpt, out_path, save):
+    """Greedy generation + beam search from a (resharded) checkpoint under tp x pp; the first-stage TP-rank-0 process
+    holds the result (the reference broadcasts the tokens from the last stage back to it)."""
+    import finetune
+    from megatron_llm_b200 import get_args
+    from megatron_llm_b200.checkpointing import load_checkpoint, save_checkpoint
+    from megatron_llm_b200.initialize import initialize_megatron
+    from megatron_llm_b200.models.enums import ModelType
+    from megatron_llm_b200.parallel import state as ps
+    from megatron_llm_b200.text_generation import beam_search_and_post_process, generate_and_post_process
+    from megatron_llm_b200.training import get_model
+    from megatron_llm_b200.utils import unwrap_model
+    extra = ["--save", ckpt, "--save_interval", "1"] if save else ["--load", ckpt, "--no_load_optim", "--no_load_rng", "--finetune"]
+    initialize_megatron(extra_args_provider=finetune.extra_args,
+                        args_list=LLAMA + COMMON + ["--tensor_model_parallel_size", str(tp),
+                                                    "--pipeline_model_parallel_size", str(pp)] + extra)
+
+    def provider(pre_process=True, post_process=True):
+        m = finetune.model_provider(pre_process, post_process)
+        unwrap_model(m).parallel_output = False
+        return m
+    model = get_model(provider, ModelType.encoder_or_decoder, wrap_with_ddp=False, args=get_args())
+    if save:
+        save_checkpoint(1, model, None, None)
+    else:
+        load_checkpoint(model, None, None)
+    model = model[0]
+    model.eval()
+    prompts = ["5 9 13 2", "7 7 1 40 3 22"]
+    out = generate_and_post_process(model, prompts=prompts, tokens_to_generate=6, return_output_log_probs=True,
+                                    top_k_sampling=1, use_eod_token_for_early_termination=False)
+    beams = beam_search_and_post_process(model, prompts=[prompts[0]], tokens_to_generate=5, beam_size=3,
+                                         stop_token=63, num_return_gen=3, length_penalty=1.0)
+    if ps.is_pipeline_first_stage() and ps.get_tensor_model_parallel_rank() == 0:
+        texts, _, logprobs, _ = out                           # (None on the other stages, as in the reference)
+        with open(out_path, "w") as f:
+            json.dump({"texts": texts, "logprobs": logprobs, "beams": beams[0],
+                       "beam_scores": [float(x) for x in beams[2]]}, f)
+
+
+@pytest.mark.parametrize("tp,pp", [(1, 2), (2, 2)], ids=["pp2", "tp2_pp2"])
+def test_generation_under_pipeline_parallelism(tmp_path, tp, pp):
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from tools import checkpoint_util
+    ckpt = tmp_path / "ckpt"
+    run_distributed(_layout_generation_worker, 1, 1, 1, str(ckpt), str(tmp_path / "ref.json"), True)
+    dst = tmp_path / "resharded"
+    checkpoint_util.main(["--model_type", "llama2", "--load_dir", str(ckpt), "--save_dir", str(dst),
+                          "--target_tensor_parallel_size", str(tp), "--target_pipeline_parallel_size", str(pp),
+                          "--true_vocab_size", "64"])
+    run_distributed(_layout_generation_worker, tp * pp, tp, pp, str(dst), str(tmp_path / "got.json"), False)
+    ref, got = json.load(open(tmp_path / "ref.json")), json.load(open(tmp_path / "got.json"))
+    assert got["texts"] == ref["texts"] and got["beams"] == ref["beams"], (got, ref)
+    for a, b in zip(got["logprobs"], ref["logprobs"]):
+        assert a == pytest.approx(b, abs=1e-4)
+    assert got["beam_scores"] == pytest.approx(ref["beam_scores"], abs=1e-4)
+
+
 def test_request_validation():
     from megatron_llm_b200.text_generation_server import RequestError, parse_request
     ok = parse_request({"prompts": ["a"], "tokens_to_generate": 4, "top_k": 2, "temperature": 0.7})
