@@ -263,6 +263,17 @@ _GROUPS = {
         ("--no_data_sharding", _SF("data_sharding")),
         ("--head_lr_mult", dict(type=float, default=1.0)),
         ("--iter_per_epoch", dict(type=int, default=1250)),
+        # DINO options: parsed for command-line compatibility (the reference ships the flags, arguments.py:1082-1102,
+        # but no DINO model reads them)
+        ("--dino_local_img_size", dict(type=int, default=96)),
+        ("--dino_local_crops_number", dict(type=int, default=10)),
+        ("--dino_head_hidden_size", dict(type=int, default=2048)),
+        ("--dino_bottleneck_size", dict(type=int, default=256)),
+        ("--dino_freeze_last_layer", dict(type=float, default=1)),
+        ("--dino_norm_last_layer", _S()),
+        ("--dino_warmup_teacher_temp", dict(type=float, default=0.04)),
+        ("--dino_teacher_temp", dict(type=float, default=0.07)),
+        ("--dino_warmup_teacher_temp_epochs", dict(type=int, default=30)),
     ],
     "inference": [
         ("--inference_batch_times_seqlen_threshold", dict(type=int, default=512)),
