@@ -266,3 +266,59 @@ def test_hf_megatron_hf_round_trip(name, tmp_path, monkeypatch):
     tokens = torch.randint(0, vocab, (2, 32), generator=torch.Generator().manual_seed(1))
     with torch.no_grad():
         assert torch.equal(back(tokens).logits, hf(tokens).logits)
+
+
+def _tiny_sentencepiece_model(d):
+    import random
+    import sentencepiece as spm
+    rnd = random.Random(0)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta", "iota", "kappa", "lambda", "mu"]
+    corpus = d / "corpus.txt"
+    corpus.write_text("\n".join(" ".join(rnd.choice(words) for _ in range(rnd.randint(3, 12))) for _ in range(500)))
+    spm.SentencePieceTrainer.train(input=str(corpus), model_prefix=str(d / "tokenizer"), vocab_size=80, model_type="bpe",
+                                   pad_id=-1, unk_id=0, bos_id=1, eos_id=2, minloglevel=2)
+    return d / "tokenizer.model"
+
+
+def test_megatron_to_hf_writes_matching_tokenizer_and_shards(tmp_path):
+    """megatron_to_hf with --vocab_file / --vocab_extra_ids_list / --override_special_tokens / --num_output_shards: the
+    vocabulary is trimmed to the Megatron tokenizer's size, the saved HF tokenizer assigns the ids Megatron trained
+    with (special tokens appended in the same order), the override lands, and the weights come in several shards."""
+    import weights_conversion.hf_to_megatron as C
+    import weights_conversion.megatron_to_hf as R
+    from megatron_llm_b200.tokenizer.tokenizer import _SentencePieceTokenizer
+    from transformers import AutoModelForCausalLM, AutoTokenizer, LlamaConfig, LlamaForCausalLM
+    sp_dir = tmp_path / "sp"
+    sp_dir.mkdir()
+    vocab_file = _tiny_sentencepiece_model(sp_dir)
+    extra = "<|im_start|>,<|im_end|>"
+    mt = _SentencePieceTokenizer(str(vocab_file), vocab_extra_ids_list=extra, new_tokens=True)
+    assert mt.vocab_size == 80 + 5 + 2                       # <CLS> <SEP> <EOD> <MASK> <PAD> + the two extra ids
+    padded = 128
+    torch.manual_seed(0)
+    cfg = LlamaConfig(vocab_size=padded, hidden_size=64, intermediate_size=176, num_hidden_layers=2,
+                      num_attention_heads=4, num_key_value_heads=2, max_position_embeddings=64, rms_norm_eps=1e-5,
+                      tie_word_embeddings=False)
+    hf = LlamaForCausalLM(cfg).float().eval()
+    mw = C.llama_like_to_megatron(C.hf_llama_state_to_meta_names(dict(hf.state_dict())), 2, 64, 4, 2, "hf")
+    a = C.architecture_args("llama2", 7, 2, 64, 4, 2, 176, padded)
+    a.update(max_position_embeddings=64, seq_length=32)
+    C.save_megatron(tmp_path / "meg", mw, a, torch.float32)
+    R.main("llama2", tmp_path / "meg", tmp_path / "hf", vocab_file=vocab_file, no_new_tokens=False, dtype=torch.float32,
+           override_special_tokens=["eos=<|im_end|>", "bogus", "xyz=<PAD>", "pad=<nope>"], num_output_shards=3,
+           vocab_extra_ids_list=extra)
+    shards = [f for f in os.listdir(tmp_path / "hf") if f.endswith(".safetensors")]
+    assert len(shards) >= 3 and (tmp_path / "hf" / "model.safetensors.index.json").exists()
+    back = AutoModelForCausalLM.from_pretrained(tmp_path / "hf").float().eval()
+    assert back.config.vocab_size == mt.vocab_size
+    tokens = torch.randint(0, mt.vocab_size, (2, 16), generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        assert torch.equal(back(tokens).logits, hf(tokens).logits[..., :mt.vocab_size])
+    tok = AutoTokenizer.from_pretrained(tmp_path / "hf")
+    vocab = tok.get_vocab()
+    for name in ("<CLS>", "<SEP>", "<EOD>", "<MASK>", "<PAD>", "<|im_start|>", "<|im_end|>", "<s>", "</s>"):
+        assert vocab[name] == mt.vocab[name], name
+    assert tok.eos_token == "<|im_end|>" and tok.eos_token_id == mt.vocab["<|im_end|>"]
+    assert tok.pad_token_id == mt.pad and tok.cls_token_id == mt.cls and tok.mask_token_id == mt.mask
+    text = "alpha beta<|im_end|> gamma"
+    assert tok.encode(text, add_special_tokens=False) == mt.tokenize(text)

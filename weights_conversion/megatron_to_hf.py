@@ -106,14 +106,90 @@ def build_hf_config(model: str, args, vocab_size: int):
     return cfg
 
 
+_HUB_TOKENIZERS = {"codellama": "TheBloke/CodeLlama-13B-fp16", "mistral": "mistralai/Mistral-7B-v0.1",
+                   "falcon": "tiiuae/falcon-40b"}          # (reference megatron_to_hf.py:489-507)
+
+
+def _megatron_tokenizer(tokenizer_type, vocab_file, new_tokens, vocab_extra_ids_list):
+    from argparse import Namespace
+    from megatron_llm_b200.tokenizer import build_tokenizer
+    return build_tokenizer(Namespace(tokenizer_type=tokenizer_type, vocab_file=vocab_file, merge_file=None, rank=0,
+                                     vocab_extra_ids=0, vocab_extra_ids_list=vocab_extra_ids_list,
+                                     new_tokens=new_tokens, make_vocab_size_divisible_by=128,
+                                     tensor_model_parallel_size=1,
+                                     tokenizer_model=vocab_file if tokenizer_type == "FalconTokenizer" else None))
+
+
+def write_tokenizer(model: str, output_dir, vocab_file=None, new_tokens=True, vocab_extra_ids_list=None,
+                    override_special_tokens=(), cache_dir=None):
+    """Save a Hugging Face tokenizer whose ids agree with the Megatron tokenizer the model was trained with
+    (parity: megatron_to_hf.py::write_tokenizer).  Llama-family: ``tokenizer.model`` (``--vocab_file``, or the hub
+    copy when reachable) plus the special tokens Megatron appends (<CLS> <SEP> <EOD> <MASK> <PAD>, the
+    ``--vocab_extra_ids_list`` entries), every id cross-checked.  Falcon: the wrapped HF tokenizer itself.
+    ``override_special_tokens``: ``key=token`` with key in bos|cls|eos|mask|pad|sep|unk."""
+    import warnings
+    if model == "falcon":
+        mt = _megatron_tokenizer("FalconTokenizer", str(vocab_file) if vocab_file else None, new_tokens,
+                                 vocab_extra_ids_list)
+        hf_tok = mt.tokenizer
+    else:
+        from transformers import LlamaTokenizerFast
+        try:
+            if vocab_file:
+                src = Path(vocab_file)
+                hf_tok = LlamaTokenizerFast.from_pretrained(src.parent if src.suffix == ".model" else src)
+            else:
+                hf_tok = LlamaTokenizerFast.from_pretrained(_HUB_TOKENIZERS.get(model, "meta-llama/Llama-2-7b-hf"),
+                                                            cache_dir=cache_dir)
+            vocab_file = hf_tok.vocab_file
+        except OSError as e:
+            print("ERROR: could not load the tokenizer ({}); no tokenizer written.".format(e))
+            return None
+        mt = _megatron_tokenizer("SentencePieceTokenizer", str(vocab_file), new_tokens, vocab_extra_ids_list)
+        # Megatron appends its special tokens after the SentencePiece pieces in a fixed order; appending the same
+        # tokens in the same order gives the same ids
+        appended = sorted((i, t) for t, i in mt.vocab.items() if i >= len(hf_tok))
+        for _, tok in appended:
+            hf_tok.add_tokens(tok, special_tokens=True)
+        for attr, name in (("cls", "cls_token"), ("sep", "sep_token"), ("mask", "mask_token"), ("pad", "pad_token")):
+            tid = getattr(mt, attr, None)
+            if tid is not None and new_tokens:
+                setattr(hf_tok, name, mt.inv_vocab[tid])
+        extra = [t for t in (vocab_extra_ids_list.split(",") if vocab_extra_ids_list else [])]
+        if extra:
+            hf_tok.add_special_tokens({"additional_special_tokens": extra})
+        hf_vocab = hf_tok.get_vocab()
+        named = [v for k, v in hf_tok.special_tokens_map.items() if k != "additional_special_tokens"]
+        for tok in named + extra + [t for _, t in appended]:
+            a, b = mt.vocab.get(tok), hf_vocab.get(tok)
+            assert a == b, f"Megatron and Hugging Face tokenizers disagree on {tok!r}: {a} vs {b}"
+    for item in override_special_tokens or ():
+        key, sep, value = item.partition("=")
+        if not sep:
+            warnings.warn(f"Illegal override string {item}")
+        elif key not in {"bos", "cls", "eos", "mask", "pad", "sep", "unk"}:
+            warnings.warn(f"Cannot override key {key}")
+        elif value not in mt.vocab:
+            warnings.warn(f"Token {value} not found in megatron tokenizer")
+        else:
+            setattr(hf_tok, f"{key}_token", value)
+            assert getattr(hf_tok, f"{key}_token_id") == mt.vocab[value]
+    print("Final HF tokenizer configuration:")
+    print(hf_tok)
+    hf_tok.save_pretrained(output_dir)
+    return hf_tok
+
+
 def main(model: str, input_dir: Path, output_dir: Path, vocab_file=None, no_new_tokens=True, dtype=torch.bfloat16,
-         override_special_tokens=None):
+         override_special_tokens=None, num_output_shards=1, vocab_extra_ids_list=None, cache_dir=None,
+         tokenizer=True):
     from transformers import AutoModelForCausalLM
     args, emb, enc, lm_head = load_megatron(Path(input_dir))
     vocab_size = emb.size(0)
-    if vocab_file is not None:
+    if vocab_file is not None and model != "falcon":
         from megatron_llm_b200.tokenizer.tokenizer import _SentencePieceTokenizer
-        tok = _SentencePieceTokenizer(str(vocab_file), new_tokens=not no_new_tokens)
+        tok = _SentencePieceTokenizer(str(vocab_file), vocab_extra_ids_list=vocab_extra_ids_list,
+                                      new_tokens=not no_new_tokens)
         vocab_size = tok.vocab_size
     sd = falcon_to_hf(args, emb, enc, vocab_size) if model == "falcon" else \
         llama_like_to_hf(args, emb, enc, lm_head, vocab_size)
@@ -124,16 +200,31 @@ def main(model: str, input_dir: Path, output_dir: Path, vocab_file=None, no_new_
     missing, unexpected = hf.load_state_dict({k: v.to(dtype) for k, v in sd.items()}, strict=False)
     missing = [m for m in missing if "rotary_emb" not in m]
     assert not missing and not unexpected, (missing, unexpected)
-    hf.save_pretrained(output_dir)
+    kw = {}
+    if num_output_shards and num_output_shards > 1:
+        total = sum(p.numel() * p.element_size() for p in hf.parameters())
+        kw["max_shard_size"] = -(-total // num_output_shards)          # bytes per safetensors shard
+    hf.save_pretrained(output_dir, **kw)
     print("Saved Hugging Face model in", output_dir)
+    if tokenizer and (vocab_file is not None or cache_dir is not None):
+        write_tokenizer(model, output_dir, vocab_file, not no_new_tokens, vocab_extra_ids_list,
+                        override_special_tokens or (), cache_dir)
 
 
 if __name__ == "__main__":
     parser = ArgumentParser(description="Convert megatron weights back to the Hugging Face format")
     parser.add_argument("--model", type=str, default="llama2", choices={"falcon", "llama", "llama2", "codellama", "mistral"})
-    parser.add_argument("--input_dir", type=Path, required=True)
-    parser.add_argument("--output_dir", type=Path, required=True)
-    parser.add_argument("--vocab_file", type=Path, default=None)
+    parser.add_argument("--input_dir", type=Path, required=True, help="Megatron checkpoint directory (tp = pp = 1)")
+    parser.add_argument("--output_dir", type=Path, required=True, help="where the HF model and tokenizer are written")
+    parser.add_argument("--num_output_shards", type=int, default=1, help="number of safetensors shards")
+    parser.add_argument("--cache_dir", help="Hugging Face cache_dir (tokenizer download when --vocab_file is not given)")
+    parser.add_argument("--vocab_file", type=Path, default=None,
+                        help="tokenizer.model (Llama family) or a local tokenizer directory (Falcon)")
+    parser.add_argument("--vocab_extra_ids_list", help="comma separated list of special tokens added to the tokenizer")
+    parser.add_argument("--override_special_tokens", nargs="*", default=[],
+                        help="key=token pairs, key in bos|cls|eos|mask|pad|sep|unk, e.g. eos=<|im_end|>")
     parser.add_argument("--no_new_tokens", action="store_false", dest="new_tokens")
     a = parser.parse_args()
-    main(a.model, a.input_dir, a.output_dir, a.vocab_file, not a.new_tokens)
+    main(a.model, a.input_dir, a.output_dir, a.vocab_file, not a.new_tokens,
+         override_special_tokens=a.override_special_tokens, num_output_shards=a.num_output_shards,
+         vocab_extra_ids_list=a.vocab_extra_ids_list, cache_dir=a.cache_dir)
