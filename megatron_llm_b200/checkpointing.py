@@ -96,6 +96,13 @@ def get_checkpoint_names(checkpoints_path, iteration, use_distributed_optimizer,
     return model_name, optim_name
 
 
+def get_checkpoint_name(checkpoints_path, iteration, release=False, pipeline_parallel=None, tensor_rank=None,
+                        pipeline_rank=None):
+    """This rank's single-file checkpoint path (reference checkpointing.py:77-104; the tools use it)."""
+    return get_checkpoint_names(checkpoints_path, iteration, False, release, pipeline_parallel, tensor_rank,
+                                pipeline_rank)[0]
+
+
 def find_checkpoint_rank_0(checkpoints_path, iteration, use_distributed_optimizer, release=False):
     """Locate rank (tp=0, pp=0)'s file whether or not the checkpoint was written with PP>1."""
     for pipeline_parallel in (False, True):

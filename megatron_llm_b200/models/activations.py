@@ -43,6 +43,36 @@ def bias_gelu_impl(x, bias):
     return ops.gelu(x, bias, approximate=True)
 
 
+def bias_gelu(bias, y):
+    """Reference argument order (fused_bias_gelu.py:14): tanh-approximate gelu(y + bias)."""
+    return ops.gelu(y, bias, approximate=True)
+
+
+def bias_gelu_back(g, bias, y):
+    """d/dy of ``bias_gelu`` times ``g`` (fused_bias_gelu.py:22-30); the training path gets it from the backward of
+    ``ops.gelu`` -- this closed form is for callers that apply it by hand."""
+    x = (bias + y).float()
+    t = torch.tanh(0.79788456 * x * (1 + 0.044715 * x * x))
+    ff = 0.5 * x * ((1 - t * t) * (0.79788456 + 0.1070322243 * x * x)) + 0.5 * (1 + t)
+    return (ff * g.float()).to(g.dtype)
+
+
+class GeLUFunction(torch.autograd.Function):
+    """autograd wrapper returning (dinput, dbias) like the reference's (fused_bias_gelu.py:32-43)."""
+
+    @staticmethod
+    def forward(ctx, input, bias):
+        ctx.save_for_backward(input, bias)
+        return bias_gelu(bias, input)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, bias = ctx.saved_tensors
+        tmp = bias_gelu_back(grad_output, bias, input)
+        dbias = tmp.reshape(-1, tmp.size(-1)).sum(0).view_as(bias) if bias.dim() == 1 else tmp
+        return tmp, dbias
+
+
 def init_method_normal(sigma):
     def init_(tensor):
         return nn.init.normal_(tensor, mean=0.0, std=sigma)

@@ -43,6 +43,16 @@ class MixedFusedLayerNorm(torch.nn.Module):
 LayerNorm = MixedFusedLayerNorm
 
 
+class FusedLayerNormAffineFunction:
+    """apex-style functional entry (reference fused_layer_norm.py:33-53): ``apply(input, weight, bias, shape, eps)``;
+    differentiable through the same autograd function the modules use."""
+
+    @staticmethod
+    def apply(input, weight, bias, normalized_shape, eps):
+        assert tuple(input.shape[-len(tuple(normalized_shape)):]) == tuple(normalized_shape)
+        return ops.layernorm(input, weight, bias, eps)
+
+
 class RMSNorm(torch.nn.Module):
     def __init__(self, dim: int, eps: float = 1e-6, sequence_parallel: bool = False):
         super().__init__()

@@ -315,6 +315,34 @@ def _bias_dropout_add(x, bias, residual, prob, training):
     return ops.bias_dropout_add(x, bias, residual, prob, training)
 
 
+def bias_dropout_add(x, bias, residual, prob, training):
+    """residual + dropout(x + bias) (reference transformer.py:529-535)."""
+    return ops.bias_dropout_add(x, bias, residual, prob, training)
+
+
+def dropout_add(x, bias, residual, prob, training):
+    """residual + dropout(x); ``bias`` must be None (reference transformer.py:503-511, the bias-free models)."""
+    assert bias is None
+    return ops.bias_dropout_add(x, None, residual, prob, training)
+
+
+def get_bias_dropout_add(training):
+    return lambda x, bias, residual, prob: bias_dropout_add(x, bias, residual, prob, training)
+
+
+def get_dropout_add(training):
+    return lambda x, bias, residual, prob: dropout_add(x, bias, residual, prob, training)
+
+
+def bias_dropout_add_fused_train(x, bias, residual, prob):
+    """(the reference needs a jit-scripted variant per mode, transformer.py:544-560; here one kernel serves both)"""
+    return bias_dropout_add(x, bias, residual, prob, True)
+
+
+def bias_dropout_add_fused_inference(x, bias, residual, prob):
+    return bias_dropout_add(x, bias, residual, prob, False)
+
+
 class ParallelTransformerLayer(MegatronModule):
     """One transformer layer, [s, b, h] -> [s, b, h].
 

@@ -14,10 +14,23 @@ import torch
 import torch.distributed as dist
 
 from ..parallel import state as ps
-from .optimizer import FlatOptimizer
+from .optimizer import MixedPrecisionOptimizer
 
 
-class DistributedOptimizer(FlatOptimizer):
+class Range:
+    """[start, end) of a flat buffer (reference distrib_optimizer.py:15-29)."""
+
+    def __init__(self, start, end):
+        self.start, self.end, self.size = start, end, end - start
+
+    def normalize(self, start=0):
+        return Range(start, start + self.size)
+
+    def __str__(self):
+        return "%d,%d [%d]" % (self.start, self.end, self.size)
+
+
+class DistributedOptimizer(MixedPrecisionOptimizer):
     def __init__(self, optimizer_config, clip_grad, log_num_zeros_in_grad, params_have_main_grad,
                  use_contiguous_buffers_in_local_ddp, fp16, bf16, params_dtype, grad_scaler, models):
         assert use_contiguous_buffers_in_local_ddp
@@ -35,6 +48,10 @@ class DistributedOptimizer(FlatOptimizer):
                 g.p16_peer_ptrs = comm.param_peer_ptrs(g.shard[0])
                 if comm not in self._fused_gather:
                     self._fused_gather.append(comm)
+
+    def shard_ranges(self):
+        """This DP rank's slice of each flat group's gradient / parameter buffer."""
+        return [Range(*g.shard) for g in self.groups]
 
     def _norm_reduce_group(self):
         """Every (tp, pp, dp) rank holds a distinct slice of the gradients: reduce over the whole world."""

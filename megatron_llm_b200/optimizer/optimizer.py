@@ -492,7 +492,13 @@ class FlatOptimizer(MegatronOptimizer):
             self.reload_model_params()
 
 
-class Float16OptimizerWithFloat16Params(FlatOptimizer):
+class MixedPrecisionOptimizer(FlatOptimizer):
+    """Optimizers with 16-bit model weights and fp32 master state (reference optimizer.py:281-457): the loss-scaling /
+    unscale / found-inf logic lives in ``FlatOptimizer`` (it degenerates to a no-op for fp32 models), this class is
+    the common base of the two mixed-precision optimizers so ``isinstance`` checks keep working."""
+
+
+class Float16OptimizerWithFloat16Params(MixedPrecisionOptimizer):
     """fp16/bf16 model weights + fp32 master weights / moments (full copy on every DP rank)."""
 
     def __init__(self, optimizer_config, clip_grad, log_num_zeros_in_grad, params_have_main_grad,

@@ -158,6 +158,14 @@ def print_rank_last(message):
         print(message, flush=True)
 
 
+def is_last_local_rank():
+    """Last process of this node (reference utils.py:218-219; LOCAL_WORLD_SIZE from torchrun, 1 if absent)."""
+    local_rank = getattr(_args(), "local_rank", None)
+    if local_rank is None:
+        local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    return local_rank == int(os.environ.get("LOCAL_WORLD_SIZE", "1")) - 1
+
+
 def print_all_nodes(message):
     """Print on the last local rank of every node (LOCAL_WORLD_SIZE from torchrun; 1 if absent)."""
     if dist.is_initialized():

@@ -159,3 +159,69 @@ def test_bench_presets_build_valid_arguments(monkeypatch):
         # the micro-batch graph is requested when one TP group of > 1 GPUs spans the job, no pipeline, no recompute
         assert bool(getattr(args, "cuda_graph_microbatch", False)) == (layout[0] > 1 and layout[0] == gpus
                                                                         and layout[1] == 1 and not a.recompute)
+
+
+def test_reference_helper_names_behave():
+    """Small public helpers that scripts written against the reference import by name."""
+    import os
+    from megatron_llm_b200.models import activations as A
+    from megatron_llm_b200.models import norms as N
+    from megatron_llm_b200.models import transformer as T
+    from megatron_llm_b200.optimizer import distrib_optimizer as D
+    from megatron_llm_b200.optimizer import optimizer as O
+    torch.manual_seed(0)
+    x = torch.randn(5, 7, dtype=torch.float64, requires_grad=True)
+    b = torch.randn(7, dtype=torch.float64, requires_grad=True)
+    y = A.bias_gelu(b, x)
+    assert torch.allclose(y, F.gelu(x + b, approximate="tanh"), atol=1e-6)
+    g = torch.randn_like(y)
+    dx, = torch.autograd.grad(F.gelu(x + b, approximate="tanh"), x, g)
+    assert torch.allclose(A.bias_gelu_back(g, b, x), dx, atol=1e-5)
+    out = A.GeLUFunction.apply(x, b)
+    gx, gb = torch.autograd.grad(out, (x, b), g)
+    assert torch.allclose(gx, dx, atol=1e-5) and torch.allclose(gb, dx.sum(0), atol=1e-5)
+    # bias-dropout-add family (inference closures are deterministic)
+    r = torch.randn(5, 7)
+    f = T.get_bias_dropout_add(False)
+    assert torch.allclose(f(x.float(), b.float(), r, 0.3), r + x.float() + b.float())
+    assert torch.allclose(T.get_dropout_add(False)(x.float(), None, r, 0.3), r + x.float())
+    assert torch.allclose(T.bias_dropout_add_fused_inference(x.float(), b.float(), r, 0.5), r + x.float() + b.float())
+    kept = T.bias_dropout_add_fused_train(torch.ones(64, 64), None, torch.zeros(64, 64), 0.5)
+    assert set(kept.unique().tolist()) <= {0.0, 2.0} and 0.3 < (kept > 0).float().mean() < 0.7
+    # functional layer norm
+    w, bias = torch.rand(7), torch.rand(7)
+    got = N.FusedLayerNormAffineFunction.apply(r, w, bias, (7,), 1e-5)
+    assert torch.allclose(got, F.layer_norm(r, (7,), w, bias, 1e-5), atol=1e-5)
+    # optimizer class tree + shard range helper
+    assert issubclass(O.Float16OptimizerWithFloat16Params, O.MixedPrecisionOptimizer)
+    assert issubclass(D.DistributedOptimizer, O.MixedPrecisionOptimizer)
+    assert not issubclass(O.FP32Optimizer, O.MixedPrecisionOptimizer)
+    rg = D.Range(8, 20)
+    assert (rg.size, str(rg.normalize(2))) == (12, "2,14 [12]")
+    # checkpoint file name
+    from megatron_llm_b200.checkpointing import get_checkpoint_name
+    assert get_checkpoint_name("/c", 12, False, True, 1, 3) == os.path.join("/c", "iter_0000012", "mp_rank_01_003",
+                                                                            "model_optim_rng.pt")
+    assert get_checkpoint_name("/c", 0, True, False, 0, 0) == os.path.join("/c", "release", "mp_rank_00",
+                                                                           "model_optim_rng.pt")
+
+
+def test_conversion_helper_names():
+    import weights_conversion.hf_to_megatron as C
+    import weights_conversion.megatron_to_hf as R
+    import verify_correctness as V
+    assert V.Llama2Wrapper is V.MetaLlamaWrapper
+    torch.manual_seed(0)
+    h, n, nkv, ffn = 64, 8, 2, 96
+    wq, wk, wv = torch.randn(h, h), torch.randn(h // 4, h), torch.randn(h // 4, h)
+    up, gate = torch.randn(ffn, h), torch.randn(ffn, h)
+    meta = {"tok_embeddings.weight": torch.randn(32, h), "norm.weight": torch.ones(h), "output.weight": torch.randn(32, h),
+            "layers.0.attention.wo.weight": torch.randn(h, h), "layers.0.ffn_norm.weight": torch.ones(h),
+            "layers.0.attention_norm.weight": torch.ones(h), "layers.0.feed_forward.w2.weight": torch.randn(h, ffn),
+            "layers.0.feed_forward.w3.weight": up, "layers.0.feed_forward.w1.weight": gate,
+            "layers.0.attention.wq.weight": wq, "layers.0.attention.wk.weight": wk, "layers.0.attention.wv.weight": wv}
+    mega = C.llama_like_to_megatron(dict(meta), 1, h, n, nkv, "hf")
+    q2, k2, v2 = R.convert_wqkv(mega, 0, n, nkv)
+    assert torch.equal(q2, wq) and torch.equal(k2, wk) and torch.equal(v2, wv)
+    w1, w3 = R.convert_ffn(mega, 0, ffn)
+    assert torch.equal(w1, gate) and torch.equal(w3, up)

@@ -74,6 +74,9 @@ class MetaLlamaWrapper(nn.Module):
         return self.model(input_ids=input_ids, position_ids=position_ids, labels=labels)
 
 
+Llama2Wrapper = MetaLlamaWrapper          # the reference's name (verify_correctness.py:21)
+
+
 def is_meta_llama2_path(path: Optional[Path]) -> bool:
     return path is not None and len(list(Path(path).glob("*.pth"))) > 0
 

@@ -61,6 +61,20 @@ def llama_like_to_megatron(weights: dict, n_layer, hidden, n_heads, n_kv_heads, 
     return {"embedding": embedding, "transformer": transformer, "lm_head": weights["output.weight"]}
 
 
+def llama_to_megatron(weights: dict, size: int, source: str = "meta", version: int = 1) -> dict:
+    """Size-table front end of ``llama_like_to_megatron`` (the reference's entry point, hf_to_megatron.py:117)."""
+    n_heads = llama_s2heads[size]
+    n_kv = n_heads if (version == 1 or size <= 13) else 8
+    return llama_like_to_megatron(weights, llama_s2layer[size], llama_s2hidden[size], n_heads, n_kv, source)
+
+
+def mistral_to_megatron(weights: dict, size: int = 7) -> dict:
+    """Mistral-7B (Meta-style names, e.g. from ``hf_llama_state_to_meta_names``): 32 layers, 32 heads over 8 KV heads,
+    Hugging Face rotary layout (reference hf_to_megatron.py:185)."""
+    assert size == 7
+    return llama_like_to_megatron(weights, 32, 4096, 32, 8, "hf")
+
+
 def falcon_to_megatron(weights: dict, size: int) -> dict:
     """HF Falcon already fuses QKV per KV group; only the rotary permutation and the key names change.
     Embeddings are tied: the LM head must equal the word embeddings."""

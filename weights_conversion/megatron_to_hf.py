@@ -26,6 +26,37 @@ def ungroup_qkv(qkv, n_heads, n_kv_heads, head_dim):
     return wq, wk, wv
 
 
+def _layer_weight(ckpt, layer_idx, name):
+    """``ckpt``: a language-model state dict (``transformer`` or ``encoder`` section, ``attention`` or
+    ``self_attention`` naming) as stored in the checkpoint."""
+    section = ckpt["transformer"] if "transformer" in ckpt else ckpt["encoder"]
+    for att in ("attention", "self_attention"):
+        key = f"layers.{layer_idx}." + name.replace("{att}", att)
+        if key in section:
+            return section[key]
+    raise KeyError(name)
+
+
+def convert_wqkv(llama_mega, layer_idx=0, n_heads=32, n_heads_kv=8):
+    """(wq, wk, wv) in the Hugging Face layout for one layer (reference megatron_to_hf.py:47-71)."""
+    qkv = _layer_weight(llama_mega, layer_idx, "{att}.query_key_value.weight")
+    hidden = qkv.size(1)
+    return ungroup_qkv(permute_qkv(qkv, hidden, n_heads, n_heads_kv, revert=True), n_heads, n_heads_kv,
+                       hidden // n_heads)
+
+
+def convert_ffn(llama_mega, layer_idx=0, n_dense=11008):
+    """(w1 = gate, w3 = up) of one layer's fused ``dense_h_to_4h`` = [up; gate] (reference :74-77)."""
+    w3, w1 = _layer_weight(llama_mega, layer_idx, "mlp.dense_h_to_4h.weight").split(n_dense, dim=0)
+    return w1, w3
+
+
+def write_json(obj, path):
+    import json
+    with open(path, "w") as f:
+        json.dump(obj, f)
+
+
 def load_megatron(input_dir: Path):
     it = (input_dir / "latest_checkpointed_iteration.txt").read_text().strip()
     sub = it if it == "release" else f"iter_{int(it):07d}"
@@ -209,6 +240,20 @@ def main(model: str, input_dir: Path, output_dir: Path, vocab_file=None, no_new_
     if tokenizer and (vocab_file is not None or cache_dir is not None):
         write_tokenizer(model, output_dir, vocab_file, not no_new_tokens, vocab_extra_ids_list,
                         override_special_tokens or (), cache_dir)
+
+
+def write_llama_model(model_path, input_base_path, num_output_shards=2, norm_eps=None, rope_theta=None):
+    """The reference's per-family writers (megatron_to_hf.py:80, :196, :333): weights + config, no tokenizer.  The
+    architecture (incl. the norm epsilon and RoPE base) comes from the checkpoint's stored arguments."""
+    main("llama2", Path(input_base_path), Path(model_path), num_output_shards=num_output_shards, tokenizer=False)
+
+
+def write_mistral_model(model_path, input_base_path, num_output_shards=2, **_):
+    main("mistral", Path(input_base_path), Path(model_path), num_output_shards=num_output_shards, tokenizer=False)
+
+
+def write_falcon_model(model_path, input_base_path, num_output_shards=2, safe_serialization=True):
+    main("falcon", Path(input_base_path), Path(model_path), num_output_shards=num_output_shards, tokenizer=False)
 
 
 if __name__ == "__main__":
