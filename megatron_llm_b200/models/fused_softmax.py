@@ -55,6 +55,13 @@ class FusedScaleMaskSoftmax(nn.Module):
     def is_kernel_available(self, mask, b, np, sq, sk):
         return bool(self.scaled_masked_softmax_fusion and self.input_in_float16)
 
+    @staticmethod
+    def get_batch_per_block(sq, sk, b, np):
+        """Softmax rows handled by one thread block.  The reference's warp-per-row kernels pack several rows per
+        block and need ``sq * b * np`` to divide by this (fused_softmax.py:155-166, :209-213); csrc/softmax.cu runs
+        one block per row, so any shape qualifies."""
+        return 1
+
     def forward_fused_softmax(self, input, mask):
         scale = self.scale if self.scale is not None else 1.0
         if self.attn_mask_type == AttnMaskType.causal and input.size(2) == input.size(3):

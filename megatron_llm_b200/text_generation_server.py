@@ -110,6 +110,9 @@ class MegatronGenerate:
     def __init__(self, model):
         self.model = model
 
+    send_do_generate = staticmethod(send_do_generate)          # (static methods in the reference, :21-29)
+    send_do_beam_search = staticmethod(send_do_beam_search)
+
     def put(self, req: dict):
         try:
             p = parse_request(req)

@@ -5,6 +5,7 @@ greedy lowest-rank pair merges with a per-word cache."""
 from __future__ import annotations
 
 import json
+import os
 from functools import lru_cache
 
 import regex as re
@@ -25,6 +26,9 @@ def bytes_to_unicode():
             chars.append(256 + extra)
             extra += 1
     return dict(zip(keep, (chr(c) for c in chars)))
+
+
+VOCAB_NAME, MERGES_NAME, SPECIAL_TOKENS_NAME = "vocab.json", "merges.txt", "special_tokens.txt"
 
 
 def get_pairs(word):
@@ -50,6 +54,42 @@ class GPT2Tokenizer:
 
     def __len__(self):
         return len(self.encoder) + len(self.special_tokens)
+
+    @classmethod
+    def from_pretrained(cls, pretrained_model_name_or_path, cache_dir=None, *inputs, **kwargs):
+        """Load ``vocab.json`` / ``merges.txt`` (+ optional ``special_tokens.txt``) from a directory, the layout
+        ``save_vocabulary`` writes (reference gpt2_tokenization.py:98-160; the reference can also download the
+        published GPT-2 files by name -- there is no download path here, ``cache_dir`` is searched instead)."""
+        base = pretrained_model_name_or_path
+        if not os.path.isdir(base) and cache_dir is not None:
+            base = os.path.join(cache_dir, pretrained_model_name_or_path)
+        vocab_file, merges_file = os.path.join(base, VOCAB_NAME), os.path.join(base, MERGES_NAME)
+        if not (os.path.exists(vocab_file) and os.path.exists(merges_file)):
+            print("GPT2Tokenizer: no {} / {} under {!r}".format(VOCAB_NAME, MERGES_NAME, base), flush=True)
+            return None
+        special_file = os.path.join(base, SPECIAL_TOKENS_NAME)
+        if os.path.exists(special_file) and "special_tokens" not in kwargs:
+            with open(special_file, encoding="utf-8") as f:
+                kwargs["special_tokens"] = f.read().split("\n")[:-1]
+        return cls(vocab_file, merges_file, *inputs, **kwargs)
+
+    def save_vocabulary(self, vocab_path):
+        """Write the vocabulary, merges and special tokens into a directory; returns the three paths."""
+        if not os.path.isdir(vocab_path):
+            print("Vocabulary path ({}) should be a directory".format(vocab_path), flush=True)
+            return None
+        vocab_file, merge_file = os.path.join(vocab_path, VOCAB_NAME), os.path.join(vocab_path, MERGES_NAME)
+        special_tokens_file = os.path.join(vocab_path, SPECIAL_TOKENS_NAME)
+        with open(vocab_file, "w", encoding="utf-8") as f:
+            f.write(json.dumps(self.encoder, ensure_ascii=False))
+        with open(merge_file, "w", encoding="utf-8") as f:
+            f.write("#version: 0.2\n")
+            for pair, _ in sorted(self.bpe_ranks.items(), key=lambda kv: kv[1]):
+                f.write(" ".join(pair) + "\n")
+        with open(special_tokens_file, "w", encoding="utf-8") as f:
+            for tok, _ in sorted(self.special_tokens.items(), key=lambda kv: kv[1]):
+                f.write(tok + "\n")
+        return vocab_file, merge_file, special_tokens_file
 
     def set_special_tokens(self, special_tokens):
         if not special_tokens:

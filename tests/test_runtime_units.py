@@ -486,3 +486,29 @@ def test_ddp_lays_deferred_params_out_last_and_never_reduces_them_from_the_hooks
     for p in m.parameters():
         ddp._on_param_ready(p)
     assert launched == [b.index for b in buckets if not b.deferred]
+
+
+def test_gpt2_tokenizer_save_and_reload(tmp_path):
+    """save_vocabulary -> from_pretrained gives back the same tokenizer (vocabulary, merge ranks, special tokens)."""
+    import json
+    from megatron_llm_b200.tokenizer.gpt2_tokenization import GPT2Tokenizer, bytes_to_unicode
+    alphabet = list(bytes_to_unicode().values())
+    vocab = {c: i for i, c in enumerate(alphabet)}
+    merges = [("h", "e"), ("l", "l"), ("he", "ll"), ("Ġ", "w"), ("hell", "o")]
+    for a, b in merges:
+        vocab[a + b] = len(vocab)
+    (tmp_path / "src").mkdir()
+    (tmp_path / "src" / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "src" / "merges.txt").write_text("#version: 0.2\n" + "\n".join(" ".join(m) for m in merges) + "\n")
+    tok = GPT2Tokenizer(str(tmp_path / "src" / "vocab.json"), str(tmp_path / "src" / "merges.txt"),
+                        special_tokens=["<|endoftext|>", "<|pad|>"])
+    assert tok.save_vocabulary(str(tmp_path / "missing")) is None
+    (tmp_path / "out").mkdir()
+    assert len(tok.save_vocabulary(str(tmp_path / "out"))) == 3
+    back = GPT2Tokenizer.from_pretrained(str(tmp_path / "out"))
+    assert back.encoder == tok.encoder and back.bpe_ranks == tok.bpe_ranks and back.special_tokens == tok.special_tokens
+    text = "hello world, hello"
+    assert back.encode(text) == tok.encode(text) and back.decode(back.encode(text)) == text
+    assert tok.tokenize("hello")[0] == "hello"
+    assert GPT2Tokenizer.from_pretrained(str(tmp_path / "nowhere")) is None
+    assert GPT2Tokenizer.from_pretrained("out", cache_dir=str(tmp_path)).encoder == tok.encoder
