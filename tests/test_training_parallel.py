@@ -207,3 +207,58 @@ def test_resume_reproduces_training(tmp_path, distopt):
     assert first == pytest.approx(full[:2], rel=1e-6)
     resumed = _run(world, extra + ["--load", str(tmp_path / "ckpt")], tmp_path / "c.json", n_steps=2)
     assert resumed == pytest.approx(full[2:], rel=2e-5, abs=2e-5), (resumed, full)
+
+
+def _flat_tensors(sd, prefix=""):
+    out = {}
+    for k, v in sd.items():
+        if isinstance(v, dict):
+            out.update(_flat_tensors(v, prefix + k + "."))
+        elif torch.is_tensor(v):
+            out[prefix + k] = v
+    return out
+
+
+FAMILIES = {
+    "falcon": (["--model_name", "falcon", "--num_layers", "4", "--hidden_size", "32", "--num_attention_heads", "4",
+                "--num_attention_heads_kv", "2", "--parallel_attn", "--parallel_layernorm", "--position_embedding_type",
+                "rotary", "--no_bias_gelu_fusion"], "falcon"),
+    "gpt": (["--model_name", "gpt", "--num_layers", "4", "--hidden_size", "32", "--num_attention_heads", "4"], "GPT"),
+}
+
+
+@pytest.mark.parametrize("family", sorted(FAMILIES))
+def test_reshard_other_families_tp2_pp2_and_back(tmp_path, family):
+    """tools/checkpoint_util.py for the Falcon (parallel attention + two norms, GQA, tied head) and GPT (biases, learned
+    positions, tied head) layouts: 1x1 -> TP2 x PP2 trains like the original (with sequence parallelism), and merging
+    back to 1x1 returns every tensor bit for bit."""
+    model, model_type = FAMILIES[family]
+    common = MODEL[MODEL.index("--seq_length"):]
+    common = [a for a in common if a not in ("--use_rms_norm", "--no_tie_embed_logits", "--no_bias_gelu_fusion")]
+    for flag in ("--glu_activation", "--position_embedding_type"):
+        i = common.index(flag)
+        del common[i:i + 2]
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from tools import checkpoint_util
+
+    def run(world, more, out, save_first=False):
+        run_distributed(_train_worker, world, model + common + more, str(out), 3, save_first, False)
+        with open(out) as f:
+            return json.load(f)
+    ckpt = tmp_path / "ckpt"
+    ref = run(1, ["--save", str(ckpt)], tmp_path / "ref.json", True)
+    sharded, back = tmp_path / "tp2pp2", tmp_path / "back"
+    checkpoint_util.main(["--model_type", model_type, "--load_dir", str(ckpt), "--save_dir", str(sharded),
+                          "--target_tensor_parallel_size", "2", "--target_pipeline_parallel_size", "2",
+                          "--true_vocab_size", "64"])
+    got = run(4, ["--tensor_model_parallel_size", "2", "--pipeline_model_parallel_size", "2", "--sequence_parallel",
+                  "--load", str(sharded), "--finetune", "--no_load_optim", "--no_load_rng"], tmp_path / "got.json")
+    assert got == pytest.approx(ref, rel=2e-4, abs=2e-4), (got, ref)
+    checkpoint_util.main(["--model_type", model_type, "--load_dir", str(sharded), "--save_dir", str(back),
+                          "--target_tensor_parallel_size", "1", "--target_pipeline_parallel_size", "1",
+                          "--true_vocab_size", "64"])
+    a = _flat_tensors(torch.load(ckpt / "iter_0000001" / "mp_rank_00" / "model_optim_rng.pt", weights_only=False)["model"])
+    sub = [p for p in os.listdir(back) if p.startswith("iter") or p == "release"][0]
+    b = _flat_tensors(torch.load(back / sub / "mp_rank_00" / "model_optim_rng.pt", weights_only=False)["model"])
+    assert set(a) == set(b)
+    assert all(torch.equal(a[k], b[k]) for k in a)
