@@ -131,3 +131,60 @@ def test_pretrain_t5_pipeline_parallel(tmp_path):
                                                  "--pipeline_model_parallel_size", "2",
                                                  "--pipeline_model_parallel_split_rank", "1"], 2)
     assert "lm loss" in out and "iteration        2/" in out
+
+
+LLAMA_TINY = ["--model_name", "llama2", "--num_layers", "4", "--hidden_size", "32", "--num_attention_heads", "4",
+              "--num_attention_heads_kv", "2", "--ffn_hidden_size", "64", "--seq_length", "16",
+              "--max_position_embeddings", "16", "--micro_batch_size", "2", "--global_batch_size", "8",
+              "--tokenizer_type", "NullTokenizer", "--vocab_file", "100", "--make_vocab_size_divisible_by", "8",
+              "--train_iters", "6", "--lr", "1e-2", "--min_lr", "1e-3", "--lr_decay_style", "cosine",
+              "--lr_warmup_iters", "2", "--weight_decay", "0.01", "--clip_grad", "1.0", "--hidden_dropout", "0.0",
+              "--attention_dropout", "0.0", "--use_rms_norm", "--glu_activation", "swiglu",
+              "--position_embedding_type", "rotary", "--no_bias_gelu_fusion", "--no_tie_embed_logits", "--eval_iters",
+              "2", "--eval_interval", "3", "--log_interval", "1", "--seed", "7", "--split", "8,1,1", "--num_workers",
+              "0"]
+
+
+def _loss_lines(out):
+    import re
+    train = [float(m.group(1)) for m in re.finditer(r"iteration\s+\d+/.*?lm loss: ([0-9.E+-]+)", out)]
+    final = [float(m.group(1)) for m in re.finditer(r"for test data \| lm loss value: ([0-9.E+-]+)", out)]
+    return train, final
+
+
+def test_finetune_entry_on_preprocessed_gpt_and_instruction_data(tmp_path):
+    """finetune.py end to end on data written by tools/preprocess_data.py / preprocess_instruct_data.py: a blended GPT
+    corpus (train / valid / test split, cosine schedule with warm-up, periodic + final evaluation), the same run on two
+    data-parallel ranks with loader workers (identical losses: the samplers shard one global batch), and instruction
+    tuning with variable sequence lengths under TP2 x PP2."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import preprocess_data
+    import preprocess_instruct_data
+    rows = [{"text": " ".join(str((i * 7 + j) % 50) for j in range(5 + i % 23))} for i in range(200)]
+    with open(tmp_path / "c.jsonl", "w") as f:
+        f.writelines(json.dumps(r) + "\n" for r in rows)
+    for name in ("a", "b"):
+        preprocess_data.main(["--input", str(tmp_path / "c.jsonl"), "--output_prefix", str(tmp_path / name),
+                              "--tokenizer_type", "NullTokenizer", "--vocab_file", "100", "--workers", "1",
+                              "--chunk_size", "8", "--append_eod"])
+    irows = [{"input": " ".join(str((i + j) % 40) for j in range(3 + i % 9)),
+              "output": " ".join(str((i * 3 + j) % 40) for j in range(2 + i % 7)), "sys": "9 9"} for i in range(120)]
+    with open(tmp_path / "i.jsonl", "w") as f:
+        f.writelines(json.dumps(r) + "\n" for r in irows)
+    preprocess_instruct_data.main(["--input", str(tmp_path / "i.jsonl"), "--output_prefix", str(tmp_path / "inst"),
+                                   "--system_key", "sys", "--tokenizer_type", "NullTokenizer", "--vocab_file", "100",
+                                   "--workers", "1", "--chunk_size", "4"])
+    blend = ["--data_path", "0.3", str(tmp_path / "a_text_document"), "0.7", str(tmp_path / "b_text_document")]
+    one = _run("finetune.py", LLAMA_TINY + blend)
+    train1, final1 = _loss_lines(one)
+    assert len(train1) == 6 and len(final1) == 1 and train1[-1] < train1[0]
+    assert one.count("validation loss at iteration") == 2           # eval_interval 3 over 6 iterations
+    two = _run_ranks("finetune.py", LLAMA_TINY + blend + ["--num_workers", "2"], 2)
+    train2, final2 = _loss_lines(two)
+    assert train2[:6] == pytest.approx(train1, rel=1e-4) and final2[0] == pytest.approx(final1[0], rel=1e-4)
+    inst = _run_ranks("finetune.py", LLAMA_TINY + ["--data_path", str(tmp_path / "inst"), "--data_type", "instruction",
+                                                   "--variable_seq_lengths", "--tensor_model_parallel_size", "2",
+                                                   "--pipeline_model_parallel_size", "2", "--metrics", "all"], 4)
+    train3, final3 = _loss_lines(inst)
+    assert len(train3) >= 6 and len(final3) >= 1 and all(l == l and l > 0 for l in train3)
+    assert "instruct accuracy" in inst and "count loss mask" in inst
