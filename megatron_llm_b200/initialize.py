@@ -60,6 +60,24 @@ def _use_side_stream_for_graphs():
         torch.cuda.set_stream(side)
 
 
+def _destroy_gloo_group():
+    """Orderly exit of a CPU (gloo) run.  gloo sends complete locally, so a rank that finishes first (the first
+    pipeline stage of an evaluation loop, say) would close its sockets while its peers still have receives to post:
+    wait for everybody -- bounded, and not at all after an uncaught exception -- before tearing the group down."""
+    import sys
+    if not dist.is_initialized():
+        return
+    try:
+        if getattr(sys, "last_value", None) is None and getattr(sys, "last_exc", None) is None:
+            dist.monitored_barrier(timeout=timedelta(seconds=60))
+    except Exception:
+        pass
+    try:
+        dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def _initialize_distributed():
     args = get_args()
     device_count = torch.cuda.device_count() if use_cuda() else 0
@@ -85,6 +103,13 @@ def _initialize_distributed():
             kwargs["device_id"] = torch.device("cuda", torch.cuda.current_device())
         dist.init_process_group(backend=args.distributed_backend, world_size=args.world_size, rank=args.rank,
                                 timeout=timedelta(minutes=10), **kwargs)
+        if args.distributed_backend == "gloo":
+            # a gloo group that is still alive when the interpreter finalises aborts the process ("terminate called
+            # without an active exception") whenever the ranks do not exit in lock step, turning a finished run into
+            # a non-zero exit code; the group this function created is torn down at exit.  (NCCL runs keep their
+            # validated behaviour: bench.py shuts down explicitly, with a watchdog.)
+            import atexit
+            atexit.register(_destroy_gloo_group)
     if ps.model_parallel_is_initialized():
         print("model parallel is already initialized")
     else:

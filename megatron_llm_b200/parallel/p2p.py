@@ -95,6 +95,9 @@ def _communicate(tensor_send_next: Optional[torch.Tensor], tensor_send_prev: Opt
     tensor_recv_prev = tensor_recv_next = None
     override_scatter_gather = False
     if not args.variable_seq_lengths:
+        if tensor_shape is None:
+            # inference / downstream-task callers give no shape (reference p2p_communication.py:132-137)
+            tensor_shape = (args.seq_length, args.micro_batch_size, args.hidden_size)
         recv_prev_shape = recv_next_shape = tensor_shape
     else:
         recv_prev_shape, recv_next_shape = _communicate_shapes(tensor_send_next, tensor_send_prev, recv_prev,
