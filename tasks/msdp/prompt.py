@@ -70,7 +70,12 @@ def generate_samples_by_calling_api():
 def model_provider(pre_process=True, post_process=True):
     import finetune
     print_rank_0("building model for prompting ...")
-    return finetune.model_provider(pre_process, post_process)
+    model = finetune.model_provider(pre_process, post_process)
+    # sampling needs the full-vocabulary logits on every TP rank (the reference builds this model with
+    # parallel_output=True, tasks/msdp/prompt.py:21-26, which only works for TP = 1)
+    from megatron_llm_b200.utils import unwrap_model
+    unwrap_model(model).parallel_output = False
+    return model
 
 
 def generate_samples_by_prompting_input_from_file(model):

@@ -195,3 +195,46 @@ def test_msdp_metrics_and_preprocessing(tmp_path):
     (tmp_path / "guess.txt").write_text("the cat is a feline\nwhatever\n")
     p, r, f = evaluate_f1(str(tmp_path / "guess.txt"), str(tmp_path / "k.txt"))
     assert f > 0.9
+
+
+def test_msdp_prompting_end_to_end(tmp_path):
+    """tasks/msdp/main.py MSDP-PROMPT (knowledge and response stages) with a byte-level GPT-2 tokenizer built here,
+    single rank and TP2 (same padded vocabulary, master-seeded CPU init -> same generations: the model must be built
+    with full-vocabulary logits), PP2, then MSDP-EVAL-F1 on files."""
+    from megatron_llm_b200.tokenizer.gpt2_tokenization import bytes_to_unicode
+    from tests.test_pretrain_entries import _run_ranks
+    vocab = {c: i for i, c in enumerate(bytes_to_unicode().values())}
+    merges = [("h", "e"), ("l", "l"), ("Ġ", "t"), ("Ġ", "a")]
+    for a, b in merges:
+        vocab[a + b] = len(vocab)
+    vocab["<|endoftext|>"] = len(vocab)
+    (tmp_path / "vocab.json").write_text(json.dumps(vocab))
+    (tmp_path / "merges.txt").write_text("#version: 0.2\n" + "\n".join(" ".join(m) for m in merges) + "\n")
+    (tmp_path / "k_prompts.jsonl").write_text(json.dumps({"cats do cats purr": [
+        "( do cats purr ) cats => cats purr when happy", "( what is a cat ) cats => a small animal"]}) + "\n")
+    (tmp_path / "r_prompts.txt").write_text("Topic: cats. User says: hi. We know that: cats purr. System replies: yes\n")
+    (tmp_path / "test.txt").write_text("cats\thello [SEP] do cats purr\tcats purr\tyes they do\n")
+    model = ["--model_name", "gpt", "--num_layers", "2", "--hidden_size", "32", "--num_attention_heads", "4",
+             "--seq_length", "256", "--max_position_embeddings", "256", "--micro_batch_size", "1", "--tokenizer_type",
+             "GPT2BPETokenizer", "--vocab_file", str(tmp_path / "vocab.json"), "--merge_file",
+             str(tmp_path / "merges.txt"), "--out_seq_length", "8", "--seed", "3", "--use_cpu_initialization"]
+    results = {}
+    for name, world, extra in (("w1", 1, ["--make_vocab_size_divisible_by", "16"]),
+                               ("tp2", 2, ["--make_vocab_size_divisible_by", "8", "--tensor_model_parallel_size", "2"]),
+                               ("pp2", 2, ["--make_vocab_size_divisible_by", "16", "--pipeline_model_parallel_size",
+                                           "2"])):
+        for ptype, pfile in (("knowledge", "k_prompts.jsonl"), ("response", "r_prompts.txt")):
+            out = tmp_path / f"{name}_{ptype}.out"
+            _run_ranks("tasks/msdp/main.py", model + extra + [
+                "--task", "MSDP-PROMPT", "--prompt_type", ptype, "--prompt_file", str(tmp_path / pfile),
+                "--sample_input_file", str(tmp_path / "test.txt"), "--sample_output_file", str(out),
+                "--num_prompt_examples", "2"], world)
+            results[name, ptype] = out.read_bytes()
+            assert results[name, ptype].endswith(b"\n") and results[name, ptype].count(b"\n") == 1
+    assert results["tp2", "knowledge"] == results["w1", "knowledge"]
+    assert results["tp2", "response"] == results["w1", "response"]
+    (tmp_path / "guess.txt").write_text("cats purr when happy\n")
+    (tmp_path / "answer.txt").write_text("cats purr\n")
+    out = _run_ranks("tasks/msdp/main.py", model + ["--task", "MSDP-EVAL-F1", "--guess_file", str(tmp_path / "guess.txt"),
+                                                    "--answer_file", str(tmp_path / "answer.txt")], 1)
+    assert "Precision: 0.5000; recall: 1.0000; f1: 0.6667" in out
