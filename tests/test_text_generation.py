@@ -186,3 +186,48 @@ def _server_worker(rank, world, port):
 def test_rest_server_roundtrip():
     from tests.dist_utils import free_port
     run_distributed(_server_worker, 1, free_port())
+
+
+def test_server_tool_with_tensor_parallel_ranks():
+    """tools/run_text_generation_server.py as two TP ranks (what torchrun starts): rank 0 serves HTTP and broadcasts the
+    op code, rank 1 sits in the generate / beam-search loop.  Greedy, beam and top-p requests must all come back."""
+    import subprocess
+    import time
+    from tests.dist_utils import free_port
+    port, http = free_port(), free_port()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, MLB200_FORCE_CPU="1", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(r),
+                   WORLD_SIZE="2", LOCAL_RANK=str(r), CUDA_VISIBLE_DEVICES="")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(ROOT, "tools", "run_text_generation_server.py")]
+                                      + LLAMA + COMMON + ["--tensor_model_parallel_size", "2", "--port", str(http)],
+                                      env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=ROOT))
+
+    def put(body):
+        data = json.dumps(body).encode()
+        for _ in range(300):
+            try:
+                req = urllib.request.Request(f"http://127.0.0.1:{http}/api", data=data, method="PUT",
+                                             headers={"Content-Type": "application/json"})
+                with urllib.request.urlopen(req, timeout=120) as resp:
+                    return json.loads(resp.read())
+            except (ConnectionRefusedError, urllib.error.URLError):
+                assert all(p.poll() is None for p in procs), "a server rank exited"
+                time.sleep(0.3)
+        raise AssertionError("server did not come up")
+    try:
+        greedy = put({"prompts": ["5 9 13 2", "7 7 1"], "tokens_to_generate": 4, "top_k": 1, "logprobs": True})
+        assert [len(t.split()) for t in greedy["text"]] == [8, 8] and len(greedy["logprobs"]) == 2
+        again = put({"prompts": ["5 9 13 2", "7 7 1"], "tokens_to_generate": 4, "top_k": 1})
+        assert again["text"] == greedy["text"]
+        beam = put({"prompts": ["5 9 13 2"], "tokens_to_generate": 4, "beam_width": 2})
+        assert len(beam["text"]) == 2 and beam["scores"][0] >= beam["scores"][1]
+        assert all(t.startswith("5 9 13 2") for t in beam["text"])
+        sampled = put({"prompts": ["1 2 3"], "tokens_to_generate": 3, "top_p": 0.9, "random_seed": 4})
+        assert len(sampled["text"][0].split()) == 6
+    finally:
+        for p in procs:
+            if p.poll() is None:
+                p.kill()
+        logs = [p.communicate()[0] for p in procs]
+    assert not any("Traceback" in log for log in logs), logs
