@@ -188,3 +188,33 @@ def test_finetune_entry_on_preprocessed_gpt_and_instruction_data(tmp_path):
     train3, final3 = _loss_lines(inst)
     assert len(train3) >= 6 and len(final3) >= 1 and all(l == l and l > 0 for l in train3)
     assert "instruct accuracy" in inst and "count loss mask" in inst
+
+
+def test_bert_checkpoint_reshards_to_tp2_and_pp2(tmp_path):
+    """tools/checkpoint_util.py --model_type BERT: pooler, LM head (incl. its vocab-parallel output bias, which the
+    reference's tool forgets) and binary head travel; continuing from the resharded checkpoint under TP2 and under PP2
+    gives the single-rank LM / SOP losses."""
+    import re
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from tools import checkpoint_util
+    vocab = _preprocess(tmp_path)
+    base = COMMON + ["--seq_length", "48", "--max_position_embeddings", "48", "--vocab_file", str(vocab), "--data_path",
+                     str(tmp_path / "data_text_sentence"), "--make_vocab_size_divisible_by", "8", "--seed", "11"]
+    _run("pretrain_bert.py", base + ["--save", str(tmp_path / "ck"), "--save_interval", "2"])
+    cont = list(base)
+    cont[cont.index("--train_iters") + 1] = "4"
+    cont += ["--finetune", "--no_load_optim", "--no_load_rng"]
+
+    def losses(out):
+        return re.findall(r"lm loss: ([0-9.E+-]+).*?sop loss: ([0-9.E+-]+)", out)
+    ref = losses(_run("pretrain_bert.py", cont + ["--load", str(tmp_path / "ck")]))
+    assert len(ref) == 4
+    for tp, pp in ((2, 1), (1, 2)):
+        dst = tmp_path / f"ck_tp{tp}_pp{pp}"
+        checkpoint_util.main(["--model_type", "BERT", "--load_dir", str(tmp_path / "ck"), "--save_dir", str(dst),
+                              "--target_tensor_parallel_size", str(tp), "--target_pipeline_parallel_size", str(pp)])
+        out = _run_ranks("pretrain_bert.py", cont + ["--load", str(dst), "--tensor_model_parallel_size", str(tp),
+                                                     "--pipeline_model_parallel_size", str(pp)], 2)
+        got = losses(out)
+        assert [tuple(map(float, g)) for g in got] == pytest.approx([tuple(map(float, r)) for r in ref], rel=2e-4), \
+            (tp, pp, got, ref)

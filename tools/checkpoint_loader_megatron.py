@@ -214,8 +214,13 @@ def _load_checkpoint(queue, args):
             put("pooler", {"weight": pooler["dense.weight"], "bias": pooler["dense.bias"]})
         if "lm_head" in last_model:
             h = last_model["lm_head"]
-            put("lm head", {"dense weight": h["dense.weight"], "dense bias": h["dense.bias"],
-                            "layernorm weight": h["layernorm.weight"], "layernorm bias": h["layernorm.bias"]})
+            m = {"dense weight": h["dense.weight"], "dense bias": h["dense.bias"],
+                 "layernorm weight": h["layernorm.weight"], "layernorm bias": h["layernorm.bias"]}
+            if "bias" in h:
+                # vocab-parallel output bias (the reference's loader drops it and the saver re-initialises it to
+                # zero, checkpoint_loader_megatron.py:318-331; it is a trained parameter, so it travels here)
+                m["vocab bias"] = torch.cat([f["model"]["lm_head"]["bias"] for f in last_files], dim=0)
+            put("lm head", m)
         if md.bert_binary_head and "binary_head" in last_model:
             put("binary head", {"weight": last_model["binary_head"]["weight"],
                                 "bias": last_model["binary_head"]["bias"]})

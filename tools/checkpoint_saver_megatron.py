@@ -177,6 +177,10 @@ def save_checkpoint(queue, args):
                     sys.exit("Loader exited, exiting saver")
                 name = msg["name"]
                 print(f"received {name}")
+                bias_shards = None
+                if name == "lm head" and "vocab bias" in msg:
+                    b = resize_vocab(msg["vocab bias"].unsqueeze(1), true_size, target_vocab).squeeze(1)
+                    bias_shards = torch.chunk(b.to(dtype), tp, dim=0)
                 for t in range(tp):
                     if name == "pooler":
                         states[t]["language_model"]["pooler"] = {"dense.weight": msg["weight"].to(dtype),
@@ -186,6 +190,8 @@ def save_checkpoint(queue, args):
                                                 "dense.bias": msg["dense bias"].to(dtype),
                                                 "layernorm.weight": msg["layernorm weight"].to(dtype),
                                                 "layernorm.bias": msg["layernorm bias"].to(dtype)}
+                        if bias_shards is not None:
+                            states[t]["lm_head"]["bias"] = bias_shards[t].clone()
                     elif name == "binary head":
                         states[t]["binary_head"] = {"weight": msg["weight"].to(dtype), "bias": msg["bias"].to(dtype)}
                     elif args.checking:
