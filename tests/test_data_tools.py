@@ -178,3 +178,36 @@ def test_mips_index():
     ref = np.argsort(-(q @ np.float32(np.float16(emb)).T), axis=1)[:, :4] + 1000
     assert (ids == ref).all()
     assert index.search_mips_index(q, 4, reconstruct=True).shape == (5, 4, 16)
+
+
+def test_instruction_preprocessing_with_sentencepiece_chatml_tokens(tmp_path):
+    """preprocess_instruct_data.py with a SentencePiece model + ``--vocab_extra_ids_list "<|im_start|>,<|im_end|>"``:
+    every turn is wrapped in the two ChatML tokens (single ids appended after Megatron's special tokens), roles are
+    aligned with the tokens, and the validation metrics' instruct mask drops the scaffolding around each turn."""
+    import preprocess_instruct_data
+    from megatron_llm_b200.data import indexed_dataset
+    from megatron_llm_b200.data.instruction_dataset import Role
+    from megatron_llm_b200.tokenizer.tokenizer import _SentencePieceTokenizer
+    from tests.test_weights_conversion import _tiny_sentencepiece_model
+    vocab_file = _tiny_sentencepiece_model(tmp_path)
+    words = ["alpha", "beta", "gamma", "delta", "epsilon", "zeta", "eta", "theta"]
+    rows = [{"input": " ".join(words[(i + j) % 8] for j in range(3 + i % 5)),
+             "output": " ".join(words[(i * 3 + j) % 8] for j in range(2 + i % 4)), "sys": "alpha beta"} for i in range(12)]
+    _write_jsonl(tmp_path / "i.jsonl", rows)
+    extra = "<|im_start|>,<|im_end|>"
+    preprocess_instruct_data.main(["--input", str(tmp_path / "i.jsonl"), "--output_prefix", str(tmp_path / "inst"),
+                                   "--system_key", "sys", "--tokenizer_type", "SentencePieceTokenizer", "--vocab_file",
+                                   str(vocab_file), "--vocab_extra_ids_list", extra, "--workers", "1", "--chunk_size", "4"])
+    tok = _SentencePieceTokenizer(str(vocab_file), vocab_extra_ids_list=extra)
+    start, end = tok.vocab["<|im_start|>"], tok.vocab["<|im_end|>"]
+    assert (start, end) == (85, 86)                           # 80 pieces + <CLS> <SEP> <EOD> <MASK> <PAD>, then ours
+    text = indexed_dataset.make_dataset(str(tmp_path / "inst-text"), "mmap")
+    role = indexed_dataset.make_dataset(str(tmp_path / "inst-role"), "mmap")
+    assert len(text) == len(role) == 12
+    for t, r in zip(text, role):
+        t, r = t.tolist(), r.tolist()
+        assert len(t) == len(r) and t[0] == start and t[-1] == end and t.count(start) == t.count(end) == 3
+        assert r == sorted(r) and set(r) == {Role.system.value, Role.prompter.value, Role.assistant.value}
+        assert all(r[i] != r[i - 1] for i in range(1, len(t)) if t[i] == start)      # roles switch at <|im_start|>
+    decoded = tok.detokenize(text[0].tolist())
+    assert decoded.count("<|im_start|>") == 3 and "alpha beta" in decoded
