@@ -552,9 +552,10 @@ class ParallelTransformer(MegatronModule):
                 "num_layers_per_stage must be divisible by virtual_pipeline_model_parallel_size"
             assert model_type != ModelType.encoder_and_decoder
             self.num_layers = self.num_layers // args.virtual_pipeline_model_parallel_size
+            first = 1 if args.standalone_embedding_stage else 0
             offset = ps.get_virtual_pipeline_model_parallel_rank() * (
                 args.num_layers // args.virtual_pipeline_model_parallel_size) + \
-                (ps.get_pipeline_model_parallel_rank() * self.num_layers)
+                (max(0, ps.get_pipeline_model_parallel_rank() - first) * self.num_layers)
         else:
             if model_type == ModelType.encoder_and_decoder and ps.get_pipeline_model_parallel_world_size() > 1:
                 pipeline_rank = ps.get_pipeline_model_parallel_rank()
@@ -563,7 +564,11 @@ class ParallelTransformer(MegatronModule):
                 else:
                     offset = (pipeline_rank - args.pipeline_model_parallel_split_rank) * self.num_layers
             else:
-                offset = ps.get_pipeline_model_parallel_rank() * self.num_layers
+                # with a standalone embedding stage, stage 0 owns no layer and stage r >= 1 owns the (r-1)-th slice
+                # (the reference numbers the layers as if stage 0 owned one as well and then indexes its per-layer
+                # tables out of range, transformer.py:1075)
+                first = 1 if args.standalone_embedding_stage else 0
+                offset = max(0, ps.get_pipeline_model_parallel_rank() - first) * self.num_layers
 
         if self.num_layers == 0:
             self.num_layers = 1

@@ -262,3 +262,11 @@ def test_reshard_other_families_tp2_pp2_and_back(tmp_path, family):
     b = _flat_tensors(torch.load(back / sub / "mp_rank_00" / "model_optim_rng.pt", weights_only=False)["model"])
     assert set(a) == set(b)
     assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_standalone_embedding_stage_trains(tmp_path):
+    """--standalone_embedding_stage with PP=3: stage 0 holds only the embedding (a no-op layer), the 8 layers are split
+    over stages 1 and 2 and numbered 1..8 (the reference numbers them 5..12 and indexes its per-layer tables out of
+    range).  Smoke test: three steps, finite decreasing-ish losses."""
+    losses = _run(3, ["--pipeline_model_parallel_size", "3", "--standalone_embedding_stage"], tmp_path / "loss.json")
+    assert len(losses) == 3 and all(l == l and 3.0 < l < 6.0 for l in losses), losses
