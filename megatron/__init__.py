@@ -36,6 +36,11 @@ _ALIASES = {
     "megatron.p2p_communication": f"{_T}.parallel.p2p",
     "megatron.schedules": f"{_T}.parallel.schedules",
     "megatron.fused_kernels": f"{_T}.ops",
+    # very old checkpoints pickle their loss scaler under these paths (reference checkpointing.py:462-474)
+    "megatron.fp16_deprecated": f"{_T}.fp16_deprecated",
+    "megatron.fp16_deprecated.loss_scaler": f"{_T}.fp16_deprecated.loss_scaler",
+    "megatron.fp16": f"{_T}.fp16_deprecated",
+    "megatron.fp16.loss_scaler": f"{_T}.fp16_deprecated.loss_scaler",
 }
 # modules whose name is identical below the package root
 for _name in ("arguments", "checkpointing", "dist_signal_handler", "global_vars", "initialize", "memory", "microbatches",

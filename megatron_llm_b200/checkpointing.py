@@ -11,6 +11,7 @@ Layout (unchanged so checkpoints carry over):
 """
 from __future__ import annotations
 
+import contextlib
 import os
 import random
 import sys
@@ -259,6 +260,27 @@ def _torch_load(path):
     return torch.load(path, map_location="cpu", weights_only=False)
 
 
+@contextlib.contextmanager
+def legacy_pickle_modules():
+    """Module paths old checkpoints were pickled under: ``megatron.*`` (the reference; aliased onto this package by the
+    ``megatron`` compat package) and ``fp16.loss_scaler`` (its ancestors' loss scaler, reference checkpointing.py:
+    462-474).  The unpickler imports the parent package too, so a stub ``fp16`` is registered for the duration."""
+    import types
+    import megatron  # noqa: F401  (compat alias package at the repo root)
+    from .fp16_deprecated import loss_scaler
+    added = []
+    if "fp16.loss_scaler" not in sys.modules:
+        parent = types.ModuleType("fp16")
+        parent.loss_scaler = loss_scaler
+        sys.modules["fp16"], sys.modules["fp16.loss_scaler"] = parent, loss_scaler
+        added = ["fp16", "fp16.loss_scaler"]
+    try:
+        yield
+    finally:
+        for name in added:
+            sys.modules.pop(name, None)
+
+
 def _load_base_checkpoint(load_dir, use_distributed_optimizer, rank0=False, iteration=None):
     """Returns (model_state_dict, optim_state_dict, release)."""
     tracker = get_checkpoint_tracker_filename(load_dir)
@@ -291,11 +313,10 @@ def _load_base_checkpoint(load_dir, use_distributed_optimizer, rank0=False, iter
         optim_state = _torch_load(optim_name) if (use_distributed_optimizer and os.path.isfile(optim_name)) \
             else model_state
     except ModuleNotFoundError:
-        # checkpoints written by the reference pickle ``megatron.*`` classes: alias them to this package
-        import megatron  # noqa: F401  (compat alias package at the repo root)
-        model_state = _torch_load(model_name)
-        optim_state = _torch_load(optim_name) if (use_distributed_optimizer and os.path.isfile(optim_name)) \
-            else model_state
+        with legacy_pickle_modules():
+            model_state = _torch_load(model_name)
+            optim_state = _torch_load(optim_name) if (use_distributed_optimizer and os.path.isfile(optim_name)) \
+                else model_state
     except BaseException as e:
         print_rank_0("could not load the checkpoint")
         print_rank_0(e)

@@ -153,10 +153,9 @@ class BiEncoderModel(MegatronModule):
         try:
             state_dict = torch.load(name, map_location="cpu", weights_only=False)
         except ModuleNotFoundError:
-            from ..fp16_deprecated import loss_scaler
-            sys.modules["fp16.loss_scaler"] = sys.modules["megatron.fp16.loss_scaler"] = loss_scaler
-            state_dict = torch.load(name, map_location="cpu", weights_only=False)
-            sys.modules.pop("fp16.loss_scaler", None), sys.modules.pop("megatron.fp16.loss_scaler", None)
+            from ..checkpointing import legacy_pickle_modules
+            with legacy_pickle_modules():
+                state_dict = torch.load(name, map_location="cpu", weights_only=False)
         version = state_dict.get("checkpoint_version", 0)
         lm = state_dict["model"]["language_model"]
         towers = [self.model] if self.biencoder_shared_query_context_model else \

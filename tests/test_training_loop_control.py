@@ -149,3 +149,42 @@ def test_validation_metrics_tensorboard_and_timers(tmp_path):
     for tag in ("learning-rate", "lm loss", "lm loss validation", "ppl validation", "lm accuracy validation"):
         assert tag in tags, (tag, sorted(tags)[:40])
     assert [e.step for e in acc.Scalars("lm loss")] == [1, 2, 3, 4]
+
+
+def test_checkpoints_pickled_with_legacy_module_paths_load(tmp_path):
+    """Checkpoints written by the reference (``megatron.*`` class paths, e.g. the args' position-embedding enum) and by
+    its ancestors (a loss scaler pickled as ``fp16.loss_scaler.DynamicLossScaler`` / ``megatron.fp16_deprecated...``)
+    must unpickle: the file written here is re-pickled with those module paths and then resumed from."""
+    import pickle
+    import types
+    import torch
+    ckpt = str(tmp_path / "ckpt")
+    _run(["--train_iters", "3", "--save", ckpt, "--save_interval", "2", "--exit_interval", "2"])
+    path = os.path.join(ckpt, "iter_0000002", "mp_rank_00", "model_optim_rng.pt")
+    state = torch.load(path, weights_only=False)
+    sys.path.insert(0, ROOT)
+    from megatron_llm_b200.fp16_deprecated import loss_scaler as shim
+    # objects whose classes claim to live in the legacy modules
+    old = types.ModuleType("fp16.loss_scaler")
+    old.DynamicLossScaler = type("DynamicLossScaler", (), {"__module__": "fp16.loss_scaler"})
+    mid = types.ModuleType("megatron.fp16_deprecated.loss_scaler")
+    mid.LossScaler = type("LossScaler", (), {"__module__": "megatron.fp16_deprecated.loss_scaler"})
+    sys.modules["fp16"], sys.modules["fp16.loss_scaler"] = types.ModuleType("fp16"), old
+    saved_mid = sys.modules.get("megatron.fp16_deprecated.loss_scaler")
+    sys.modules["megatron.fp16_deprecated.loss_scaler"] = mid
+    try:
+        a, b = old.DynamicLossScaler(), mid.LossScaler()
+        a.cur_scale, b.cur_scale = 4096.0, 1.0
+        state["legacy_scaler"], state["legacy_scaler2"] = a, b
+        torch.save(state, path)
+    finally:
+        sys.modules.pop("fp16", None), sys.modules.pop("fp16.loss_scaler", None)
+        if saved_mid is None:
+            sys.modules.pop("megatron.fp16_deprecated.loss_scaler", None)
+        else:
+            sys.modules["megatron.fp16_deprecated.loss_scaler"] = saved_mid
+    with open(path, "rb") as f:
+        assert b"fp16.loss_scaler" in f.read()
+    assert hasattr(shim, "DynamicLossScaler") and hasattr(shim, "LossScaler")
+    r = _run(["--train_iters", "3", "--load", ckpt])
+    assert [i for i, *_ in _iters(r.stdout)] == [3]
