@@ -25,12 +25,13 @@ struct AttnBwdParams {
   const float* lse;     // [b, heads, seq]
   const float* delta;   // [b, heads, seq]
   RowAddr dq, dk, dv;   // strided outputs ([seq, batch, heads, 128])
+  DropoutParams drop;   // (read by the AF_DROPOUT instantiations only; same p and seed as the forward)
 };
 
 // ------------------------------------------------------------------------------------------------
 // delta = rowsum(dO * O)
 // ------------------------------------------------------------------------------------------------
-template <int D>
+template <int D, int F>
 __global__ void attn_delta_kernel(RowAddr o, RowAddr dout, float* __restrict__ delta, int seq, int batch, int heads) {
   const int warps_per_block = blockDim.x >> 5;
   const long long row_id = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -44,11 +45,11 @@ __global__ void attn_delta_kernel(RowAddr o, RowAddr dout, float* __restrict__ d
   if constexpr (D == 128) {          // 4 elements per lane
     const uint2 a = *reinterpret_cast<const uint2*>(o.row(s, b, h) + lane * 4);
     const uint2 g = *reinterpret_cast<const uint2*>(dout.row(s, b, h) + lane * 4);
-    const float2 a0 = unpack_bf16x2(a.x), a1 = unpack_bf16x2(a.y), g0 = unpack_bf16x2(g.x), g1 = unpack_bf16x2(g.y);
+    const float2 a0 = unpack_h2<F>(a.x), a1 = unpack_h2<F>(a.y), g0 = unpack_h2<F>(g.x), g1 = unpack_h2<F>(g.y);
     v = a0.x * g0.x + a0.y * g0.y + a1.x * g1.x + a1.y * g1.y;
   } else {                           // 2 elements per lane
-    const float2 a0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(o.row(s, b, h) + lane * 2));
-    const float2 g0 = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dout.row(s, b, h) + lane * 2));
+    const float2 a0 = unpack_h2<F>(*reinterpret_cast<const uint32_t*>(o.row(s, b, h) + lane * 2));
+    const float2 g0 = unpack_h2<F>(*reinterpret_cast<const uint32_t*>(dout.row(s, b, h) + lane * 2));
     v = a0.x * g0.x + a0.y * g0.y;
   }
   v = warp_sum(v);
@@ -66,8 +67,9 @@ constexpr int AT_ROWS64 = 64 * 128;   // byte offset of tile row 64 inside a 64-
 // TMEM column map (dK/dV kernel)
 constexpr uint32_t KV_ST = 0, KV_DPT = 128, KV_DV = 256, KV_DK = 384;
 constexpr int BWD_SMEM = 6 * AT_TILE_BYTES + 2 * 2 * 128 * 4 + 256 + 1024;   // K, V, 2 x (Q, dO), 2 x (lse, D)
+constexpr int BWD_SMEM_DROPOUT = BWD_SMEM + 2 * 128 * 4;                     // + 2 x per-query dropout row keys
 
-template <int D>
+template <int D, int F>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                      const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -88,6 +90,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   uint64_t* pds_full = bars + 7;   // [2] P^T and dS^T of half x written (4 warps)
   uint64_t* acc_done = bars + 9;   // all MMAs retired (epilogue)
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 10);
+  uint32_t* sRowKey = reinterpret_cast<uint32_t*>(bars) + 64;    // [2][128], behind the 256-byte barrier block (dropout)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int j = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -116,8 +119,9 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
-  constexpr uint32_t ID_KK = make_idesc_f16(AT_N, 64, false, false, true);     // [128 kv] x [64 q], both K-major smem
-  constexpr uint32_t ID_TS = make_idesc_f16(AT_N, D, false, true, true);    // A from TMEM, B MN-major smem
+  constexpr bool BF16 = (F & AF_FP16) == 0;
+  constexpr uint32_t ID_KK = make_idesc_f16(AT_N, 64, false, false, BF16);     // [128 kv] x [64 q], both K-major smem
+  constexpr uint32_t ID_TS = make_idesc_f16(AT_N, D, false, true, BF16);    // A from TMEM, B MN-major smem
 
   if (warp == 0) {
     if (lane == 0) {
@@ -196,6 +200,12 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
         const long long stat = ((long long)b * p.heads + hq) * p.seq + q0 + x * 64 + c;
         if (r < 64) sLse[st * 128 + x * 64 + c] = p.lse[stat] * 1.4426950408889634f;
         else sD[st * 128 + x * 64 + c] = p.delta[stat];
+        if constexpr ((F & AF_DROPOUT) != 0) {
+          if (r < 64)
+            sRowKey[st * 128 + x * 64 + c] =
+                drop_row_key(p.drop.seed_lo, drop_head_key(p.drop.seed_hi, uint32_t(b * p.heads + hq)),
+                             uint32_t(q0 + x * 64 + c));
+        }
       }
       if (x == 0) asm volatile("bar.sync 2, 128;" ::: "memory");
       else asm volatile("bar.sync 3, 128;" ::: "memory");
@@ -207,6 +217,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
       const int qhi = (p.window > 0) ? kv + p.window - q0 - x * 64 : (1 << 30);   // columns > qhi lost it from the window
       const float* lse_s = sLse + st * 128 + x * 64;
       const float* d_s = sD + st * 128 + x * 64;
+      [[maybe_unused]] const uint32_t* rk_s = sRowKey + st * 128 + x * 64;
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t s[32], dp[32];
@@ -222,11 +233,20 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
             const int col = c * 32 + 2 * i + e;     // query index inside the half
             float pe = fast_exp2(fmaf(__uint_as_float(s[2 * i + e]), p.scale_log2, -lse_s[col]));
             if (need_mask) pe = (col < qlo || col > qhi) ? 0.f : pe;
-            pv[e] = pe;
-            dv[e] = pe * (__uint_as_float(dp[2 * i + e]) - d_s[col]) * p.scale;
+            if constexpr ((F & AF_DROPOUT) != 0) {
+              // O = (P o Z) V with Z = keep / (1 - p):  dV += (P o Z)^T dO,  dS = P o (Z o dP - D)
+              const bool dropped = drop_is_dropped(drop_bytes(rk_s[col], uint32_t(kv) >> 2), uint32_t(kv),
+                                                   p.drop.threshold);
+              const float dpz = dropped ? 0.f : __uint_as_float(dp[2 * i + e]) * p.drop.inv_keep;
+              pv[e] = dropped ? 0.f : pe * p.drop.inv_keep;
+              dv[e] = pe * (dpz - d_s[col]) * p.scale;
+            } else {
+              pv[e] = pe;
+              dv[e] = pe * (__uint_as_float(dp[2 * i + e]) - d_s[col]) * p.scale;
+            }
           }
-          pk[i] = pack_bf16x2(pv[0], pv[1]);
-          dk[i] = pack_bf16x2(dv[0], dv[1]);
+          pk[i] = pack_h2<F>(pv[0], pv[1]);
+          dk[i] = pack_h2<F>(dv[0], dv[1]);
         }
         tmem_st_32x16(st_addr + c * 16, pk);     // in place: only already-consumed columns of this half
         tmem_st_32x16(dp_addr + c * 16, dk);
@@ -254,15 +274,15 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(a[i * 8 + 0]), __uint_as_float(a[i * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(a[i * 8 + 2]), __uint_as_float(a[i * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(a[i * 8 + 4]), __uint_as_float(a[i * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(a[i * 8 + 6]), __uint_as_float(a[i * 8 + 7]));
+          o.x = pack_h2<F>(__uint_as_float(a[i * 8 + 0]), __uint_as_float(a[i * 8 + 1]));
+          o.y = pack_h2<F>(__uint_as_float(a[i * 8 + 2]), __uint_as_float(a[i * 8 + 3]));
+          o.z = pack_h2<F>(__uint_as_float(a[i * 8 + 4]), __uint_as_float(a[i * 8 + 5]));
+          o.w = pack_h2<F>(__uint_as_float(a[i * 8 + 6]), __uint_as_float(a[i * 8 + 7]));
           d0[i] = o;
-          o.x = pack_bf16x2(__uint_as_float(bb[i * 8 + 0]), __uint_as_float(bb[i * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(bb[i * 8 + 2]), __uint_as_float(bb[i * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(bb[i * 8 + 4]), __uint_as_float(bb[i * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(bb[i * 8 + 6]), __uint_as_float(bb[i * 8 + 7]));
+          o.x = pack_h2<F>(__uint_as_float(bb[i * 8 + 0]), __uint_as_float(bb[i * 8 + 1]));
+          o.y = pack_h2<F>(__uint_as_float(bb[i * 8 + 2]), __uint_as_float(bb[i * 8 + 3]));
+          o.z = pack_h2<F>(__uint_as_float(bb[i * 8 + 4]), __uint_as_float(bb[i * 8 + 5]));
+          o.w = pack_h2<F>(__uint_as_float(bb[i * 8 + 6]), __uint_as_float(bb[i * 8 + 7]));
           d1[i] = o;
         }
       }
@@ -277,7 +297,7 @@ attn_bwd_dkdv_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_const
 constexpr uint32_t Q_S = 0, Q_DP = 128, Q_DQ = 256;
 constexpr int BWD_DQ_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;   // Q, dO, 2 x (K, V)
 
-template <int D>
+template <int D, int F>
 __global__ void __launch_bounds__(BW_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO,
@@ -322,8 +342,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
-  constexpr uint32_t ID_KK = make_idesc_f16(AT_M, 64, false, false, true);
-  constexpr uint32_t ID_TS = make_idesc_f16(AT_M, D, false, true, true);
+  constexpr bool BF16 = (F & AF_FP16) == 0;
+  constexpr uint32_t ID_KK = make_idesc_f16(AT_M, 64, false, false, BF16);
+  constexpr uint32_t ID_TS = make_idesc_f16(AT_M, D, false, true, BF16);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -387,6 +408,9 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const long long stat = ((long long)b * p.heads + h) * p.seq + row;
     const float lse2 = p.lse[stat] * 1.4426950408889634f;
     const float dlt = p.delta[stat];
+    uint32_t row_key = 0;
+    if constexpr ((F & AF_DROPOUT) != 0)
+      row_key = drop_row_key(p.drop.seed_lo, drop_head_key(p.drop.seed_hi, uint32_t(b * p.heads + h)), uint32_t(row));
     for (int it = 0; it < n_iter; ++it) {
       const int kv0 = (j_lo + it) * AT_N + x * 64;
       mbar_wait(&sdp_full[x], it & 1);
@@ -409,9 +433,15 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const int col = c * 32 + 2 * e2 + e;
             float pe = fast_exp2(fmaf(__uint_as_float(s[2 * e2 + e]), p.scale_log2, -lse2));
             if (need_mask) pe = (col > hi || col < lo) ? 0.f : pe;
-            dv[e] = pe * (__uint_as_float(dp[2 * e2 + e]) - dlt) * p.scale;
+            float dpe = __uint_as_float(dp[2 * e2 + e]);
+            if constexpr ((F & AF_DROPOUT) != 0) {
+              const uint32_t key = uint32_t(kv0 + col);
+              dpe = drop_is_dropped(drop_bytes(row_key, key >> 2), key, p.drop.threshold) ? 0.f
+                                                                                          : dpe * p.drop.inv_keep;
+            }
+            dv[e] = pe * (dpe - dlt) * p.scale;
           }
-          dk[e2] = pack_bf16x2(dv[0], dv[1]);
+          dk[e2] = pack_h2<F>(dv[0], dv[1]);
         }
         tmem_st_32x16(dp_addr + c * 16, dk);
       }
@@ -433,10 +463,10 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #pragma unroll
         for (int i2 = 0; i2 < 4; ++i2) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(a[i2 * 8 + 0]), __uint_as_float(a[i2 * 8 + 1]));
-          o.y = pack_bf16x2(__uint_as_float(a[i2 * 8 + 2]), __uint_as_float(a[i2 * 8 + 3]));
-          o.z = pack_bf16x2(__uint_as_float(a[i2 * 8 + 4]), __uint_as_float(a[i2 * 8 + 5]));
-          o.w = pack_bf16x2(__uint_as_float(a[i2 * 8 + 6]), __uint_as_float(a[i2 * 8 + 7]));
+          o.x = pack_h2<F>(__uint_as_float(a[i2 * 8 + 0]), __uint_as_float(a[i2 * 8 + 1]));
+          o.y = pack_h2<F>(__uint_as_float(a[i2 * 8 + 2]), __uint_as_float(a[i2 * 8 + 3]));
+          o.z = pack_h2<F>(__uint_as_float(a[i2 * 8 + 4]), __uint_as_float(a[i2 * 8 + 5]));
+          o.w = pack_h2<F>(__uint_as_float(a[i2 * 8 + 6]), __uint_as_float(a[i2 * 8 + 7]));
           d0[i2] = o;
         }
       }
@@ -447,38 +477,53 @@ attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
   if (warp == 2) { tc_fence_after(); tmem_dealloc<1>(tmem, 512); }
 }
 
-template <int D>
+template <int D, int F>
 static int launch_attn_bwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const CUtensorMap& tdo,
                            const AttnBwdParams& p, const RowAddr& ro, const RowAddr& rdo, float* delta, int q_per_kv,
                            cudaStream_t stream) {
+  constexpr int KV_SMEM = (F & AF_DROPOUT) != 0 ? BWD_SMEM_DROPOUT : BWD_SMEM;
   const long long rows = (long long)p.seq * p.batch * p.heads;
-  attn_delta_kernel<D><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ro, rdo, delta, p.seq, p.batch, p.heads);
+  attn_delta_kernel<D, F & AF_FP16><<<(unsigned)((rows + 7) / 8), 256, 0, stream>>>(ro, rdo, delta, p.seq, p.batch,
+                                                                                    p.heads);
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkdv_kernel<D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, KV_SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attn_bwd_dq_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_DQ_SMEM);
+    e = cudaFuncSetAttribute(attn_bwd_dq_kernel<D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_DQ_SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   dim3 g1(p.seq / AT_N, p.heads / q_per_kv, p.batch);
-  attn_bwd_dkdv_kernel<D><<<g1, BW_THREADS, BWD_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dkdv_kernel<D, F><<<g1, BW_THREADS, KV_SMEM, stream>>>(tq, tk, tv, tdo, p);
   dim3 g2(p.seq / AT_M, p.heads, p.batch);
-  attn_bwd_dq_kernel<D><<<g2, BW_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
+  attn_bwd_dq_kernel<D, F><<<g2, BW_THREADS, BWD_DQ_SMEM, stream>>>(tq, tk, tv, tdo, p);
   return (int)cudaGetLastError();
+}
+
+template <int D>
+static int launch_attn_bwd_flags(int flags, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                 const CUtensorMap& tdo, const AttnBwdParams& p, const RowAddr& ro, const RowAddr& rdo,
+                                 float* delta, int q_per_kv, cudaStream_t stream) {
+  switch (flags) {
+    case 0: return launch_attn_bwd<D, 0>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
+    case AF_FP16: return launch_attn_bwd<D, AF_FP16>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
+    case AF_DROPOUT: return launch_attn_bwd<D, AF_DROPOUT>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
+    default: return launch_attn_bwd<D, AF_FP16 | AF_DROPOUT>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
+  }
 }
 
 }  // namespace mlb
 
-extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const void* o, const void* dout,
-                            const long long* q_str, const long long* k_str, const long long* v_str,
-                            const long long* o_str, const long long* do_str, int q_map_heads, int k_map_heads,
-                            int v_map_heads, const int* head_map, int q_per_kv, int seq, int batch, int heads,
-                            int window, float softmax_scale, const float* lse, float* delta, void* dq, void* dk,
-                            void* dv, const long long* dq_str, const long long* dk_str, const long long* dv_str,
-                            int head_dim, cudaStream_t stream) {
+// ``fp16`` / ``dropout_p`` / ``seed``: as in mlb_attn_fwd_ex (the mask is regenerated from the same p and seed).
+extern "C" int mlb_attn_bwd_ex(const void* q, const void* k, const void* v, const void* o, const void* dout,
+                               const long long* q_str, const long long* k_str, const long long* v_str,
+                               const long long* o_str, const long long* do_str, int q_map_heads, int k_map_heads,
+                               int v_map_heads, const int* head_map, int q_per_kv, int seq, int batch, int heads,
+                               int window, float softmax_scale, const float* lse, float* delta, void* dq, void* dk,
+                               void* dv, const long long* dq_str, const long long* dk_str, const long long* dv_str,
+                               int head_dim, int fp16, float dropout_p, unsigned long long seed, cudaStream_t stream) {
   using namespace mlb;
-  if (seq % AT_M != 0 || (head_dim != 64 && head_dim != 128)) return -2;
+  if (seq % AT_M != 0 || (head_dim != 64 && head_dim != 128) || dropout_p < 0.f || dropout_p >= 1.f) return -2;
   CUtensorMap tq, tk, tv, tdo;
   int r = make_tmap_heads(&tq, q, head_dim, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
   if (r) return 1000 + r;
@@ -500,6 +545,8 @@ extern "C" int mlb_attn_bwd(const void* q, const void* k, const void* v, const v
   p.dv = RowAddr{dv, dv_str[0], dv_str[1], dv_str[2]};
   const RowAddr ro{const_cast<void*>(o), o_str[0], o_str[1], o_str[2]};
   const RowAddr rdo{const_cast<void*>(dout), do_str[0], do_str[1], do_str[2]};
-  return head_dim == 128 ? launch_attn_bwd<128>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream)
-                         : launch_attn_bwd<64>(tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
+  p.drop = make_dropout_params(dropout_p, seed);
+  const int flags = (fp16 ? AF_FP16 : 0) | (p.drop.threshold > 0 ? AF_DROPOUT : 0);
+  return head_dim == 128 ? launch_attn_bwd_flags<128>(flags, tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream)
+                         : launch_attn_bwd_flags<64>(flags, tq, tk, tv, tdo, p, ro, rdo, delta, q_per_kv, stream);
 }

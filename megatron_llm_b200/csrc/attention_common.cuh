@@ -1,5 +1,6 @@
 // Shared pieces of the sm_100a attention kernels (forward / dK,dV / dQ).
 #pragma once
+#include "attention_dropout.cuh"
 #include "gemm_types.h"
 #include "ptx.cuh"
 
@@ -68,6 +69,20 @@ __device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k) {
 }
 __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_addr, int k) {
   return make_smem_desc(tile_addr + k * 2048, AT_HALF_BYTES, 1024, kSwizzle128B);
+}
+
+// Kernel variants (template flags): 16-bit element type of Q / K / V / O and the gradients, and attention dropout.
+// Flag 0 (bf16, no dropout) is the training hot path; the other instantiations add code only under `if constexpr`.
+constexpr int AF_FP16 = 1, AF_DROPOUT = 2;
+template <int F>
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+  if constexpr ((F & AF_FP16) != 0) return pack_f16x2(a, b);
+  else return pack_bf16x2(a, b);
+}
+template <int F>
+__device__ __forceinline__ float2 unpack_h2(uint32_t u) {
+  if constexpr ((F & AF_FP16) != 0) return unpack_f16x2(u);
+  else return unpack_bf16x2(u);
 }
 
 __device__ __forceinline__ float fast_exp2(float x) {

@@ -33,12 +33,13 @@ struct AttnParams {
   void* out;                      // [.., hn] rows: out + ((s * out_s_stride) + b * out_b_stride + h * 128)
   long long out_s_stride, out_b_stride;   // in elements
   float* lse;                     // [batch, heads, seq] natural-log logsumexp of the scaled scores
+  DropoutParams drop;             // (read by the AF_DROPOUT instantiations only)
 };
 
 // =================================================================================================
 // forward
 // =================================================================================================
-template <int D>
+template <int D, int F>
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -93,8 +94,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
-  constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, true);   // Q K^T : both K-major
-  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, D, false, true, true);   // P (TMEM) x V (MN-major)
+  constexpr bool BF16 = (F & AF_FP16) == 0;
+  constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, BF16);   // Q K^T : both K-major
+  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, D, false, true, BF16);   // P (TMEM) x V (MN-major)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -152,6 +154,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int row = q0 + r;                 // global query position
     const uint32_t lane_addr = uint32_t(q * 32) << 16;
     float m_used = -INFINITY, l = 0.f;
+    uint32_t row_key = 0;
+    if constexpr ((F & AF_DROPOUT) != 0)
+      row_key = drop_row_key(p.drop.seed_lo, drop_head_key(p.drop.seed_hi, uint32_t(b * p.heads + h)), uint32_t(row));
     for (int t = 0; t < n_tiles; ++t) {
       const int st = t & 1;
       const int kv0 = (j_lo + t) * AT_N;
@@ -214,9 +219,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (col > row || (p.window > 0 && col < row - p.window)) s0 = -INFINITY;
             if (col + 1 > row || (p.window > 0 && col + 1 < row - p.window)) s1 = -INFINITY;
           }
-          const float p0 = fast_exp2(s0 * p.scale_log2 - moff), p1 = fast_exp2(s1 * p.scale_log2 - moff);
+          float p0 = fast_exp2(s0 * p.scale_log2 - moff), p1 = fast_exp2(s1 * p.scale_log2 - moff);
           l += p0 + p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          if constexpr ((F & AF_DROPOUT) != 0) {     // the row sum keeps the undropped probabilities
+            const uint32_t key = uint32_t(kv0 + c * 32 + 2 * i);
+            const uint32_t bytes = drop_bytes(row_key, key >> 2);
+            p0 = drop_is_dropped(bytes, key, p.drop.threshold) ? 0.f : p0;
+            p1 = drop_is_dropped(bytes, key + 1, p.drop.threshold) ? 0.f : p1;
+          }
+          pk[i] = pack_h2<F>(p0, p1);
         }
         tmem_st_32x16(p_addr + c * 16, pk);
       }
@@ -228,7 +239,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------ epilogue: O / l -> bf16, plus the log-sum-exp ------------------------------
     mbar_wait(o_done, (n_tiles - 1) & 1);
     tc_fence_after();
-    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    if constexpr ((F & AF_DROPOUT) != 0) inv_l *= p.drop.inv_keep;
     if (row < p.seq) {
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.out_s_stride +
                             (long long)b * p.out_b_stride + (long long)h * D;
@@ -241,10 +253,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
-          o.y = pack_bf16x2(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
-          o.z = pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
-          o.w = pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+          o.x = pack_h2<F>(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+          o.y = pack_h2<F>(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+          o.z = pack_h2<F>(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+          o.w = pack_h2<F>(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
           dst[i] = o;
         }
       }
@@ -275,7 +287,7 @@ constexpr int AT2_THREADS = 384;
 constexpr uint32_t T2_S0 = 0, T2_S1 = 128, T2_O0 = 256, T2_O1 = 384;
 constexpr int AT_FWD2_SMEM = 6 * AT_TILE_BYTES + 256 + 1024;
 
-template <int D>
+template <int D, int F>
 __global__ void __launch_bounds__(AT2_THREADS, 1)
 attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                  const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -330,8 +342,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_ptr_smem;
-  constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, true);
-  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, D, false, true, true);
+  constexpr bool BF16 = (F & AF_FP16) == 0;
+  constexpr uint32_t IDESC_S = make_idesc_f16(AT_M, AT_N, false, false, BF16);
+  constexpr uint32_t IDESC_PV = make_idesc_f16(AT_M, D, false, true, BF16);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -404,6 +417,9 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     const uint32_t o_addr = tmem + lane_addr + (x ? T2_O1 : T2_O0);
     const float sc = p.scale_log2;
     float m_used = -INFINITY, l = 0.f;
+    uint32_t row_key = 0;
+    if constexpr ((F & AF_DROPOUT) != 0)
+      row_key = drop_row_key(p.drop.seed_lo, drop_head_key(p.drop.seed_hi, uint32_t(b * p.heads + h)), uint32_t(row));
     for (int t = 0; t < n_x; ++t) {
       const int kv0 = (j_lo + t) * AT_N;
       mbar_wait(&s_full[x], t & 1);
@@ -471,10 +487,16 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, -moff));
-          const float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, -moff));
+          float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * i]), sc, -moff));
+          float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), sc, -moff));
           l0 += p0; l1 += p1;
-          pk[i] = pack_bf16x2(p0, p1);
+          if constexpr ((F & AF_DROPOUT) != 0) {     // the row sum keeps the undropped probabilities
+            const uint32_t key = uint32_t(kv0 + c * 32 + 2 * i);
+            const uint32_t bytes = drop_bytes(row_key, key >> 2);
+            p0 = drop_is_dropped(bytes, key, p.drop.threshold) ? 0.f : p0;
+            p1 = drop_is_dropped(bytes, key + 1, p.drop.threshold) ? 0.f : p1;
+          }
+          pk[i] = pack_h2<F>(p0, p1);
         }
         tmem_st_32x16(s_addr + c * 16, pk);
       }
@@ -487,7 +509,8 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     // ------------------------------ epilogue ------------------------------------------------------------------
     mbar_wait(&o_done[x], (n_x - 1) & 1);
     tc_fence_after();
-    const float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    float inv_l = (l > 0.f) ? 1.f / l : 0.f;
+    if constexpr ((F & AF_DROPOUT) != 0) inv_l *= p.drop.inv_keep;
     if (row < p.seq) {
       __nv_bfloat16* orow = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.out_s_stride +
                             (long long)b * p.out_b_stride + (long long)h * D;
@@ -500,10 +523,10 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           uint4 o;
-          o.x = pack_bf16x2(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
-          o.y = pack_bf16x2(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
-          o.z = pack_bf16x2(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
-          o.w = pack_bf16x2(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
+          o.x = pack_h2<F>(__uint_as_float(v[i * 8 + 0]) * inv_l, __uint_as_float(v[i * 8 + 1]) * inv_l);
+          o.y = pack_h2<F>(__uint_as_float(v[i * 8 + 2]) * inv_l, __uint_as_float(v[i * 8 + 3]) * inv_l);
+          o.z = pack_h2<F>(__uint_as_float(v[i * 8 + 4]) * inv_l, __uint_as_float(v[i * 8 + 5]) * inv_l);
+          o.w = pack_h2<F>(__uint_as_float(v[i * 8 + 6]) * inv_l, __uint_as_float(v[i * 8 + 7]) * inv_l);
           dst[i] = o;
         }
       }
@@ -519,39 +542,53 @@ attn_fwd2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
   }
 }
 
-template <int D>
+template <int D, int F>
 static int launch_attn_fwd(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                            cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_kernel<D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD_SMEM);
     if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(attn_fwd2_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD2_SMEM);
+    e = cudaFuncSetAttribute(attn_fwd2_kernel<D, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_FWD2_SMEM);
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
   static const int force_single = getenv("MLB200_ATTN_FWD1") != nullptr;
   if (p.seq % (2 * AT_M) == 0 && !force_single) {
     dim3 grid(p.seq / (2 * AT_M), p.heads, p.batch);
-    attn_fwd2_kernel<D><<<grid, AT2_THREADS, AT_FWD2_SMEM, stream>>>(tq, tk, tv, p);
+    attn_fwd2_kernel<D, F><<<grid, AT2_THREADS, AT_FWD2_SMEM, stream>>>(tq, tk, tv, p);
   } else {
     dim3 grid(p.seq / AT_M, p.heads, p.batch);
-    attn_fwd_kernel<D><<<grid, AT_THREADS, AT_FWD_SMEM, stream>>>(tq, tk, tv, p);
+    attn_fwd_kernel<D, F><<<grid, AT_THREADS, AT_FWD_SMEM, stream>>>(tq, tk, tv, p);
   }
   return (int)cudaGetLastError();
+}
+
+template <int D>
+static int launch_attn_fwd_flags(int flags, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                                 const AttnParams& p, cudaStream_t stream) {
+  switch (flags) {
+    case 0: return launch_attn_fwd<D, 0>(tq, tk, tv, p, stream);
+    case AF_FP16: return launch_attn_fwd<D, AF_FP16>(tq, tk, tv, p, stream);
+    case AF_DROPOUT: return launch_attn_fwd<D, AF_DROPOUT>(tq, tk, tv, p, stream);
+    default: return launch_attn_fwd<D, AF_FP16 | AF_DROPOUT>(tq, tk, tv, p, stream);
+  }
 }
 
 }  // namespace mlb
 
 // q/k/v described by (base pointer, head stride, seq stride, batch stride) in elements + number of heads in the map;
 // head coordinates come from the group-stride / offset triple (see AttnParams).  head_dim = 128 or 64.
-extern "C" int mlb_attn_fwd(const void* q, const void* k, const void* v, const long long* q_str, const long long* k_str,
-                            const long long* v_str, int q_map_heads, int k_map_heads, int v_map_heads,
-                            const int* head_map /* 6 ints */, int q_per_kv, int seq, int batch, int heads, int window,
-                            float softmax_scale, void* out, long long out_s_stride, long long out_b_stride, float* lse,
-                            int head_dim, cudaStream_t stream) {
+// ``fp16``: the tensors hold IEEE half instead of bf16.  ``dropout_p`` > 0: attention-probability dropout with the
+// counter-based mask of attention_dropout.cuh (the backward must be called with the same p and seed).
+extern "C" int mlb_attn_fwd_ex(const void* q, const void* k, const void* v, const long long* q_str,
+                               const long long* k_str, const long long* v_str, int q_map_heads, int k_map_heads,
+                               int v_map_heads, const int* head_map /* 6 ints */, int q_per_kv, int seq, int batch,
+                               int heads, int window, float softmax_scale, void* out, long long out_s_stride,
+                               long long out_b_stride, float* lse, int head_dim, int fp16, float dropout_p,
+                               unsigned long long seed, cudaStream_t stream) {
   using namespace mlb;
-  if (seq % AT_M != 0 || (head_dim != 64 && head_dim != 128)) return -2;
+  if (seq % AT_M != 0 || (head_dim != 64 && head_dim != 128) || dropout_p < 0.f || dropout_p >= 1.f) return -2;
   CUtensorMap tq, tk, tv;
   int r = make_tmap_heads(&tq, q, head_dim, q_map_heads, seq, batch, q_str[0], q_str[1], q_str[2], AT_M);
   if (r) return 1000 + r;
@@ -566,5 +603,8 @@ extern "C" int mlb_attn_fwd(const void* q, const void* k, const void* v, const l
   p.q_per_kv = q_per_kv; p.seq = seq; p.batch = batch; p.heads = heads; p.window = window;
   p.scale_log2 = softmax_scale * 1.4426950408889634f;
   p.out = out; p.out_s_stride = out_s_stride; p.out_b_stride = out_b_stride; p.lse = lse;
-  return head_dim == 128 ? launch_attn_fwd<128>(tq, tk, tv, p, stream) : launch_attn_fwd<64>(tq, tk, tv, p, stream);
+  p.drop = make_dropout_params(dropout_p, seed);
+  const int flags = (fp16 ? AF_FP16 : 0) | (p.drop.threshold > 0 ? AF_DROPOUT : 0);
+  return head_dim == 128 ? launch_attn_fwd_flags<128>(flags, tq, tk, tv, p, stream)
+                         : launch_attn_fwd_flags<64>(flags, tq, tk, tv, p, stream);
 }

@@ -233,6 +233,11 @@ class ParallelAttention(MegatronModule):
         return torch.empty(inference_max_sequence_len, batch_size, self.num_kv_heads_per_partition,
                            self.hidden_size_per_attention_head, dtype=self.params_dtype, device=current_device())
 
+    def _attention_dropout_rng(self, p):
+        """RNG scope of the attention dropout (reference transformer.py:540-553): the model-parallel stream, so TP ranks
+        -- which hold different heads -- draw different masks; sequence-parallel runs use the default stream."""
+        return get_cuda_rng_tracker().fork() if (not self.sequence_parallel and p > 0) else nullcontext()
+
     def forward(self, hidden_states, attention_mask, encoder_output=None, inference_params=None, position_ids=None):
         hn = self.hidden_size_per_attention_head
         pos_offset = 0
@@ -261,8 +266,9 @@ class ParallelAttention(MegatronModule):
                 window = None
                 if self.sliding_window_size is not None and sq > self.sliding_window_size:
                     window = self.sliding_window_size
-                context_layer = attention_sm100.packed_attention(mixed, self.num_kv_heads_per_partition,
-                                                                 self.q_per_kv, window, None, hn)
+                with self._attention_dropout_rng(p_drop):
+                    context_layer = attention_sm100.packed_attention(mixed, self.num_kv_heads_per_partition,
+                                                                     self.q_per_kv, window, None, hn, p_drop)
                 return self.dense(context_layer)
             qkv = mixed.view(sq, b, self.num_kv_heads_per_partition, self.q_per_kv + 2, hn)
             if self.q_per_kv == 1:
@@ -302,8 +308,7 @@ class ParallelAttention(MegatronModule):
             k = key_layer.transpose(0, 1)
             v = value_layer.transpose(0, 1)
             p = self.attention_dropout_p if self.training else 0.0
-            rng_ctx = get_cuda_rng_tracker().fork() if (not self.sequence_parallel and p > 0) else nullcontext()
-            with rng_ctx:
+            with self._attention_dropout_rng(p):
                 ctx = ops.flash_attention(q, k, v, causal=True, window=window, dropout_p=p)
             # [b, s, n, hn] -> [s, b, n*hn]
             context_layer = ctx.transpose(0, 1).reshape(sq, b, -1)

@@ -1,0 +1,125 @@
+// Minimal CUDA execution model on CPU threads, enough to RUN the repo's SIMT kernels (not the tcgen05 / TMA ones) in the
+// CPU test suite: one std::thread per CUDA thread of a block, blocks one after the other,
+//   __shared__        -> a static (one block is alive at a time)
+//   __syncthreads()   -> std::barrier over the block          __syncwarp() -> std::barrier over the warp
+//   __shfl_xor_sync   -> exchange through a per-warp buffer between two warp barriers
+// A thread that returns from the kernel drops out of its barriers, so early exits of whole warps do not dead-lock.
+// The fake <cuda_runtime.h> / <cuda_bf16.h> / <cuda_fp16.h> next to this file all include it.
+#pragma once
+#include <algorithm>
+#include <barrier>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __launch_bounds__(...)
+#define __align__(n) __attribute__((aligned(n)))
+#define __shared__ static
+
+using std::max;
+using std::min;
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+struct float2 { float x, y; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct __attribute__((aligned(8))) uint2 { uint32_t x, y; };
+struct __attribute__((aligned(16))) uint4 { uint32_t x, y, z, w; };
+inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
+inline float2 make_float2(float a, float b) { return float2{a, b}; }
+
+// ---- 16-bit floating point types (round-to-nearest-even conversions)
+struct __nv_bfloat16 { uint16_t bits; };
+struct __nv_bfloat162 { __nv_bfloat16 x, y; };
+struct __half { _Float16 v; };
+struct __half2 { __half x, y; };
+inline float __bfloat162float(__nv_bfloat16 h) {
+  uint32_t u = uint32_t(h.bits) << 16; float f; std::memcpy(&f, &u, 4); return f;
+}
+inline __nv_bfloat16 __float2bfloat16_rn(float f) {
+  uint32_t u; std::memcpy(&u, &f, 4);
+  if ((u & 0x7fffffffu) > 0x7f800000u) return __nv_bfloat16{uint16_t((u >> 16) | 0x40)};   // NaN stays NaN
+  u += 0x7fffu + ((u >> 16) & 1u);
+  return __nv_bfloat16{uint16_t(u >> 16)};
+}
+inline float2 __bfloat1622float2(__nv_bfloat162 h) { return float2{__bfloat162float(h.x), __bfloat162float(h.y)}; }
+inline __nv_bfloat162 __floats2bfloat162_rn(float a, float b) {
+  return __nv_bfloat162{__float2bfloat16_rn(a), __float2bfloat16_rn(b)};
+}
+inline float __half2float(__half h) { return float(h.v); }
+inline __half __float2half_rn(float f) { return __half{_Float16(f)}; }
+inline float2 __half22float2(__half2 h) { return float2{float(h.x.v), float(h.y.v)}; }
+inline __half2 __floats2half2_rn(float a, float b) { return __half2{__float2half_rn(a), __float2half_rn(b)}; }
+
+// ---- execution context
+namespace cuda_emu {
+struct Block {
+  unsigned n_threads, n_warps;
+  std::barrier<> block_bar;
+  std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
+  std::vector<uint32_t> shfl;     // [n_warps][32]
+  explicit Block(unsigned n) : n_threads(n), n_warps((n + 31) / 32), block_bar(n), shfl(((n + 31) / 32) * 32) {
+    for (unsigned w = 0; w < n_warps; ++w)
+      warp_bar.emplace_back(new std::barrier<>(std::min(32u, n - w * 32)));
+  }
+};
+inline thread_local Block* blk = nullptr;
+}  // namespace cuda_emu
+
+inline thread_local uint3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0};
+inline thread_local dim3 blockDim, gridDim;
+
+inline void __syncthreads() { cuda_emu::blk->block_bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned = 0xffffffffu) { cuda_emu::blk->warp_bar[threadIdx.x >> 5]->arrive_and_wait(); }
+inline uint32_t emu_shfl_bits(uint32_t v, int src_lane) {
+  auto* b = cuda_emu::blk;
+  const unsigned w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  b->shfl[w * 32 + lane] = v;
+  b->warp_bar[w]->arrive_and_wait();
+  const uint32_t r = b->shfl[w * 32 + (unsigned(src_lane) & 31u)];
+  b->warp_bar[w]->arrive_and_wait();
+  return r;
+}
+inline float __shfl_xor_sync(unsigned, float v, int o) {
+  uint32_t u; std::memcpy(&u, &v, 4);
+  u = emu_shfl_bits(u, int(threadIdx.x & 31) ^ o);
+  float r; std::memcpy(&r, &u, 4); return r;
+}
+inline int __shfl_xor_sync(unsigned, int v, int o) { return int(emu_shfl_bits(uint32_t(v), int(threadIdx.x & 31) ^ o)); }
+
+namespace cuda_emu {
+// run `kernel()` for every thread of every block of a 1-D-thread-block grid
+template <class F>
+void launch(dim3 grid, unsigned threads, F kernel) {
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        Block block(threads);
+        std::vector<std::thread> pool;
+        pool.reserve(threads);
+        for (unsigned t = 0; t < threads; ++t)
+          pool.emplace_back([&, t] {
+            blk = &block;
+            threadIdx = uint3{t, 0, 0};
+            blockIdx = uint3{bx, by, bz};
+            blockDim = dim3(threads);
+            gridDim = grid;
+            kernel();
+            block.warp_bar[t >> 5]->arrive_and_drop();
+            block.block_bar.arrive_and_drop();
+          });
+        for (auto& th : pool) th.join();
+      }
+}
+}  // namespace cuda_emu

@@ -1,0 +1,3 @@
+// CPU stand-in for <cuda_fp16.h> (see cuda_emu.h)
+#pragma once
+#include "cuda_emu.h"

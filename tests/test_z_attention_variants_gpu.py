@@ -1,0 +1,148 @@
+"""Hardware checks of the attention kernel variants that were written after the round's GPU budget was spent: fp16
+operands and attention dropout in the tcgen05 forward / dK,dV / dQ kernels, the split-KV decode kernel and the padded
+prompt path.  (CPU-side evidence: the bf16 / no-dropout instantiations are SASS-identical to the validated build, the
+decode kernel source runs on CPU threads in tests/test_kernel_emulation.py, the dropout tile math and mask are pinned
+there too.)
+
+Every check runs in its own process with a hard timeout, so a fault or a hang in one of these first runs cannot take
+the rest of the GPU suite with it, and is marked ``xfail(strict=False)``: XPASS in the log = validated on hardware,
+XFAIL = the variant is broken there (production code then self-tests it off, see ops/attention_sm100.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="first hardware run of these kernel variants (no GPU budget was "
+                                                     "left when they were written); XPASS = validated")]
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PRELUDE = r'''
+import json, math, os, sys, torch
+sys.path.insert(0, %(root)r)
+from megatron_llm_b200.ops import _ext, attention_sm100
+from megatron_llm_b200.ops.attention import attention_reference, dropout_keep_mask, flash_attention
+mod = _ext.load()
+dev = torch.device("cuda:0")
+def rel(a, b):
+    a, b = a.float(), b.float()
+    return ((a - b).norm() / b.norm().clamp_min(1e-12)).item()
+def train_case(dtype, b, s, nq, nkv, hn, window, p, seed=0x1357_9BDF_0246_8ACE):
+    g = torch.Generator(device=dev).manual_seed(s + nq)
+    q, k, v, do = (torch.randn(b, s, n, hn, device=dev, generator=g).to(dtype) for n in (nq, nkv, nkv, nq))
+    sc = 1.0 / math.sqrt(hn)
+    w = -1 if window is None else window
+    out, lse = mod.attn_fwd(q, k, v, True, w, sc, p, seed if p > 0 else 0)
+    dq, dk, dv = mod.attn_bwd(do, q, k, v, out, lse, True, w, sc, p, seed if p > 0 else 0)
+    qf, kf, vf = (t.float().requires_grad_() for t in (q, k, v))
+    keep = dropout_keep_mask(seed, p, b, nq, s, s, device=dev) if p > 0 else None
+    ref = attention_reference(qf, kf, vf, True, window, sc, p, keep)
+    ref.backward(do.float())
+    return dict(out=rel(out, ref), dq=rel(dq, qf.grad), dk=rel(dk, kf.grad), dv=rel(dv, vf.grad))
+res = {}
+'''
+
+CHECKS = {
+    "fp16_training": r'''
+for name, args in {"hd128_two_tile": (2, 512, 8, 2, 128, None), "hd128_one_tile_window": (1, 384, 4, 4, 128, 200),
+                   "hd64_mqa": (2, 256, 8, 1, 64, None)}.items():
+    res[name] = train_case(torch.float16, *args, 0.0)
+''',
+    "dropout_training": r'''
+for name, args in {"hd128_two_tile_gqa": (2, 512, 8, 2, 128, None, 0.1), "hd128_one_tile_window": (1, 384, 4, 4, 128, 200, 0.25),
+                   "hd64_mqa": (2, 256, 8, 1, 64, None, 0.5), "hd128_long": (1, 2048, 2, 1, 128, None, 0.1)}.items():
+    res[name] = train_case(torch.bfloat16, *args)
+res["fp16_and_dropout"] = train_case(torch.float16, 1, 256, 4, 2, 128, None, 0.1)
+# a different seed gives a different output; the same seed is reproducible (what activation recompute relies on)
+g = torch.Generator(device=dev).manual_seed(5)
+q, k, v = (torch.randn(1, 256, 4, 128, device=dev, generator=g).bfloat16() for _ in range(3))
+o1, _ = mod.attn_fwd(q, k, v, True, -1, 0.1, 0.2, 11)
+o2, _ = mod.attn_fwd(q, k, v, True, -1, 0.1, 0.2, 11)
+o3, _ = mod.attn_fwd(q, k, v, True, -1, 0.1, 0.2, 12)
+res["reproducible"] = dict(same=float(not torch.equal(o1, o2)), differs=float(torch.equal(o1, o3)))
+''',
+    "packed_dropout": r'''
+# the packed-QKV entry (what the transformer layer calls) draws the same mask as the separate-tensor entry
+s, b, nkv, gq, hn, p, seed = 256, 2, 2, 4, 128, 0.1, 77
+g = torch.Generator(device=dev).manual_seed(9)
+mixed = torch.randn(s, b, nkv * (gq + 2) * hn, device=dev, generator=g).bfloat16()
+do = torch.randn(s, b, nkv * gq * hn, device=dev, generator=g).bfloat16()
+sc = 1.0 / math.sqrt(hn)
+out, lse = mod.attn_fwd_packed(mixed, nkv, gq, -1, sc, hn, p, seed)
+dmixed = mod.attn_bwd_packed(do, mixed, out, lse, nkv, gq, -1, sc, hn, p, seed)
+qkv = mixed.view(s, b, nkv, gq + 2, hn)
+q = qkv[:, :, :, :gq].reshape(s, b, nkv * gq, hn).transpose(0, 1).float().requires_grad_()
+k = qkv[:, :, :, gq].transpose(0, 1).float().requires_grad_()
+v = qkv[:, :, :, gq + 1].transpose(0, 1).float().requires_grad_()
+keep = dropout_keep_mask(seed, p, b, nkv * gq, s, s, device=dev)
+ref = attention_reference(q, k, v, True, None, sc, p, keep)
+ref.backward(do.view(s, b, nkv * gq, hn).transpose(0, 1).float())
+dm = dmixed.view(s, b, nkv, gq + 2, hn)
+res["packed"] = dict(out=rel(out.view(s, b, nkv * gq, hn).transpose(0, 1), ref),
+                     dq=rel(dm[:, :, :, :gq].reshape(s, b, nkv * gq, hn).transpose(0, 1), q.grad),
+                     dk=rel(dm[:, :, :, gq].transpose(0, 1), k.grad), dv=rel(dm[:, :, :, gq + 1].transpose(0, 1), v.grad))
+''',
+    "decode": r'''
+for dtype in (torch.bfloat16, torch.float16):
+    for name, (b, sq, sk, nq, nkv, hn, window) in {"mha": (2, 1, 777, 8, 8, 128, None), "gqa_long": (1, 1, 4099, 32, 8, 128, None),
+                                                  "mqa_hd64": (4, 1, 1500, 16, 1, 64, None), "window": (1, 1, 3000, 8, 2, 128, 1024),
+                                                  "few_positions": (2, 3, 130, 6, 2, 64, None)}.items():
+        g = torch.Generator(device=dev).manual_seed(sk)
+        q = torch.randn(b, sq, nq, hn, device=dev, generator=g).to(dtype)
+        kmem = torch.randn(sk + 5, b + 1, nkv, hn, device=dev, generator=g).to(dtype)
+        vmem = torch.randn(sk + 5, b + 1, nkv, hn, device=dev, generator=g).to(dtype)
+        k, v = kmem[:sk, 1:].transpose(0, 1), vmem[:sk, 1:].transpose(0, 1)
+        out = mod.attn_decode(q, k, v, -1 if window is None else window, 1.0 / math.sqrt(hn), 0)
+        res[f"{name}_{str(dtype)[6:]}"] = dict(out=rel(out, attention_reference(q.float(), k.float(), v.float(), True, window)))
+''',
+    "public_api_inference": r'''
+# through ops.flash_attention, as text generation calls it (no grad): prompt of a ragged length, then decode steps
+with torch.no_grad():
+    g = torch.Generator(device=dev).manual_seed(1)
+    for dtype in (torch.bfloat16, torch.float16):
+        b, nq, nkv, hn, s_max = 2, 8, 2, 128, 300
+        kmem = torch.zeros(s_max, b, nkv, hn, device=dev, dtype=dtype)
+        vmem = torch.zeros(s_max, b, nkv, hn, device=dev, dtype=dtype)
+        allq = torch.randn(s_max, b, nq, hn, device=dev, generator=g).to(dtype)
+        kmem.copy_(torch.randn(s_max, b, nkv, hn, device=dev, generator=g).to(dtype))
+        vmem.copy_(torch.randn(s_max, b, nkv, hn, device=dev, generator=g).to(dtype))
+        ref_all = attention_reference(allq.transpose(0, 1).float(), kmem.transpose(0, 1).float(),
+                                      vmem.transpose(0, 1).float(), True)
+        prompt = 203
+        n0 = _ext.LAUNCHES
+        o = flash_attention(allq[:prompt].transpose(0, 1), kmem[:prompt].transpose(0, 1), vmem[:prompt].transpose(0, 1))
+        errs = [rel(o, ref_all[:, :prompt])]
+        for t in range(prompt, prompt + 4):
+            o = flash_attention(allq[t:t + 1].transpose(0, 1), kmem[:t + 1].transpose(0, 1), vmem[:t + 1].transpose(0, 1))
+            errs.append(rel(o, ref_all[:, t:t + 1]))
+        res[str(dtype)[6:]] = dict(out=max(errs), launched=float(_ext.LAUNCHES - n0 < 5))
+res["selftests"] = {f"{k[0]}_{k[1]}": float(not v) for k, v in attention_sm100._feature_state.items()}
+''',
+    "public_api_training_dropout": r'''
+# ops.flash_attention with dropout: the self-test admits the kernel, gradients flow, the RNG stream advances
+torch.manual_seed(0)
+q, k, v = (torch.randn(2, 256, 4, 128, device=dev).bfloat16().requires_grad_() for _ in range(3))
+n0 = _ext.LAUNCHES
+o1 = flash_attention(q, k, v, dropout_p=0.1)
+o1.float().square().mean().backward()
+o2 = flash_attention(q, k, v, dropout_p=0.1)
+res["api"] = dict(kernel_used=float(_ext.LAUNCHES - n0 < 5), masks_differ=float(torch.equal(o1, o2)),
+                  grads=float(not all(torch.isfinite(t.grad.float()).all().item() and t.grad.float().abs().sum().item() > 0
+                                      for t in (q, k, v))))
+res["selftests"] = {f"{k[0]}_{k[1]}": float(not v) for k, v in attention_sm100._feature_state.items()}
+''',
+}
+
+
+@pytest.mark.parametrize("name", list(CHECKS))
+def test_attention_variant_on_hardware(name):
+    code = PRELUDE % {"root": ROOT} + CHECKS[name] + '\nprint("RESULT " + json.dumps(res))\n'
+    env = dict(os.environ, MLB200_FORCE_CPU="0", MLB200_DISABLE_KERNELS="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=420)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
+    print(json.dumps(res, indent=1))
+    bad = {f"{case}.{key}": val for case, d in res.items() for key, val in d.items() if not (val == val and val < 2e-2)}
+    assert not bad, bad
