@@ -236,7 +236,6 @@ static inline int fill_decode_params(DecodeParams& p, const void* q, const void*
   return 0;
 }
 
-#ifndef MLB_HOST_EMULATION   // (tests/emu runs the kernels above on CPU threads and supplies its own launcher)
 template <int D, typename T>
 static int launch_decode(const DecodeParams& p, cudaStream_t stream) {
   dim3 grid(p.n_splits, p.nkv, p.batch);
@@ -245,11 +244,9 @@ static int launch_decode(const DecodeParams& p, cudaStream_t stream) {
   attn_decode_merge_kernel<D, T><<<(unsigned)((rows + 3) / 4), 128, 0, stream>>>(p);
   return (int)cudaGetLastError();
 }
-#endif
 
 }  // namespace mlb
 
-#ifndef MLB_HOST_EMULATION
 // part_o: fp32 [b * nkv * n_splits * sq * g * hn], part_ml: 2 floats per such row.
 extern "C" int mlb_attn_decode(int dtype, const void* q, const void* k, const void* v, const long long* q_str,
                                const long long* k_str, const long long* v_str, int batch, int sq, int sk, int nq,
@@ -266,4 +263,3 @@ extern "C" int mlb_attn_decode(int dtype, const void* q, const void* k, const vo
     return head_dim == 128 ? launch_decode<128, __half>(p, stream) : launch_decode<64, __half>(p, stream);
   return -100;
 }
-#endif

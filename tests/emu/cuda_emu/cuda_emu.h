@@ -26,6 +26,9 @@
 
 using std::max;
 using std::min;
+using std::isfinite;
+using std::isinf;
+using std::isnan;
 
 struct uint3 { unsigned x, y, z; };
 struct dim3 {
@@ -123,3 +126,14 @@ void launch(dim3 grid, unsigned threads, F kernel) {
       }
 }
 }  // namespace cuda_emu
+
+// ---- the little of the runtime API the launchers touch
+using cudaStream_t = void*;
+using cudaError_t = int;
+constexpr cudaError_t cudaSuccess = 0;
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline float __expf(float x) { return std::exp(x); }
+inline float __logf(float x) { return std::log(x); }
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
+inline float __fdividef(float a, float b) { return a / b; }
+template <class T> inline T __ldg(const T* p) { return *p; }

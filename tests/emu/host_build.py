@@ -1,0 +1,67 @@
+"""Build a host (CPU) shared library out of the repo's SIMT ``.cu`` files for tests/test_kernel_emulation.py.
+
+The kernel source is used as is.  The only textual change is the launch syntax, which a C++ compiler cannot parse:
+``kernel<<<grid, threads, smem, stream>>>(args)`` becomes ``cuda_emu::launch(dim3(grid), dim3(threads).x, [&] {
+kernel(args); })``, so the real ``extern "C"`` launchers (grid / block selection, dtype dispatch) run too.  Everything
+else -- threadIdx, __shared__, __syncthreads, shuffles, the 16-bit types -- comes from ``cuda_emu/cuda_emu.h``."""
+import os
+import re
+import subprocess
+
+EMU = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(os.path.dirname(os.path.dirname(EMU)), "megatron_llm_b200", "csrc")
+_LAUNCH = re.compile(r"((?:mlb::)?\w+(?:<[^<>;()]*>)?)\s*<<<")
+
+
+def _split_top_level(text):
+    parts, depth, cur = [], 0, []
+    for ch in text:
+        if ch in "([{":
+            depth += 1
+        elif ch in ")]}":
+            depth -= 1
+        if ch == "," and depth == 0:
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur).strip())
+    return parts
+
+
+def launches_to_host(src: str) -> str:
+    out, i = [], 0
+    while True:
+        m = _LAUNCH.search(src, i)
+        if not m:
+            out.append(src[i:])
+            return "".join(out)
+        out.append(src[i:m.start()])
+        j = src.index(">>>", m.end())
+        cfg = _split_top_level(src[m.end():j])
+        k = src.index("(", j)
+        depth = 0
+        for e in range(k, len(src)):
+            depth += src[e] == "("
+            depth -= src[e] == ")"
+            if depth == 0:
+                break
+        out.append(f"cuda_emu::launch(dim3({cfg[0]}), dim3({cfg[1]}).x, [&] {{ {m.group(1)}({src[k + 1:e]}); }})")
+        i = e + 1
+
+
+def build(cu_files, out_dir, name="emu_kernels", extra_cpp=()):
+    """Compile ``cu_files`` (names inside csrc/) plus ``extra_cpp`` (paths) into ``<out_dir>/<name>.so``."""
+    os.makedirs(out_dir, exist_ok=True)
+    sources = []
+    for f in cu_files:
+        body = launches_to_host(open(os.path.join(CSRC, f)).read())
+        assert "<<<" not in body, f
+        dst = os.path.join(out_dir, f.replace(".cu", "_host.cpp"))
+        with open(dst, "w") as fh:
+            fh.write('#include "cuda_emu.h"\n' + body)
+        sources.append(dst)
+    so = os.path.join(out_dir, name + ".so")
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-w",
+                           "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources, *extra_cpp, "-o", so])
+    return so
