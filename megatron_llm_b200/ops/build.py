@@ -35,7 +35,10 @@ def build_main_extension(verbose: bool = False):
     dst = os.path.join(PKG, "_C_b200.so")
     src = os.path.join(BUILD, "_C_b200.so")
     if (not os.path.exists(dst)) or os.path.getmtime(src) > os.path.getmtime(dst):
-        shutil.copy2(src, dst)
+        # new inode, atomically: a process that has the old library mapped keeps running on the old file (copying over
+        # it in place changes the pages under that process and crashes it -- seen with a test run during a rebuild)
+        shutil.copy2(src, dst + ".tmp")
+        os.replace(dst + ".tmp", dst)
     return mod
 
 

@@ -135,6 +135,46 @@ res["selftests"] = {f"{k[0]}_{k[1]}": float(not v) for k, v in attention_sm100._
 ''',
 }
 
+# model level: greedy generation with the KV cache (padded-prompt kernel + decode kernel inside the transformer) must
+# pick, at every step, a token whose logit in a cache-free forward over the whole prefix is (within bf16 noise) the max
+CHECKS["generation_with_kv_cache"] = r'''
+os.environ.update(RANK="0", WORLD_SIZE="1", MASTER_ADDR="127.0.0.1", MASTER_PORT="29688")
+import finetune
+from megatron_llm_b200.initialize import initialize_megatron
+from megatron_llm_b200.text_generation import generate_and_post_process
+from megatron_llm_b200.utils import unwrap_model
+argv = ("--model_name llama2 --num_layers 2 --hidden_size 512 --num_attention_heads 4 --num_attention_heads_kv 2 "
+        "--ffn_hidden_size 1024 --use_rms_norm --glu_activation swiglu --position_embedding_type rotary "
+        "--no_tie_embed_logits --seq_length 512 --max_position_embeddings 512 --micro_batch_size 2 --tokenizer_type "
+        "NullTokenizer --vocab_file 250 --make_vocab_size_divisible_by 8 --train_iters 1 --lr 1e-3 --hidden_dropout 0 "
+        "--attention_dropout 0 --seed 3 --bf16 --use_flash_attn --init_method_std 0.2").split()
+initialize_megatron(extra_args_provider=finetune.extra_args, args_list=argv)
+model = finetune.model_provider(True, True)
+unwrap_model(model).parallel_output = False
+model = model.cuda().bfloat16().eval()
+g = torch.Generator().manual_seed(0)
+prompts = [" ".join(str(int(t)) for t in torch.randint(1, 250, (n,), generator=g)) for n in (150, 37)]
+n0 = _ext.LAUNCHES
+texts, _, _, _ = generate_and_post_process(model, prompts=prompts, tokens_to_generate=6, top_k_sampling=1,
+                                           use_eod_token_for_early_termination=False)
+worst = 0.0
+for i, p in enumerate(prompts):
+    n_prompt = len(p.split())
+    toks = [int(x) for x in texts[i].split()]
+    n_new = min(6, len(toks) - n_prompt)                        # (the longest prompt may be cut at the batch's length)
+    assert toks[:n_prompt] == [int(x) for x in p.split()] and n_new >= 3
+    L = (n_prompt + n_new + 127) // 128 * 128                   # cache-free oracle on the training-shape kernel
+    t = torch.tensor([toks[:n_prompt + n_new] + [0] * (L - n_prompt - n_new)], device=dev)
+    with torch.no_grad():
+        logits = model(t, torch.arange(L, device=dev).unsqueeze(0), None).float()
+    for s in range(n_prompt, n_prompt + n_new):
+        row = logits[0, s - 1, :250]                            # (ids 250.. are vocabulary padding)
+        worst = max(worst, (row.max() - row[toks[s]]).item() / max(1.0, row.abs().max().item()))
+res["generation"] = dict(logit_gap=worst)
+res["selftests"] = {f"{k[0]}_{k[1]}": float(not v) for k, v in attention_sm100._feature_state.items()}
+res["used"] = dict(decode_kernel=float(attention_sm100._feature_state.get(("decode", 128)) is not True))
+'''
+
 
 @pytest.mark.parametrize("name", list(CHECKS))
 def test_attention_variant_on_hardware(name):
