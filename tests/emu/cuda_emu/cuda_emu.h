@@ -7,6 +7,7 @@
 // The fake <cuda_runtime.h> / <cuda_bf16.h> / <cuda_fp16.h> next to this file all include it.
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <barrier>
 #include <cmath>
 #include <cstdint>
@@ -35,10 +36,12 @@ struct dim3 {
   unsigned x, y, z;
   dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
+// (natural alignment only: kernels reinterpret register arrays as vectors, which the host must not turn into aligned
+// SSE moves; the 16-byte alignment of global / shared addresses is a property of the device code under test)
 struct float2 { float x, y; };
-struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
-struct __attribute__((aligned(8))) uint2 { uint32_t x, y; };
-struct __attribute__((aligned(16))) uint4 { uint32_t x, y, z, w; };
+struct float4 { float x, y, z, w; };
+struct uint2 { uint32_t x, y; };
+struct uint4 { uint32_t x, y, z, w; };
 inline float4 make_float4(float a, float b, float c, float d) { return float4{a, b, c, d}; }
 inline float2 make_float2(float a, float b) { return float2{a, b}; }
 
@@ -137,3 +140,11 @@ inline float __logf(float x) { return std::log(x); }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 inline float __fdividef(float a, float b) { return a / b; }
 template <class T> inline T __ldg(const T* p) { return *p; }
+
+namespace cuda_emu {
+// red.global.add.v4.f32: four relaxed float atomics (blocks run one after the other, threads of a block concurrently)
+inline void atomic_add4(float* addr, float a, float b, float c, float d) {
+  const float v[4] = {a, b, c, d};
+  for (int i = 0; i < 4; ++i) std::atomic_ref<float>(addr[i]).fetch_add(v[i], std::memory_order_relaxed);
+}
+}  // namespace cuda_emu

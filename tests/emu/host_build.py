@@ -11,6 +11,10 @@ import subprocess
 EMU = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(EMU)), "megatron_llm_b200", "csrc")
 _LAUNCH = re.compile(r"((?:mlb::)?\w+(?:<[^<>;()]*>)?)\s*<<<")
+# the few inline-PTX statements of the SIMT files, replaced by their host meaning
+_PTX = [(re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::\s*"l"\((\w+)\), "f"\((\w+)\), '
+                    r'"f"\((\w+)\), "f"\((\w+)\), "f"\((\w+)\)\s*:\s*"memory"\);'),
+         r"cuda_emu::atomic_add4(\1, \2, \3, \4, \5);")]
 
 
 def _split_top_level(text):
@@ -30,6 +34,8 @@ def _split_top_level(text):
 
 
 def launches_to_host(src: str) -> str:
+    for pat, repl in _PTX:
+        src = pat.sub(repl, src)
     out, i = [], 0
     while True:
         m = _LAUNCH.search(src, i)
@@ -56,7 +62,7 @@ def build(cu_files, out_dir, name="emu_kernels", extra_cpp=()):
     sources = []
     for f in cu_files:
         body = launches_to_host(open(os.path.join(CSRC, f)).read())
-        assert "<<<" not in body, f
+        assert "<<<" not in body and "asm volatile" not in body, f
         dst = os.path.join(out_dir, f.replace(".cu", "_host.cpp"))
         with open(dst, "w") as fh:
             fh.write('#include "cuda_emu.h"\n' + body)

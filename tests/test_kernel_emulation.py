@@ -29,7 +29,8 @@ def _ptr(t):
 @pytest.fixture(scope="module")
 def kernels(tmp_path_factory):
     """The SIMT translation units (kernels AND their extern "C" launchers) compiled for the host."""
-    so = host_build.build(["attention_decode.cu", "ce.cu", "softmax.cu", "norm.cu", "elementwise.cu"],
+    so = host_build.build(["attention_decode.cu", "ce.cu", "softmax.cu", "norm.cu", "elementwise.cu", "optim.cu",
+                           "embedding.cu"],
                           str(tmp_path_factory.mktemp("emu")))
     return ctypes.CDLL(so)
 
@@ -280,3 +281,138 @@ def test_glu_kernels_on_cpu_threads(kernels, kind, act):
     assert kernels.mlb_glu_bwd(DT[torch.float32], _ptr(dy), _ptr(x.detach()), _ptr(dx), ctypes.c_longlong(rows), F_, kind,
                                None) == 0
     assert (dx - x.grad).abs().max().item() < 1e-5
+
+
+def test_flat_optimizer_kernels_on_cpu_threads(kernels):
+    """csrc/optim.cu over a flat buffer of three parameters (segment table with per-parameter weight decay / lr
+    multiplier, a ragged tail, a shard offset): AdamW with the device-side gradient scale and the bf16 write-back, the
+    skip flag, the weighted squared norm and the clip coefficient."""
+    torch.manual_seed(4)
+    off = 5000                                             # this shard starts at element 5000 of the global buffer
+    sizes = [3000, 1111, 2050]
+    n = sum(sizes)
+    seg_start = torch.tensor([off, off + 3000, off + 4111, off + n])
+    wd, lrm, wgt = torch.tensor([0.1, 0.0, 0.05]), torch.tensor([1.0, 2.0, 0.5]), torch.tensor([1.0, 0.5, 0.0])
+    p, g, m, v = torch.randn(n), torch.randn(n) * 4, torch.randn(n) * 0.1, torch.rand(n) * 0.1
+    lr, b1, b2, eps, step, gscale = 1e-2, 0.9, 0.95, 1e-8, 3, torch.tensor([0.25])
+    bc1, bc2 = 1 - b1 ** step, 1 - b2 ** step
+    seg_of = torch.repeat_interleave(torch.arange(3), torch.tensor(sizes))
+    gg = g * gscale
+    m_ref = b1 * m + (1 - b1) * gg
+    v_ref = b2 * v + (1 - b2) * gg * gg
+    p_ref = p - lr * lrm[seg_of] * ((m_ref / bc1) / ((v_ref / bc2).sqrt() + eps) + wd[seg_of] * p)
+    # skip flag set: nothing moves
+    pk, mk, vk, p16 = p.clone(), m.clone(), v.clone(), torch.zeros(n, dtype=torch.bfloat16)
+    flag = torch.tensor([1], dtype=torch.int32)
+    args = lambda fl: (_ptr(pk), _ptr(g), _ptr(mk), _ptr(vk), _ptr(p16), DT[torch.bfloat16], ctypes.c_longlong(n),
+                       ctypes.c_longlong(off), _ptr(seg_start), _ptr(wd), _ptr(lrm), 3, ctypes.c_float(lr),
+                       ctypes.c_float(b1), ctypes.c_float(b2), ctypes.c_float(eps), ctypes.c_float(bc1),
+                       ctypes.c_float(bc2), _ptr(gscale), _ptr(fl), None, 0, None)
+    assert kernels.mlb_adamw_flat(*args(flag)) == 0
+    assert torch.equal(pk, p) and torch.equal(mk, m) and torch.equal(vk, v)
+    flag.zero_()
+    assert kernels.mlb_adamw_flat(*args(flag)) == 0
+    assert torch.allclose(mk, m_ref, atol=1e-6) and torch.allclose(vk, v_ref, atol=1e-6)
+    assert torch.allclose(pk, p_ref, atol=1e-6)
+    assert torch.equal(p16, pk.bfloat16())
+    # weighted squared norm (weights drop TP-duplicated parameters), accumulated onto a previous value
+    ws, out = torch.zeros(148 * 8), torch.tensor([2.0])
+    gb = g.bfloat16()
+    assert kernels.mlb_sqnorm_flat(DT[torch.bfloat16], _ptr(gb), ctypes.c_longlong(n), ctypes.c_longlong(off),
+                                   _ptr(seg_start), _ptr(wgt), 3, _ptr(ws), _ptr(out), 1, None) == 0
+    ref = 2.0 + (wgt[seg_of] * gb.float() ** 2).sum()
+    assert abs(out.item() - ref.item()) < 1e-3 * ref.item()
+    # clip coefficient: min(1, max_norm / (norm + 1e-6)) * norm_scale, and the inf flag
+    nrm, coef, inf = torch.zeros(1), torch.zeros(1), torch.tensor([7], dtype=torch.int32)
+    tot = torch.tensor([400.0])
+    assert kernels.mlb_clip_coef(_ptr(tot), ctypes.c_float(1.0), _ptr(nrm), _ptr(coef), _ptr(inf), ctypes.c_float(0.5),
+                                 None) == 0
+    assert abs(nrm.item() - 10.0) < 1e-5 and abs(coef.item() - 0.5 * (1.0 / (10.0 + 1e-6))) < 1e-7 and inf.item() == 0
+    tot[0] = float("inf")
+    assert kernels.mlb_clip_coef(_ptr(tot), ctypes.c_float(1.0), _ptr(nrm), _ptr(coef), _ptr(inf), ctypes.c_float(1.0),
+                                 None) == 0
+    assert inf.item() == 1
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_bias_dropout_add_and_gelu_kernels_on_cpu_threads(kernels, dtype):
+    """csrc/elementwise.cu: residual + dropout(x + bias) forward, its backward (the same mask regenerated from the
+    seed), and bias + GeLU forward / backward."""
+    torch.manual_seed(5)
+    rows, F_, pdrop, seed = 6, 64, 0.3, 123456789
+    x, bias, res = (torch.randn(*sh).to(dtype) for sh in ((rows, F_), (F_,), (rows, F_)))
+    out = torch.empty_like(x)
+    assert kernels.mlb_bias_dropout_add(DT[dtype], _ptr(x), _ptr(bias), _ptr(res), _ptr(out), ctypes.c_longlong(rows), F_,
+                                        ctypes.c_float(pdrop), ctypes.c_ulonglong(seed), 0, None) == 0
+    full = (x.float() + bias.float()) / (1 - pdrop) + res.float()
+    kept = (out.float() - full).abs() < (5e-2 if dtype == torch.bfloat16 else 1e-5)
+    dropped = (out.float() - res.float()).abs() < 1e-6
+    assert (kept | dropped).all() and 0.15 < 1 - kept.float().mean().item() < 0.45
+    dy, dx = torch.randn(rows, F_).to(dtype), torch.empty_like(x)
+    assert kernels.mlb_bias_dropout_add(DT[dtype], _ptr(dy), None, None, _ptr(dx), ctypes.c_longlong(rows), F_,
+                                        ctypes.c_float(pdrop), ctypes.c_ulonglong(seed), 1, None) == 0
+    unambiguous = kept != dropped
+    ref_dx = torch.where(kept, dy.float() / (1 - pdrop), torch.zeros(()))
+    assert (dx.float() - ref_dx)[unambiguous].abs().max().item() < (5e-2 if dtype == torch.bfloat16 else 1e-5)
+    # p = 0: plain bias + residual add
+    assert kernels.mlb_bias_dropout_add(DT[dtype], _ptr(x), _ptr(bias), _ptr(res), _ptr(out), ctypes.c_longlong(rows), F_,
+                                        ctypes.c_float(0.0), ctypes.c_ulonglong(seed), 0, None) == 0
+    assert (out.float() - (x.float() + bias.float() + res.float())).abs().max().item() < (5e-2 if dtype == torch.bfloat16 else 1e-6)
+    # bias + GeLU (exact and tanh approximation), forward and backward
+    for approx in (0, 1):
+        xg = (x.float() + bias.float()).requires_grad_()
+        ref = torch.nn.functional.gelu(xg, approximate="tanh" if approx else "none")
+        ref.backward(dy.float())
+        y, dxg = torch.empty_like(x), torch.empty_like(x)
+        assert kernels.mlb_gelu(DT[dtype], _ptr(x), _ptr(bias), None, _ptr(y), ctypes.c_longlong(rows), F_, approx, 0, None) == 0
+        assert kernels.mlb_gelu(DT[dtype], _ptr(x), _ptr(bias), _ptr(dy), _ptr(dxg), ctypes.c_longlong(rows), F_, approx, 1, None) == 0
+        tol = 5e-2 if dtype == torch.bfloat16 else 2e-3
+        assert (y.float() - ref).abs().max().item() < tol and (dxg.float() - xg.grad).abs().max().item() < tol
+
+
+@pytest.mark.parametrize("with_ids", [False, True])
+def test_rope_kernel_on_cpu_threads(kernels, with_ids):
+    """csrc/elementwise.cu rope_qkv: in-place rotation of the q heads and the k head of the packed QKV buffer (the v
+    head untouched), from a position offset or explicit position ids, and the inverse rotation used in backward."""
+    from megatron_llm_b200 import ops
+    torch.manual_seed(6)
+    s, b, nkv, hpg, hn = 5, 2, 2, 4, 16                    # hpg = 2 query heads + k + v per group
+    table = ops.rope_table(hn, 64)
+    mixed = torch.randn(s, b, nkv * hpg * hn)
+    pos = torch.randint(0, 64, (b, s)) if with_ids else None
+    ref = ops._rope_qkv_apply_(mixed.clone(), nkv, hpg, hn, table, pos, 0 if with_ids else 7, False)   # torch path
+    got = mixed.clone()
+    assert kernels.mlb_rope_qkv(DT[torch.float32], _ptr(got), _ptr(table), _ptr(pos), s * b, b, nkv, hpg, hn,
+                                0 if with_ids else 7, 0, ctypes.c_longlong(nkv * hpg * hn), None) == 0
+    assert (got - ref).abs().max().item() < 1e-5
+    v_slice = got.view(s, b, nkv, hpg, hn)[:, :, :, -1]
+    assert torch.equal(v_slice, mixed.view(s, b, nkv, hpg, hn)[:, :, :, -1])
+    assert kernels.mlb_rope_qkv(DT[torch.float32], _ptr(got), _ptr(table), _ptr(pos), s * b, b, nkv, hpg, hn,
+                                0 if with_ids else 7, 1, ctypes.c_longlong(nkv * hpg * hn), None) == 0
+    assert (got - mixed).abs().max().item() < 1e-5          # inverse rotation restores the input
+
+
+@pytest.mark.parametrize("sbh", [0, 1])
+def test_embedding_kernels_on_cpu_threads(kernels, sbh):
+    """csrc/embedding.cu: vocab-shard gather (rows of other shards give zeros, optional [s, b, h] output order) and the
+    scatter-add backward into the fp32 main gradient (repeated ids accumulate)."""
+    torch.manual_seed(7)
+    b, s, H, start, rows_local = 3, 11, 40, 100, 50
+    ids = torch.randint(start - 10, start + rows_local + 10, (b, s))
+    ids[0, :4] = start + 7                                   # repeated id -> accumulation in backward
+    w = torch.randn(rows_local, H).bfloat16()
+    out = torch.full((s, b, H) if sbh else (b, s, H), float("nan")).bfloat16()
+    assert kernels.mlb_embedding_fwd(DT[torch.bfloat16], _ptr(ids), _ptr(w), _ptr(out), b, s, H, ctypes.c_longlong(start),
+                                     ctypes.c_longlong(rows_local), sbh, None) == 0
+    local = ids - start
+    owned = (local >= 0) & (local < rows_local)
+    ref = torch.where(owned[..., None], w[local.clamp(0, rows_local - 1)].float(), torch.zeros(()))
+    ref = ref.transpose(0, 1) if sbh else ref
+    assert torch.equal(out.float(), ref)
+    dout = torch.randn_like(out.float()).bfloat16()
+    dw = torch.ones(rows_local, H)                           # accumulates into what is already there
+    assert kernels.mlb_embedding_bwd(DT[torch.bfloat16], _ptr(ids), _ptr(dout), _ptr(dw), b, s, H, ctypes.c_longlong(start),
+                                     ctypes.c_longlong(rows_local), sbh, None) == 0
+    d = (dout.float().transpose(0, 1) if sbh else dout.float()).reshape(b * s, H)
+    ref_dw = torch.ones(rows_local, H).index_add_(0, local.reshape(-1)[owned.reshape(-1)], d[owned.reshape(-1)])
+    assert (dw - ref_dw).abs().max().item() < 1e-4
