@@ -95,10 +95,9 @@ def flash_attention(q, k, v, causal: bool = True, window: Optional[int] = None, 
         from . import attention_sm100
         if attention_sm100.supported(q, k, v, causal, window, dropout_p):
             return attention_sm100.attention(q, k, v, causal, window, scale, dropout_p)
-        mode = attention_sm100.inference_mode_for(q, k, v, causal, dropout_p)
-        if mode is not None:
-            return attention_sm100.inference_attention(mode, q, k, v, window, scale)
-        # outside the hand-written kernels' envelope (non-causal, training with sq % 128 != 0 or sq != sk, a kernel
-        # variant that failed its self-test): the FA-2 library
+        if attention_sm100.decode_supported(q, k, v, causal, dropout_p):
+            return attention_sm100.decode_attention(q, k, v, window, scale)
+        # outside the hand-written kernels' envelope (non-causal, sq != sk with gradients or many query positions, a
+        # kernel variant that failed its self-test): the FA-2 library
         return _library_flash(q, k, v, causal, window, scale, dropout_p)
     return attention_reference(q, k, v, causal, window, scale, dropout_p)

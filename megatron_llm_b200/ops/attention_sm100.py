@@ -2,9 +2,9 @@
 attention_decode.cu).
 
 Envelope: causal self-attention, head_dim 128 or 64, bf16 or fp16, GQA / MQA, sliding window, attention dropout
-(counter-based mask, csrc/attention_dropout.cuh), training shapes (sq == sk, multiple of 128) on the tcgen05 kernels;
-inference shapes: the prompt (sq == sk of any length, padded to the tile) on the same forward kernel and the KV-cache
-decode step (a few query positions) on the split-KV kernel.
+(counter-based mask, csrc/attention_dropout.cuh).  sq == sk (training, and the prompt pass of text generation) runs on
+the tcgen05 kernels, with lengths that are not a multiple of the 128-row tile zero-padded; the KV-cache decode step
+(a few query positions against a long cache) runs on the split-KV kernel.
 
 Kernel variants that could not be run on hardware before they were merged (``_FEATURES``) are guarded by a one-time
 numerical self-test against the fp32 oracle on first use: a variant that fails it is reported loudly and the call falls
@@ -117,13 +117,14 @@ def _variants_ok(t, hn: int, dropout_p: float) -> bool:
 
 
 def supported(q, k, v, causal, window, dropout_p) -> bool:
-    """Training shape on the tcgen05 kernels (forward + backward)."""
+    """Self-attention (sq == sk) on the tcgen05 kernels, forward + backward.  Sequence lengths that are not a multiple
+    of the 128-row tile (variable-length instruction tuning) are zero-padded by ``attention``."""
     if not _kernels_enabled():
         return False
     _ext.load()      # a CUDA tensor without the built extension is an error, never a silent library fallback
     hn = q.size(-1)
-    return (_head_dim_ok(hn) and causal and q.size(1) == k.size(1) and q.size(1) % 128 == 0
-            and q.size(2) % k.size(2) == 0 and _variants_ok(q, hn, dropout_p))
+    return (_head_dim_ok(hn) and causal and q.size(1) == k.size(1) and q.size(2) % k.size(2) == 0
+            and _variants_ok(q, hn, dropout_p))
 
 
 def _draw_seed(dropout_p: float, n_elems: int) -> int:
@@ -157,11 +158,19 @@ class _AttnFn(torch.autograd.Function):
 def attention(q, k, v, causal, window, scale, dropout_p: float = 0.0):
     scale = scale if scale is not None else 1.0 / math.sqrt(q.size(-1))
     seed = _draw_seed(dropout_p, q.size(0) * q.size(2) * q.size(1) * k.size(1))
-    return _AttnFn.apply(q, k, v, causal, window, scale, dropout_p, seed)
+    sq = q.size(1)
+    pad = (-sq) % 128
+    if pad:
+        # zero rows up to the tile: padded keys lie in every real query's future (causal), padded query rows are
+        # dropped again and receive a zero output gradient, so they contribute nothing to dK / dV either; autograd
+        # differentiates through pad / slice
+        q, k, v = (F.pad(t, (0, 0, 0, 0, 0, pad)) for t in (q, k, v))
+    out = _AttnFn.apply(q, k, v, causal, window, scale, dropout_p, seed)
+    return out[:, :sq] if pad else out
 
 
 # ------------------------------------------------------------------------------------------------ inference shapes
-_DECODE_MAX_ROWS = 64        # query rows per KV group (sq * g) the split-KV kernel takes; more goes to the prompt path
+_DECODE_MAX_ROWS = 64        # query rows per KV group (sq * g) the split-KV kernel takes (8 per pass over the cache)
 
 
 def _decode_aligned(*ts) -> bool:
@@ -169,43 +178,29 @@ def _decode_aligned(*ts) -> bool:
                and t.data_ptr() % 16 == 0 for t in ts)
 
 
-def inference_mode_for(q, k, v, causal, dropout_p):
-    """'decode' / 'prompt' when the forward-only kernels cover this call (no gradient needed), else None."""
+def decode_supported(q, k, v, causal, dropout_p) -> bool:
+    """The KV-cache step of text generation: a few query positions against a longer cache, no gradient needed.
+    (The prompt pass has sq == sk and runs on the tcgen05 forward kernel through ``supported`` / ``attention``.)"""
     if not _kernels_enabled() or not causal or dropout_p != 0.0 or q.dtype not in (torch.bfloat16, torch.float16):
-        return None
+        return False
     if torch.is_grad_enabled() and (q.requires_grad or k.requires_grad or v.requires_grad):
-        return None
+        return False
     hn, sq, sk = q.size(-1), q.size(1), k.size(1)
     if not _head_dim_ok(hn) or q.size(2) % k.size(2) != 0 or sk < sq:
-        return None
+        return False
     _ext.load()
-    if sq == sk and sq > 1:
-        if q.dtype == torch.bfloat16 or feature_ok("fp16", hn, q.dtype, q.device):
-            return "prompt"
-    if sq * (q.size(2) // k.size(2)) <= _DECODE_MAX_ROWS and _decode_aligned(q, k, v) \
-            and feature_ok("decode", hn, q.dtype, q.device):
-        return "decode"
-    return None
+    return (sq * (q.size(2) // k.size(2)) <= _DECODE_MAX_ROWS and _decode_aligned(q, k, v)
+            and feature_ok("decode", hn, q.dtype, q.device))
 
 
-def inference_attention(mode, q, k, v, window, scale):
-    """Forward-only attention of text generation.  'prompt': sq == sk of any length -- zero-padded to the 128-row tile
-    of the tcgen05 forward kernel (padded keys lie in every real query's future, padded query rows are dropped);
-    'decode': the new positions against the KV cache on the split-KV kernel (csrc/attention_decode.cu)."""
+def decode_attention(q, k, v, window, scale):
+    """The new positions against the KV cache on the split-KV kernel (csrc/attention_decode.cu); the causal mask is
+    aligned bottom-right (query i sits at position sk - sq + i)."""
     mod = _ext.load()
     scale = scale if scale is not None else 1.0 / math.sqrt(q.size(-1))
-    w = -1 if window is None else int(window)
-    if mode == "decode":
-        out = mod.attn_decode(q, k, v, w, float(scale), 0)
-        _ext.count(2)
-        return out
-    sq = q.size(1)
-    pad = (-sq) % 128
-    if pad:
-        q, k, v = (F.pad(t, (0, 0, 0, 0, 0, pad)) for t in (q, k, v))
-    out, _ = mod.attn_fwd(q, k, v, True, w, float(scale), 0.0, 0)
-    _ext.count()
-    return out[:, :sq] if pad else out
+    out = mod.attn_decode(q, k, v, -1 if window is None else int(window), float(scale), 0)
+    _ext.count(2)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------ packed QKV path

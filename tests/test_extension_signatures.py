@@ -57,3 +57,10 @@ def test_bindings_accept_the_python_call_sites(ext):
     ctx = torch.zeros(128, 1, 128, dtype=bf)
     _accepts(ext.attn_fwd_packed, mixed, 1, 1, -1, 0.088, 128)
     _accepts(ext.attn_bwd_packed, ctx, mixed, ctx, lse, 1, 1, -1, 0.088, 128)
+    # ... with the dropout arguments (probability, 63-bit seed from ops._dropout_seed), fp16 tensors, the decode step
+    seed = 0x7FFF_FFFF_FFFF_FFFF
+    _accepts(ext.attn_fwd, q, q, q, True, -1, 0.088, 0.1, seed)
+    _accepts(ext.attn_bwd, q, q, q, q, q, lse, True, -1, 0.088, 0.1, seed)
+    _accepts(ext.attn_fwd_packed, mixed.half(), 1, 1, -1, 0.088, 128, 0.1, seed)
+    _accepts(ext.attn_bwd_packed, ctx, mixed, ctx, lse, 1, 1, -1, 0.088, 128, 0.1, seed)
+    _accepts(ext.attn_decode, q[:, :1], q, q, -1, 0.088, 0)

@@ -1,6 +1,6 @@
 """Hardware checks of the attention kernel variants that were written after the round's GPU budget was spent: fp16
-operands and attention dropout in the tcgen05 forward / dK,dV / dQ kernels, the split-KV decode kernel and the padded
-prompt path.  (CPU-side evidence: the bf16 / no-dropout instantiations are SASS-identical to the validated build, the
+operands and attention dropout in the tcgen05 forward / dK,dV / dQ kernels, the split-KV decode kernel and the zero-padding
+of sequence lengths that are not a multiple of the tile (ragged prompts, variable-length training).  (CPU-side evidence: the bf16 / no-dropout instantiations are SASS-identical to the validated build, the
 decode kernel source runs on CPU threads in tests/test_kernel_emulation.py, the dropout tile math and mask are pinned
 there too.)
 
@@ -134,6 +134,24 @@ res["api"] = dict(kernel_used=float(_ext.LAUNCHES - n0 < 5), masks_differ=float(
 res["selftests"] = {f"{k[0]}_{k[1]}": float(not v) for k, v in attention_sm100._feature_state.items()}
 ''',
 }
+
+# sequence lengths that are not a multiple of the 128-row tile (variable-length instruction tuning): zero-padded onto the
+# bf16 kernels by ops.attention_sm100.attention, forward and all gradients through autograd
+CHECKS["ragged_training_length"] = r'''
+for name, (b, s, nq, nkv, hn, window) in {"s200_gqa": (2, 200, 8, 2, 128, None), "s333_window": (1, 333, 4, 4, 64, 100),
+                                          "s77": (1, 77, 4, 1, 128, None)}.items():
+    g = torch.Generator(device=dev).manual_seed(s)
+    q, k, v = (torch.randn(b, s, n, hn, device=dev, generator=g).bfloat16().requires_grad_() for n in (nq, nkv, nkv))
+    do = torch.randn(b, s, nq, hn, device=dev, generator=g).bfloat16()
+    n0 = _ext.LAUNCHES
+    out = flash_attention(q, k, v, causal=True, window=window)
+    out.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref = attention_reference(qf, kf, vf, True, window)
+    ref.backward(do.float())
+    res[name] = dict(out=rel(out, ref), dq=rel(q.grad, qf.grad), dk=rel(k.grad, kf.grad), dv=rel(v.grad, vf.grad),
+                     kernel_used=float(_ext.LAUNCHES - n0 != 4))
+'''
 
 # model level: greedy generation with the KV cache (padded-prompt kernel + decode kernel inside the transformer) must
 # pick, at every step, a token whose logit in a cache-free forward over the whole prefix is (within bf16 noise) the max
