@@ -6,6 +6,8 @@
 // not a tensor-core one:
 //   * grid (split, kv head, batch): a CTA owns one slice of the cache for ALL query rows that share the kv head
 //     (g query heads of the GQA group x sq positions) -- K / V are read once per group, not once per query head;
+//   * K tiles (32 keys) are staged through shared memory: coalesced 16-byte global loads (two cache rows per warp
+//     instruction), rows padded by 16 bytes so that the per-lane row reads are bank-conflict free;
 //   * scores: one key per lane (the query rows are broadcast from shared memory), so a score needs no shuffle;
 //   * online softmax per 32-key tile (two warp reductions per row and tile), probabilities parked in shared memory;
 //   * P V: the lanes split the head dimension, 32 coalesced V rows per tile;
@@ -51,10 +53,14 @@ template <int D, typename T>
 __global__ void __launch_bounds__(DEC_THREADS)
 attn_decode_split_kernel(const DecodeParams p) {
   constexpr int E = D / 32;                       // head-dim elements per lane in the P V phase (4 or 2)
-  __shared__ __align__(16) float sQ[DEC_RC][D];                 // query rows of this pass, pre-scaled
+  constexpr int CH = D / 8;                       // 16-byte chunks per K row
+  constexpr int KROW = D * 2 + 16;                // bytes per staged K row (+16: conflict-free 16-byte column reads)
+  __shared__ __align__(16) float sQ[DEC_RC][D];   // query rows of this pass, pre-scaled
   __shared__ float sP[DEC_WARPS][DEC_RC][32];     // probabilities of the warp's current tile
-  __shared__ float sAcc[DEC_WARPS][DEC_RC][D];    // cross-warp merge
+  // per warp: the staged K tile; after the warp's last tile the same bytes carry its accumulators to the merge
+  __shared__ __align__(16) uint8_t sK[DEC_WARPS][32 * KROW];
   __shared__ float sM[DEC_WARPS][DEC_RC], sL[DEC_WARPS][DEC_RC];
+  static_assert(32 * KROW >= DEC_RC * D * 4, "the accumulator hand-over must fit into the K staging area");
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int split = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -69,7 +75,7 @@ attn_decode_split_kernel(const DecodeParams p) {
   for (int r0 = 0; r0 < R; r0 += DEC_RC) {
     const int rc = min(DEC_RC, R - r0);
     // ---- stage the query rows (fp32, softmax scale and log2(e) folded in); rows >= rc are zero
-    __syncthreads();                               // previous pass finished with sQ / sAcc
+    __syncthreads();                               // previous pass finished with sQ and the merge buffers
     for (int idx = threadIdx.x; idx < DEC_RC * D; idx += DEC_THREADS) {
       const int r = idx / D, d = idx % D;
       float val = 0.f;
@@ -97,14 +103,23 @@ attn_decode_split_kernel(const DecodeParams p) {
       const int key0 = k_begin + t * 32;
       const int key = key0 + lane;
       const bool key_ok = key < k_end;
+      // ---- stage the K tile (rows past the slice repeat its last key; they are masked below)
+      uint8_t* sKw = sK[warp];
+#pragma unroll 4
+      for (int idx = lane; idx < 32 * CH; idx += 32) {
+        const int r = idx / CH, c = idx % CH;
+        const T* src = kbase + (long long)min(key0 + r, k_end - 1) * p.k_s + c * 8;
+        *reinterpret_cast<uint4*>(sKw + r * KROW + c * 16) = *reinterpret_cast<const uint4*>(src);
+      }
+      __syncwarp();
       // ---- scores of this lane's key against every row
       float s[DEC_RC];
 #pragma unroll
       for (int r = 0; r < DEC_RC; ++r) s[r] = 0.f;
-      const T* krow = kbase + (long long)(key_ok ? key : (k_end - 1)) * p.k_s;
+      const uint8_t* krow = sKw + lane * KROW;
 #pragma unroll 2
       for (int d0 = 0; d0 < D; d0 += 8) {
-        const uint4 kv4 = *reinterpret_cast<const uint4*>(krow + d0);
+        const uint4 kv4 = *reinterpret_cast<const uint4*>(krow + d0 * 2);
         const float2 k01 = Pair16<T>::unpack(kv4.x), k23 = Pair16<T>::unpack(kv4.y);
         const float2 k45 = Pair16<T>::unpack(kv4.z), k67 = Pair16<T>::unpack(kv4.w);
 #pragma unroll
@@ -153,14 +168,15 @@ attn_decode_split_kernel(const DecodeParams p) {
           for (int e = 0; e < E; ++e) acc[r][e] += pr * vf[e];
         }
       }
-      __syncwarp();                                // sP is rewritten by the next tile
+      __syncwarp();                                // sP and the K stage are rewritten by the next tile
     }
 
     // ---- merge the warps of the CTA and publish the slice's partial result
+    float* sAccW = reinterpret_cast<float*>(sK[warp]);          // [DEC_RC][D], this warp's own staging bytes
 #pragma unroll
     for (int r = 0; r < DEC_RC; ++r) {
 #pragma unroll
-      for (int e = 0; e < E; ++e) sAcc[warp][r][lane * E + e] = acc[r][e];
+      for (int e = 0; e < E; ++e) sAccW[r * D + lane * E + e] = acc[r][e];
       if (lane == 0) { sM[warp][r] = m[r]; sL[warp][r] = l[r]; }
     }
     __syncthreads();
@@ -173,7 +189,7 @@ attn_decode_split_kernel(const DecodeParams p) {
 #pragma unroll
       for (int w = 0; w < DEC_WARPS; ++w) {
         const float wgt = (sM[w][r] == -INFINITY) ? 0.f : exp2f(sM[w][r] - mm);
-        o += sAcc[w][r][d] * wgt;
+        o += reinterpret_cast<const float*>(sK[w])[r * D + d] * wgt;
         ll += sL[w][r] * wgt;
       }
       p.part_o[(part_row0 + r0 + r) * D + d] = o;
