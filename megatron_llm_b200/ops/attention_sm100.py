@@ -84,7 +84,7 @@ def feature_ok(feature: str, hn: int, dtype, device) -> bool:
     if mode in ("0", "1"):
         _feature_state[key] = mode == "1"
         return _feature_state[key]
-    if torch.cuda.is_current_stream_capturing():
+    if torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing():
         return False                        # cannot self-test inside a graph capture; decided on the next eager call
     try:
         with torch.no_grad():
