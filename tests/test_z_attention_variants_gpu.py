@@ -5,8 +5,9 @@ decode kernel source runs on CPU threads in tests/test_kernel_emulation.py, the 
 there too.)
 
 Every check runs in its own process with a hard timeout, so a fault or a hang in one of these first runs cannot take
-the rest of the GPU suite with it, and is marked ``xfail(strict=False)``: XPASS in the log = validated on hardware,
-XFAIL = the variant is broken there (production code then self-tests it off, see ops/attention_sm100.py)."""
+the rest of the GPU suite with it.  A check that passes is an ordinary PASS (= validated on hardware); one that fails
+is reported as XFAIL with the reason instead of turning the suite red, because nothing here could be debugged on a
+device beforehand (production code self-tests such a variant off and falls back, see ops/attention_sm100.py)."""
 import json
 import os
 import subprocess
@@ -14,9 +15,7 @@ import sys
 
 import pytest
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.xfail(strict=False, reason="first hardware run of these kernel variants (no GPU budget was "
-                                                     "left when they were written); XPASS = validated")]
+pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 PRELUDE = r'''
@@ -194,8 +193,7 @@ res["used"] = dict(decode_kernel=float(attention_sm100._feature_state.get(("deco
 '''
 
 
-@pytest.mark.parametrize("name", list(CHECKS))
-def test_attention_variant_on_hardware(name):
+def _run_check(name):
     code = PRELUDE % {"root": ROOT} + CHECKS[name] + '\nprint("RESULT " + json.dumps(res))\n'
     env = dict(os.environ, MLB200_FORCE_CPU="0", MLB200_DISABLE_KERNELS="0")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=420)
@@ -204,3 +202,12 @@ def test_attention_variant_on_hardware(name):
     print(json.dumps(res, indent=1))
     bad = {f"{case}.{key}": val for case, d in res.items() for key, val in d.items() if not (val == val and val < 2e-2)}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name", list(CHECKS))
+def test_attention_variant_on_hardware(name):
+    try:
+        _run_check(name)
+    except Exception as e:  # noqa: BLE001 - incl. subprocess.TimeoutExpired
+        pytest.xfail(f"first hardware run of '{name}' failed (never debugged on a device): {type(e).__name__}: "
+                     f"{str(e)[-1500:]}")
