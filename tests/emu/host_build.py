@@ -56,18 +56,37 @@ def launches_to_host(src: str) -> str:
         i = e + 1
 
 
-def build(cu_files, out_dir, name="emu_kernels", extra_cpp=()):
-    """Compile ``cu_files`` (names inside csrc/) plus ``extra_cpp`` (paths) into ``<out_dir>/<name>.so``."""
+def _host_sources(cu_files, out_dir, mutate=None):
     os.makedirs(out_dir, exist_ok=True)
     sources = []
     for f in cu_files:
-        body = launches_to_host(open(os.path.join(CSRC, f)).read())
+        body = open(os.path.join(CSRC, f)).read()
+        if mutate is not None:
+            body = mutate(f, body)
+        body = launches_to_host(body)
         assert "<<<" not in body and "asm volatile" not in body, f
         dst = os.path.join(out_dir, f.replace(".cu", "_host.cpp"))
         with open(dst, "w") as fh:
             fh.write('#include "cuda_emu.h"\n' + body)
         sources.append(dst)
+    return sources
+
+
+def build(cu_files, out_dir, name="emu_kernels", extra_cpp=()):
+    """Compile ``cu_files`` (names inside csrc/) plus ``extra_cpp`` (paths) into ``<out_dir>/<name>.so``."""
+    sources = _host_sources(cu_files, out_dir)
     so = os.path.join(out_dir, name + ".so")
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-w",
                            "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources, *extra_cpp, "-o", so])
     return so
+
+
+def build_race_driver(cu_files, out_dir, name="race_driver", mutate=None, defines=()):
+    """``race_driver.cpp`` + the kernels as an executable instrumented by ThreadSanitizer (see the driver's header).
+    ``mutate(file_name, source) -> source`` lets a test break a kernel on purpose to show that the race is found."""
+    sources = _host_sources(cu_files, out_dir, mutate)
+    exe = os.path.join(out_dir, name)
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fsanitize=thread", "-pthread", "-w",
+                           *["-D" + d for d in defines], "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources,
+                           os.path.join(EMU, "race_driver.cpp"), "-o", exe])
+    return exe

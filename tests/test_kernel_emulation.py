@@ -416,3 +416,27 @@ def test_embedding_kernels_on_cpu_threads(kernels, sbh):
     d = (dout.float().transpose(0, 1) if sbh else dout.float()).reshape(b * s, H)
     ref_dw = torch.ones(rows_local, H).index_add_(0, local.reshape(-1)[owned.reshape(-1)], d[owned.reshape(-1)])
     assert (dw - ref_dw).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# shared-memory race check: the same host build under ThreadSanitizer
+# ------------------------------------------------------------------------------------------------------------------
+
+def test_simt_kernels_have_no_shared_memory_races(tmp_path):
+    """One OS thread per CUDA thread makes a missing __syncthreads / __syncwarp a data race that ThreadSanitizer sees:
+    decode attention, norms, cross-entropy, softmax, the flat norm reduction and the embedding scatter-add run clean,
+    and a decode kernel with one __syncwarp removed on purpose is reported (so a clean run means something)."""
+    import subprocess
+    files = ["attention_decode.cu", "norm.cu", "ce.cu", "softmax.cu", "optim.cu", "embedding.cu"]
+    exe = host_build.build_race_driver(files, str(tmp_path / "clean"))
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+
+    def drop_a_barrier(name, src):
+        old = "      __syncwarp();\n      // ---- acc += P V"
+        assert src.count(old) == 1
+        return src.replace(old, "      // ---- acc += P V")
+    exe = host_build.build_race_driver(["attention_decode.cu"], str(tmp_path / "mutant"), mutate=drop_a_barrier,
+                                       defines=["RACE_DECODE_ONLY"])
+    r = subprocess.run([exe, "decode"], capture_output=True, text=True, timeout=600)
+    assert r.returncode != 0 and "ThreadSanitizer: data race" in r.stderr
