@@ -14,7 +14,16 @@ _LAUNCH = re.compile(r"((?:mlb::)?\w+(?:<[^<>;()]*>)?)\s*<<<")
 # the few inline-PTX statements of the SIMT files, replaced by their host meaning
 _PTX = [(re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::\s*"l"\((\w+)\), "f"\((\w+)\), '
                     r'"f"\((\w+)\), "f"\((\w+)\), "f"\((\w+)\)\s*:\s*"memory"\);'),
-         r"cuda_emu::atomic_add4(\1, \2, \3, \4, \5);")]
+         r"cuda_emu::atomic_add4(\1, \2, \3, \4, \5);"),
+        # NVLS (csrc/comm.cu): the in-switch reduction / multicast store, emulated over the registered copies
+        (re.compile(r'asm volatile\("multimem\.ld_reduce\.relaxed\.sys\.global\.add\.v4\.f32 \{%0, %1, %2, %3\}, \[%4\];"\s*'
+                    r':\s*"=f"\((v\[u\])\.x\), "=f"\(v\[u\]\.y\), "=f"\(v\[u\]\.z\), "=f"\(v\[u\]\.w\)\s*'
+                    r':\s*"l"\(([^;]*?)\)\s*:\s*"memory"\);', re.S),
+         r"\1 = cuda_emu::multimem_ld_reduce_add_v4(\2);"),
+        (re.compile(r'asm volatile\("multimem\.st\.relaxed\.sys\.global\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::\s*'
+                    r'"l"\(([^;]*?)\),\s*"f"\(([\w.]+)\), "f"\(([\w.]+)\), "f"\(([\w.]+)\), "f"\(([\w.]+)\)\s*'
+                    r':\s*"memory"\);', re.S),
+         r"cuda_emu::multimem_st_v4(\1, \2, \3, \4, \5);")]
 
 
 def _split_top_level(text):

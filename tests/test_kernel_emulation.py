@@ -440,3 +440,72 @@ def test_simt_kernels_have_no_shared_memory_races(tmp_path):
                                        defines=["RACE_DECODE_ONLY"])
     r = subprocess.run([exe, "decode"], capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "ThreadSanitizer: data race" in r.stderr
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# peer-memory collectives: ranks = processes, symmetric memory = files every rank maps (tests/emu/comm_rank.py)
+# ------------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def comm_lib(tmp_path_factory):
+    return host_build.build(["comm.cu"], str(tmp_path_factory.mktemp("emu_comm")))
+
+
+def _ranks(comm_lib, d, ranks, world, n, mode, epoch=1, ctas=2, timeout=300):
+    import subprocess
+    present = ",".join(str(r) for r in ranks)
+    procs = [subprocess.Popen([sys.executable, os.path.join(EMU, "comm_rank.py"), comm_lib, str(d), str(r), str(world),
+                               str(n), mode, str(epoch), str(ctas), present]) for r in ranks]
+    return [p.wait(timeout=timeout) for p in procs]
+
+
+def _symmetric_memory(d, world, n, seed):
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    data = [rng.standard_normal(n).astype(np.float32) for _ in range(world)]
+    for r in range(world):
+        data[r].tofile(os.path.join(d, f"buf{r}.bin"))
+        np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
+    return data
+
+
+@pytest.mark.parametrize("mode,world", [("peer_ar", 2), ("peer_rs", 3), ("nvls_ar", 3), ("nvls_rs", 2)])
+def test_dp_reduction_kernels_between_emulated_ranks(comm_lib, tmp_path, mode, world):
+    """csrc/comm.cu: the two-shot DP gradient reduction (peer loads, and the NVLS form with the in-switch reduction
+    emulated) between concurrent ranks: handshake in, reduce + 1/DP scale, all-gather / scatter, handshake out; then a
+    second epoch on the same pads."""
+    import numpy as np
+    n = world * 4 * 700
+    data = _symmetric_memory(tmp_path, world, n, seed=world)
+    assert _ranks(comm_lib, tmp_path, range(world), world, n, mode, epoch=1) == [0] * world
+    mean = sum(data) / world
+    slice_ = n // world
+    for r in range(world):
+        got = np.fromfile(os.path.join(tmp_path, f"buf{r}.bin"), dtype=np.float32)
+        pad = np.fromfile(os.path.join(tmp_path, f"pad{r}.bin"), dtype=np.int32)
+        assert pad[32] == 0 and pad[40] == 0                         # no timeout, CTA counter reset
+        if mode.endswith("_ar"):
+            assert np.allclose(got, mean, atol=1e-6)
+        else:                                                        # reduce-scatter: rank r owns slice r
+            assert np.allclose(got[r * slice_:(r + 1) * slice_], mean[r * slice_:(r + 1) * slice_], atol=1e-6)
+            other = (r + 1) % world
+            assert np.array_equal(got[other * slice_:(other + 1) * slice_], data[r][other * slice_:(other + 1) * slice_])
+    if mode.endswith("_ar"):                                         # next step: epoch 2 over the reduced buffers
+        assert _ranks(comm_lib, tmp_path, range(world), world, n, mode, epoch=2) == [0] * world
+        got = np.fromfile(os.path.join(tmp_path, "buf0.bin"), dtype=np.float32)
+        assert np.allclose(got, mean, atol=1e-6)                     # the mean of equal copies is the copy
+
+
+def test_lost_peer_times_out_instead_of_hanging(comm_lib, tmp_path):
+    """A rank whose peer never arrives leaves its bounded spin, records the timeout in its pad (what
+    ``symm.check_timeouts`` polls once per training step) and the kernel retires."""
+    import numpy as np
+    n = 2 * 4 * 64
+    _symmetric_memory(tmp_path, 2, n, seed=9)
+    assert _ranks(comm_lib, tmp_path, [0], 2, n, "barrier", ctas=1) == [0]
+    pad = np.fromfile(os.path.join(tmp_path, "pad0.bin"), dtype=np.int32)
+    assert pad[32] == 1
+    # both present: the barrier completes without the flag
+    _symmetric_memory(tmp_path, 2, n, seed=9)
+    assert _ranks(comm_lib, tmp_path, [0, 1], 2, n, "barrier", ctas=1) == [0, 0]
+    assert all(np.fromfile(os.path.join(tmp_path, f"pad{r}.bin"), dtype=np.int32)[32] == 0 for r in range(2))
