@@ -184,8 +184,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float m_new = fmaxf(m_used, mx * p.scale_log2);
       // lazy rescale: only when the running max grew by more than 2^8 (warp-uniform decision)
       const bool grow = (m_new > m_used + 8.0f) || (m_used == -INFINITY && m_new != -INFINITY);
+      bool saw_pv = false;                 // (warp-uniform) this iteration already waited for PV_{t-1}
       if (__any_sync(0xffffffffu, grow && t > 0)) {
         mbar_wait(o_done, (t - 1) & 1);    // PV_{t-1} must have landed in O
+        saw_pv = true;
         tc_fence_after();
         const float alpha = grow ? ((m_used == -INFINITY) ? 0.f : fast_exp2(m_used - m_new)) : 1.f;
         if (grow) { m_used = m_new; l *= alpha; }
@@ -232,6 +234,12 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_st_32x16(p_addr + c * 16, pk);
       }
       tmem_st_wait();
+      // Every warp observes EVERY phase of o_done, one per PV: a parity wait can only tell two consecutive phases
+      // apart, and with two S buffers a warp may otherwise finish its last tile while PV_{n-2} is still pending and
+      // take the epilogue's wait for PV_{n-1} as already satisfied (found by running this kernel on the functional
+      // tcgen05 model under ThreadSanitizer, tests/test_attention_kernel_model.py).  PV_t cannot complete before this
+      // warp arrives on p_full below, so the barrier is never more than one phase ahead of the waiter.
+      if (t > 0 && !saw_pv) mbar_wait(o_done, (t - 1) & 1);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[st]);

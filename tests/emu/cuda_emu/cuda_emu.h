@@ -135,6 +135,8 @@ using cudaStream_t = void*;
 using cudaError_t = int;
 constexpr cudaError_t cudaSuccess = 0;
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+#define CUDART_VERSION 12090
+inline cudaError_t cudaFree(void*) { return cudaSuccess; }
 inline float __expf(float x) { return std::exp(x); }
 inline float __logf(float x) { return std::log(x); }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }

@@ -1,9 +1,12 @@
-// Host stand-in for csrc/ptx.cuh, limited to what the peer-memory kernels of csrc/comm.cu use (system-scope loads /
-// stores and fences become C++ atomics; "peers" are other PROCESSES that map the same shared memory, see
-// tests/test_kernel_emulation.py).  The tcgen05 / TMA / mbarrier wrappers of the real header have no host meaning and
-// are not provided: a translation unit that needs them cannot be built for the host.
+// Host stand-in for csrc/ptx.cuh (see cuda_emu.h and tcgen05_model.h):
+//   * system-scope loads / stores / fences of the peer-memory kernels (csrc/comm.cu) become C++ atomics; "peers" are other
+//     PROCESSES that map the same files (tests/emu/comm_rank.py);
+//   * mbarrier / TMA / tensor memory / tcgen05.mma wrappers run on the functional model of tcgen05_model.h;
+//   * the descriptor builders (make_smem_desc, make_idesc_f16) are NOT re-implemented: host_build.py copies their source
+//     out of the real header into "ptx_real_extract.h", so the kernels' descriptors are decoded by the model as the
+//     real code encodes them.
 #pragma once
-#include "cuda_emu.h"
+#include "tcgen05_model.h"
 
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }   // (keeps the bounded spins of the kernels time-like)
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
@@ -14,11 +17,183 @@ inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return
 template <class T> inline T __ldcs(const T* p) { return *p; }
 
 namespace mlb {
+// ---- system-scope flags
 inline int ld_acquire_sys(const int* p) { return std::atomic_ref<const int>(*p).load(std::memory_order_acquire); }
 inline int ld_relaxed_sys(const int* p) { return std::atomic_ref<const int>(*p).load(std::memory_order_relaxed); }
 inline void st_release_sys(int* p, int v) { std::atomic_ref<int>(*p).store(v, std::memory_order_release); }
 inline uint4 ld_v4_relaxed_sys(const void* p) { uint4 r; std::memcpy(&r, p, 16); return r; }
 inline void st_v4(void* p, const uint4& v) { std::memcpy(p, &v, 16); }
+
+// ---- shared-memory addresses, misc
+inline uint32_t smem_u32(const void* p) { return uint32_t(static_cast<const uint8_t*>(p) - cuda_emu::bm->smem); }
+inline uint32_t lane_id() { return threadIdx.x & 31; }
+inline uint32_t pack_bf16x2(float a, float b) {
+  return uint32_t(__float2bfloat16_rn(a).bits) | (uint32_t(__float2bfloat16_rn(b).bits) << 16);
+}
+inline uint32_t pack_f16x2(float a, float b) {
+  _Float16 x = _Float16(a), y = _Float16(b); uint16_t lo, hi; std::memcpy(&lo, &x, 2); std::memcpy(&hi, &y, 2);
+  return uint32_t(lo) | (uint32_t(hi) << 16);
+}
+inline float2 unpack_bf16x2(uint32_t u) { return float2{cuda_emu::to_float16bits(uint16_t(u), true), cuda_emu::to_float16bits(uint16_t(u >> 16), true)}; }
+inline float2 unpack_f16x2(uint32_t u) { return float2{cuda_emu::to_float16bits(uint16_t(u), false), cuda_emu::to_float16bits(uint16_t(u >> 16), false)}; }
+inline float warp_sum(float v) { for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o); return v; }
+inline float warp_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o)); return v; }
+
+// ---- mbarrier
+inline void mbar_init(uint64_t* bar, uint32_t count) {
+  auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
+  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  *b = cuda_emu::MBar{uint8_t(count), uint8_t(count), 0, 0, 0};
+}
+inline void fence_barrier_init() {}
+inline void fence_proxy_async_smem() {}
+inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
+  for (;;) {
+    {
+      std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+      if (b->phase != (parity & 1)) return;
+    }
+    std::this_thread::yield();
+  }
+}
+inline void mbar_arrive(uint64_t* bar) {
+  auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
+  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  b->pending -= 1;
+  cuda_emu::mbar_check(b);
+}
+inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
+  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  b->tx += int32_t(bytes);
+  b->pending -= 1;
+  cuda_emu::mbar_check(b);
+}
+inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
+  auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
+  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  b->tx -= int32_t(bytes);
+  cuda_emu::mbar_check(b);
+}
+
+// ---- TMA: 4-D tiled load through the 128-byte swizzle
+inline void tma_prefetch_desc(const void*) {}
+inline void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  const CUtensorMap& tm = *static_cast<const CUtensorMap*>(desc);
+  const uint32_t dst = smem_u32(smem_dst);
+  const uint32_t row_bytes = tm.box[0] * tm.elem_bytes;
+  uint32_t r = 0;
+  for (uint32_t i3 = 0; i3 < tm.box[3]; ++i3)
+    for (uint32_t i2 = 0; i2 < tm.box[2]; ++i2)
+      for (uint32_t i1 = 0; i1 < tm.box[1]; ++i1, ++r) {
+        const uint64_t x1 = c1 + i1, x2 = c2 + i2, x3 = c3 + i3;
+        const bool row_ok = c1 >= 0 && c2 >= 0 && c3 >= 0 && x1 < tm.dims[1] && x2 < tm.dims[2] && x3 < tm.dims[3];
+        for (uint32_t byte = 0; byte < row_bytes; byte += tm.elem_bytes) {
+          const uint64_t x0 = uint64_t(c0) + byte / tm.elem_bytes;
+          uint32_t a = dst + r * row_bytes + byte;
+          if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B) a = cuda_emu::swizzle128(a);
+          if (row_ok && c0 >= 0 && x0 < tm.dims[0])
+            std::memcpy(cuda_emu::smem_ptr(a), tm.base + x0 * tm.elem_bytes + x1 * tm.strides[1] + x2 * tm.strides[2] +
+                                                 x3 * tm.strides[3], tm.elem_bytes);
+          else
+            std::memset(cuda_emu::smem_ptr(a), 0, tm.elem_bytes);          // out-of-bounds elements are zero-filled
+        }
+      }
+  mbar_complete_tx(bar, r * row_bytes);                                      // (the full box counts, in or out of bounds)
+}
+
+// ---- tensor memory
+template <int G = 1> inline void tmem_alloc(uint32_t* smem_out, uint32_t) { if ((threadIdx.x & 31) == 0) *smem_out = 0; }   // (warp-collective)
+template <int G = 1> inline void tmem_relinquish() {}
+template <int G = 1> inline void tmem_dealloc(uint32_t, uint32_t) {}
+inline void tc_fence_before() {}
+inline void tc_fence_after() {}
+inline void tmem_ld_wait() {}
+inline void tmem_st_wait() {}
+template <int N> inline void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+  const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
+  for (int i = 0; i < N; ++i) r[i] = cuda_emu::tmem_at(lane, col + i);
+}
+template <int N> inline void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
+  const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
+  for (int i = 0; i < N; ++i) cuda_emu::tmem_at(lane, col + i) = r[i];
+}
+inline void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) { tmem_ld_n<32>(taddr, r); }
+inline void tmem_ld_32x16(uint32_t taddr, uint32_t (&r)[16]) { tmem_ld_n<16>(taddr, r); }
+inline void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) { tmem_st_n<32>(taddr, r); }
+
+}  // namespace mlb
+
+#define __host__
+#include "ptx_real_extract.h"      // enum kSwizzle*, make_smem_desc, make_idesc_f16: copied from the real header
+
+namespace mlb {
+// ---- tcgen05.mma kind::f16, cta_group::1, M = 128: D[128 x N] (+)= A[128 x 16] * B[16 x N], executed at issue
+struct SmemOperand {
+  uint32_t start, lbo, sbo, swizzle;
+  explicit SmemOperand(uint64_t d)
+      : start(uint32_t(d & 0x3FFF) << 4), lbo(uint32_t((d >> 16) & 0x3FFF) << 4), sbo(uint32_t((d >> 32) & 0x3FFF) << 4),
+        swizzle(uint32_t(d >> 61) & 7) {}
+  // element (mn, k) of an operand tile, k in [0, 16).  K-major: rows of 128 bytes hold the reduction dim, 8-row atoms are
+  // SBO apart.  MN-major: rows of 128 bytes hold 64 mn-elements, the next 64 are LBO apart, 8 k-rows are SBO apart.
+  uint16_t at(uint32_t mn, uint32_t k, bool mn_major) const {
+    uint32_t a = mn_major ? start + (mn / 64) * lbo + (k / 8) * sbo + (k % 8) * 128 + (mn % 64) * 2
+                          : start + (mn / 8) * sbo + (mn % 8) * 128 + k * 2;
+    if (swizzle == kSwizzle128B) a = cuda_emu::swizzle128(a);
+    uint16_t v; std::memcpy(&v, cuda_emu::smem_ptr(a), 2);
+    return v;
+  }
+};
+struct IDesc {
+  uint32_t M, N; bool a_bf16, b_bf16, a_mn, b_mn;
+  explicit IDesc(uint32_t d)
+      : M(((d >> 24) & 0x1F) << 4), N(((d >> 17) & 0x3F) << 3), a_bf16(((d >> 7) & 7) == 1), b_bf16(((d >> 10) & 7) == 1),
+        a_mn((d >> 15) & 1), b_mn((d >> 16) & 1) {}
+};
+inline void umma_store(uint32_t tmem_d, const IDesc& id, const std::vector<float>& acc, uint32_t accumulate) {
+  const uint32_t lane0 = tmem_d >> 16, col0 = tmem_d & 0xFFFF;
+  for (uint32_t m = 0; m < id.M; ++m)
+    for (uint32_t n = 0; n < id.N; ++n) {
+      uint32_t& slot = cuda_emu::tmem_at(lane0 + m, col0 + n);
+      slot = __float_as_uint((accumulate ? __uint_as_float(slot) : 0.f) + acc[m * id.N + n]);
+    }
+}
+template <int G = 1>
+inline void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const IDesc id(idesc);
+  const SmemOperand A(desc_a), B(desc_b);
+  std::vector<float> acc(id.M * id.N, 0.f), b(16 * id.N);
+  for (uint32_t n = 0; n < id.N; ++n)
+    for (uint32_t k = 0; k < 16; ++k) b[k * id.N + n] = cuda_emu::to_float16bits(B.at(n, k, id.b_mn), id.b_bf16);
+  for (uint32_t m = 0; m < id.M; ++m)
+    for (uint32_t k = 0; k < 16; ++k) {
+      const float a = cuda_emu::to_float16bits(A.at(m, k, id.a_mn), id.a_bf16);
+      for (uint32_t n = 0; n < id.N; ++n) acc[m * id.N + n] += a * b[k * id.N + n];
+    }
+  umma_store(tmem_d, id, acc, accumulate);
+}
+// A from tensor memory: lane = row, 16 k-elements as 8 columns of 16-bit pairs (even element in the low half)
+inline void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const IDesc id(idesc);
+  const SmemOperand B(desc_b);
+  std::vector<float> acc(id.M * id.N, 0.f), b(16 * id.N);
+  for (uint32_t n = 0; n < id.N; ++n)
+    for (uint32_t k = 0; k < 16; ++k) b[k * id.N + n] = cuda_emu::to_float16bits(B.at(n, k, id.b_mn), id.b_bf16);
+  const uint32_t alane = tmem_a >> 16, acol = tmem_a & 0xFFFF;
+  for (uint32_t m = 0; m < id.M; ++m)
+    for (uint32_t k = 0; k < 16; ++k) {
+      const uint32_t word = cuda_emu::tmem_at(alane + m, acol + k / 2);
+      const float a = cuda_emu::to_float16bits(uint16_t(k & 1 ? word >> 16 : word), id.a_bf16);
+      for (uint32_t n = 0; n < id.N; ++n) acc[m * id.N + n] += a * b[k * id.N + n];
+    }
+  umma_store(tmem_d, id, acc, accumulate);
+}
+template <int G = 1> inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }     // the MMAs above already retired
+
+// run-time 16-bit format helpers of the real header
+inline uint32_t pack_16x2(int fp16, float a, float b) { return fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }
+inline float2 unpack_16x2(int fp16, uint32_t u) { return fp16 ? unpack_f16x2(u) : unpack_bf16x2(u); }
 }  // namespace mlb
 
 namespace cuda_emu {

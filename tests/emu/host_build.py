@@ -23,7 +23,14 @@ _PTX = [(re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2,
         (re.compile(r'asm volatile\("multimem\.st\.relaxed\.sys\.global\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::\s*'
                     r'"l"\(([^;]*?)\),\s*"f"\(([\w.]+)\), "f"\(([\w.]+)\), "f"\(([\w.]+)\), "f"\(([\w.]+)\)\s*'
                     r':\s*"memory"\);', re.S),
-         r"cuda_emu::multimem_st_v4(\1, \2, \3, \4, \5);")]
+         r"cuda_emu::multimem_st_v4(\1, \2, \3, \4, \5);"),
+        # attention kernels (csrc/attention_common.cuh, attention_bwd_sm100.cu): exp2, the 16-column tcgen05.st, the
+        # named barrier of a 128-thread warpgroup -- on the functional model of tcgen05_model.h
+        (re.compile(r'asm volatile\("ex2\.approx\.ftz\.f32 %0, %1;" : "=f"\((\w+)\) : "f"\((\w+)\)\);'), r"\1 = exp2f(\2);"),
+        (re.compile(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?:\s*"memory"\);', re.S),
+         r"mlb::tmem_st_n<16>(taddr, r);"),
+        (re.compile(r'asm volatile\("bar\.sync (\d+), (\d+);" ::: "memory"\);'), r"cuda_emu::named_barrier(\1, \2);"),
+        (re.compile(r"extern __shared__ uint8_t smem_raw\[\];"), r"uint8_t* smem_raw = cuda_emu::bm->smem;")]
 
 
 def _split_top_level(text):
@@ -61,12 +68,34 @@ def launches_to_host(src: str) -> str:
             depth -= src[e] == ")"
             if depth == 0:
                 break
-        out.append(f"cuda_emu::launch(dim3({cfg[0]}), dim3({cfg[1]}).x, [&] {{ {m.group(1)}({src[k + 1:e]}); }})")
+        call = f"[&] {{ {m.group(1)}({src[k + 1:e]}); }}"
+        if len(cfg) > 2 and cfg[2] != "0":      # dynamic shared memory: a kernel of the tcgen05 / TMA model
+            out.append(f"cuda_emu::launch_dyn(dim3({cfg[0]}), dim3({cfg[1]}).x, {cfg[2]}, {call})")
+        else:
+            out.append(f"cuda_emu::launch(dim3({cfg[0]}), dim3({cfg[1]}).x, {call})")
         i = e + 1
+
+
+_MODEL_HEADERS = ("attention_common.cuh",)       # csrc headers with inline PTX: transformed copies shadow the originals
+
+
+def _write_model_headers(out_dir):
+    """For the kernels that run on the functional tcgen05 / TMA model: a transformed copy of the csrc headers that carry
+    inline PTX, and the descriptor builders of the REAL ptx.cuh (the model decodes what the real code encodes)."""
+    for h in _MODEL_HEADERS:
+        with open(os.path.join(out_dir, h), "w") as fh:
+            fh.write(launches_to_host(open(os.path.join(CSRC, h)).read()))
+    real = open(os.path.join(CSRC, "ptx.cuh")).read()
+    a = real.index("// ---------------------------------------------------------------- UMMA descriptors")
+    b = real.index("// ---------------------------------------------------------------- cluster")
+    with open(os.path.join(out_dir, "ptx_real_extract.h"), "w") as fh:
+        fh.write("// extracted verbatim from csrc/ptx.cuh by tests/emu/host_build.py\n#pragma once\nnamespace mlb {\n"
+                 + real[a:b] + "}  // namespace mlb\n")
 
 
 def _host_sources(cu_files, out_dir, mutate=None):
     os.makedirs(out_dir, exist_ok=True)
+    _write_model_headers(out_dir)
     sources = []
     for f in cu_files:
         body = open(os.path.join(CSRC, f)).read()
@@ -86,16 +115,16 @@ def build(cu_files, out_dir, name="emu_kernels", extra_cpp=()):
     sources = _host_sources(cu_files, out_dir)
     so = os.path.join(out_dir, name + ".so")
     subprocess.check_call(["g++", "-O1", "-std=c++20", "-shared", "-fPIC", "-pthread", "-w",
-                           "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources, *extra_cpp, "-o", so])
+                           "-I" + out_dir, "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources, *extra_cpp, "-o", so])
     return so
 
 
-def build_race_driver(cu_files, out_dir, name="race_driver", mutate=None, defines=()):
+def build_race_driver(cu_files, out_dir, name="race_driver", mutate=None, defines=(), driver="race_driver.cpp"):
     """``race_driver.cpp`` + the kernels as an executable instrumented by ThreadSanitizer (see the driver's header).
     ``mutate(file_name, source) -> source`` lets a test break a kernel on purpose to show that the race is found."""
     sources = _host_sources(cu_files, out_dir, mutate)
     exe = os.path.join(out_dir, name)
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fsanitize=thread", "-pthread", "-w",
-                           *["-D" + d for d in defines], "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources,
-                           os.path.join(EMU, "race_driver.cpp"), "-o", exe])
+                           *["-D" + d for d in defines], "-I" + out_dir, "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources,
+                           os.path.join(EMU, driver), "-o", exe])
     return exe
