@@ -6,15 +6,22 @@
 //     out of the real header into "ptx_real_extract.h", so the kernels' descriptors are decoded by the model as the
 //     real code encodes them.
 #pragma once
+#include <chrono>
+
 #include "tcgen05_model.h"
 
 inline void __nanosleep(unsigned) { std::this_thread::yield(); }   // (keeps the bounded spins of the kernels time-like)
 inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
+inline unsigned long long atomicAdd(unsigned long long* p, unsigned long long v) {
+  return std::atomic_ref<unsigned long long>(*p).fetch_add(v, std::memory_order_acq_rel);
+}
 inline int atomicAdd(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_acq_rel); }
 inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
 inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
 inline uint4 make_uint4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) { return uint4{a, b, c, d}; }
 template <class T> inline T __ldcs(const T* p) { return *p; }
+template <class T> inline T __ldcg(const T* p) { return *p; }
 
 namespace mlb {
 // ---- system-scope flags
@@ -79,28 +86,48 @@ inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
 
 // ---- TMA: 4-D tiled load through the 128-byte swizzle
 inline void tma_prefetch_desc(const void*) {}
-inline void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3) {
+inline void tma_load_tile(void* smem_dst, const void* desc, uint64_t* bar, const int (&c)[4]) {
   const CUtensorMap& tm = *static_cast<const CUtensorMap*>(desc);
   const uint32_t dst = smem_u32(smem_dst);
   const uint32_t row_bytes = tm.box[0] * tm.elem_bytes;
+  uint32_t box[4] = {tm.box[0], 1, 1, 1};
+  uint64_t dims[4] = {tm.dims[0], 1, 1, 1}, strides[4] = {tm.elem_bytes, 0, 0, 0};
+  for (uint32_t i = 1; i < tm.rank; ++i) { box[i] = tm.box[i]; dims[i] = tm.dims[i]; strides[i] = tm.strides[i]; }
   uint32_t r = 0;
-  for (uint32_t i3 = 0; i3 < tm.box[3]; ++i3)
-    for (uint32_t i2 = 0; i2 < tm.box[2]; ++i2)
-      for (uint32_t i1 = 0; i1 < tm.box[1]; ++i1, ++r) {
-        const uint64_t x1 = c1 + i1, x2 = c2 + i2, x3 = c3 + i3;
-        const bool row_ok = c1 >= 0 && c2 >= 0 && c3 >= 0 && x1 < tm.dims[1] && x2 < tm.dims[2] && x3 < tm.dims[3];
+  for (uint32_t i3 = 0; i3 < box[3]; ++i3)
+    for (uint32_t i2 = 0; i2 < box[2]; ++i2)
+      for (uint32_t i1 = 0; i1 < box[1]; ++i1, ++r) {
+        const int64_t x1 = int64_t(c[1]) + i1, x2 = int64_t(c[2]) + i2, x3 = int64_t(c[3]) + i3;
+        const bool row_ok = x1 >= 0 && x2 >= 0 && x3 >= 0 && uint64_t(x1) < dims[1] && uint64_t(x2) < dims[2] && uint64_t(x3) < dims[3];
         for (uint32_t byte = 0; byte < row_bytes; byte += tm.elem_bytes) {
-          const uint64_t x0 = uint64_t(c0) + byte / tm.elem_bytes;
+          const int64_t x0 = int64_t(c[0]) + byte / tm.elem_bytes;
           uint32_t a = dst + r * row_bytes + byte;
           if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B) a = cuda_emu::swizzle128(a);
-          if (row_ok && c0 >= 0 && x0 < tm.dims[0])
-            std::memcpy(cuda_emu::smem_ptr(a), tm.base + x0 * tm.elem_bytes + x1 * tm.strides[1] + x2 * tm.strides[2] +
-                                                 x3 * tm.strides[3], tm.elem_bytes);
+          if (row_ok && x0 >= 0 && uint64_t(x0) < dims[0])
+            std::memcpy(cuda_emu::smem_ptr(a), tm.base + x0 * tm.elem_bytes + x1 * strides[1] + x2 * strides[2] +
+                                                 x3 * strides[3], tm.elem_bytes);
           else
             std::memset(cuda_emu::smem_ptr(a), 0, tm.elem_bytes);          // out-of-bounds elements are zero-filled
         }
       }
   mbar_complete_tx(bar, r * row_bytes);                                      // (the full box counts, in or out of bounds)
+}
+inline void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  tma_load_tile(smem_dst, desc, bar, {c0, c1, c2, c3});
+}
+inline void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+  tma_load_tile(smem_dst, desc, bar, {c0, c1, 0, 0});
+}
+inline void fence_proxy_async_global() {}
+inline void fence_proxy_async_all() {}
+inline void tma_store_commit() {}
+template <int N> inline void tma_store_wait_read() {}
+template <int N> inline void tma_store_wait() {}
+inline void red_add_release_sys(int* p, int v) { std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_release); }
+inline int atom_add_acqrel_sys(int* p, int v) { return std::atomic_ref<int>(*p).fetch_add(v, std::memory_order_acq_rel); }
+inline unsigned long long globaltimer_ns() {
+  return (unsigned long long)std::chrono::duration_cast<std::chrono::nanoseconds>(
+             std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
 // ---- tensor memory

@@ -30,7 +30,15 @@ _PTX = [(re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2,
         (re.compile(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?:\s*"memory"\);', re.S),
          r"mlb::tmem_st_n<16>(taddr, r);"),
         (re.compile(r'asm volatile\("bar\.sync (\d+), (\d+);" ::: "memory"\);'), r"cuda_emu::named_barrier(\1, \2);"),
-        (re.compile(r"extern __shared__ uint8_t smem_raw\[\];"), r"uint8_t* smem_raw = cuda_emu::bm->smem;")]
+        (re.compile(r"extern __shared__ uint8_t smem_raw\[\];"), r"uint8_t* smem_raw = cuda_emu::bm->smem;"),
+        # GEMM header (csrc/gemm_sm100.cuh): the bulk copies / multicast store of the fused modes.  Those modes need
+        # co-resident CTAs and peers and are NOT run on the model; the statements only have to compile.
+        (re.compile(r'asm volatile\("cp\.async\.bulk\.shared::cluster\.global\.mbarrier::complete_tx::bytes.*?:\s*"memory"\);', re.S),
+         r"std::memcpy(smem_dst, gsrc, bytes); mbar_complete_tx(bar, bytes);"),
+        (re.compile(r'asm volatile\("cp\.async\.bulk\.global\.shared::cta\.bulk_group.*?:\s*"memory"\);', re.S),
+         r"std::memcpy(gdst, smem_src, bytes);"),
+        (re.compile(r'asm volatile\("multimem\.st\.relaxed\.sys\.global\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};" ::"l"\(mc_addr\),.*?:\s*"memory"\);', re.S),
+         r"cuda_emu::multimem_st_v4(static_cast<float*>(mc_addr), __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));")]
 
 
 def _split_top_level(text):
@@ -76,7 +84,7 @@ def launches_to_host(src: str) -> str:
         i = e + 1
 
 
-_MODEL_HEADERS = ("attention_common.cuh",)       # csrc headers with inline PTX: transformed copies shadow the originals
+_MODEL_HEADERS = ("attention_common.cuh", "gemm_sm100.cuh")       # csrc headers with inline PTX: transformed copies shadow the originals
 
 
 def _write_model_headers(out_dir):

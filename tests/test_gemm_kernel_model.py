@@ -1,0 +1,59 @@
+"""The 1-CTA tcgen05 GEMM kernel (csrc/gemm_sm100.cuh / gemm_sm100.cu, plain mode) executed on the CPU on the
+functional model of TMA / mbarrier / tensor memory / tcgen05.mma (tests/emu/cuda_emu/tcgen05_model.h, see
+tests/test_attention_kernel_model.py): NT / NN / TN operand layouts (K-major and MN-major shared-memory descriptors for
+A and B), the four epilogues, both tile widths, ragged M / N / K edges (TMA zero fill, guarded stores), fp16 operands,
+a persistent CTA walking several tiles; and the barrier protocol under ThreadSanitizer.  The fused all-gather /
+reduce-scatter modes need co-resident CTAs and peers and are not run here; the 2-CTA kernel (cta_group::2, clusters)
+is outside the model."""
+import ctypes
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "emu"))
+import host_build  # noqa: E402
+
+EPI_16, EPI_F32_ACCUM, EPI_F32, EPI_16_ACCUM = 0, 1, 2, 3
+
+
+@pytest.fixture(scope="module")
+def lib(tmp_path_factory):
+    return ctypes.CDLL(host_build.build(["gemm_sm100.cu"], str(tmp_path_factory.mktemp("emu_gemm"))))
+
+
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,epi,block_n,dtype", [
+    (128, 128, 64, 0, 0, EPI_16, 128, torch.bfloat16),          # NT (forward of a Linear), one tile
+    (200, 264, 136, 0, 0, EPI_16, 128, torch.bfloat16),         # ragged M / N / K
+    (256, 256, 128, 0, 1, EPI_16, 256, torch.bfloat16),         # NN (dgrad): B is MN-major, 256-wide tiles
+    (136, 128, 256, 1, 1, EPI_F32, 128, torch.bfloat16),        # TN (wgrad): A and B MN-major, fp32 output
+    (136, 200, 128, 1, 1, EPI_F32_ACCUM, 128, torch.bfloat16),  # ... accumulated into an fp32 main_grad
+    (128, 136, 72, 0, 0, EPI_16_ACCUM, 128, torch.bfloat16),    # 16-bit accumulate epilogue
+    (128, 256, 64, 0, 0, EPI_16, 256, torch.float16),           # fp16 operands and output
+    (640, 128, 192, 0, 0, EPI_16, 128, torch.bfloat16),         # persistent CTAs: 5 tiles on 4 "SMs"
+])
+def test_gemm_kernel_on_the_functional_model(lib, M, N, K, a_mn, b_mn, epi, block_n, dtype):
+    torch.manual_seed(M + N + K)
+    A, B = torch.randn(M, K).to(dtype), torch.randn(N, K).to(dtype)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out_dtype = dtype if epi in (EPI_16, EPI_16_ACCUM) else torch.float32
+    before = torch.randn(M, N).to(out_dtype) if epi in (EPI_F32_ACCUM, EPI_16_ACCUM) else None
+    c = before.clone() if before is not None else torch.full((M, N), float("nan"), dtype=out_dtype)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.mlb_gemm_bf16(p(a), p(b), p(c), M, N, K, a.stride(0), b.stride(0), c.stride(0), a_mn, b_mn, epi, block_n,
+                             int(dtype == torch.float16), 4, None) == 0
+    ref = A.float() @ B.float().t()
+    if before is not None:
+        ref = ref + before.float()
+    err = ((c.float() - ref).norm() / ref.norm()).item()
+    assert err < (1e-5 if out_dtype == torch.float32 else (3e-3 if dtype == torch.bfloat16 else 5e-4)), err
+
+
+def test_gemm_barrier_protocol_under_thread_sanitizer(tmp_path):
+    exe = host_build.build_race_driver(["gemm_sm100.cu"], str(tmp_path), name="gemm_race", driver="gemm_race_driver.cpp")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
