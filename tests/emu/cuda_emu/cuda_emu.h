@@ -137,6 +137,10 @@ constexpr cudaError_t cudaSuccess = 0;
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 #define CUDART_VERSION 12090
 inline cudaError_t cudaFree(void*) { return cudaSuccess; }
+template <class T> inline cudaError_t cudaMemcpyFromSymbol(void* dst, const T& symbol, size_t bytes) {
+  std::memcpy(dst, &symbol, bytes);
+  return cudaSuccess;
+}
 inline float __expf(float x) { return std::exp(x); }
 inline float __logf(float x) { return std::log(x); }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }

@@ -32,7 +32,15 @@ inline uint4 ld_v4_relaxed_sys(const void* p) { uint4 r; std::memcpy(&r, p, 16);
 inline void st_v4(void* p, const uint4& v) { std::memcpy(p, &v, 16); }
 
 // ---- shared-memory addresses, misc
-inline uint32_t smem_u32(const void* p) { return uint32_t(static_cast<const uint8_t*>(p) - cuda_emu::bm->smem); }
+inline uint32_t smem_u32(const void* p) {
+  return uint32_t(static_cast<const uint8_t*>(p) - cuda_emu::bm->smem) | (cuda_emu::bm->cluster_rank << 24);
+}
+// the same shared-memory object in CTA `rank` of the cluster
+template <class T> inline T* cluster_peer_ptr(T* p, uint32_t rank) {
+  return reinterpret_cast<T*>(cuda_emu::bm->cluster[rank]->smem + (reinterpret_cast<uint8_t*>(p) - cuda_emu::bm->smem));
+}
+inline uint32_t cluster_ctarank() { return cuda_emu::bm->cluster_rank; }
+inline void cluster_sync() { cuda_emu::bm->cluster_bar->arrive_and_wait(); }
 inline uint32_t lane_id() { return threadIdx.x & 31; }
 inline uint32_t pack_bf16x2(float a, float b) {
   return uint32_t(__float2bfloat16_rn(a).bits) | (uint32_t(__float2bfloat16_rn(b).bits) << 16);
@@ -49,7 +57,7 @@ inline float warp_max(float v) { for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, _
 // ---- mbarrier
 inline void mbar_init(uint64_t* bar, uint32_t count) {
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
-  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
   *b = cuda_emu::MBar{uint8_t(count), uint8_t(count), 0, 0, 0};
 }
 inline void fence_barrier_init() {}
@@ -58,7 +66,7 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
   for (;;) {
     {
-      std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+      std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
       if (b->phase != (parity & 1)) return;
     }
     std::this_thread::yield();
@@ -66,20 +74,20 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void mbar_arrive(uint64_t* bar) {
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
-  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
   b->pending -= 1;
   cuda_emu::mbar_check(b);
 }
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
-  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
   b->tx += int32_t(bytes);
   b->pending -= 1;
   cuda_emu::mbar_check(b);
 }
 inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
-  std::lock_guard<std::mutex> g(cuda_emu::bm->mu);
+  std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
   b->tx -= int32_t(bytes);
   cuda_emu::mbar_check(b);
 }
@@ -118,6 +126,33 @@ inline void tma_load_4d(void* smem_dst, const void* desc, uint64_t* bar, int c0,
 inline void tma_load_2d(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
   tma_load_tile(smem_dst, desc, bar, {c0, c1, 0, 0});
 }
+inline void mbar_arrive_cluster(uint64_t* bar, uint32_t cta_rank) { mbar_arrive(cluster_peer_ptr(bar, cta_rank)); }
+// cta_group::2 load: the data lands in THIS CTA's shared memory, the bytes complete on the LEADER CTA's barrier
+inline void tma_load_2d_2sm(void* smem_dst, const void* desc, uint64_t* bar, int c0, int c1) {
+  tma_load_tile(smem_dst, desc, cluster_peer_ptr(bar, 0), {c0, c1, 0, 0});
+}
+// shared -> global tile store (optionally an element-wise add), clipped to the tensor
+inline void tma_store_tile_2d(const void* desc, const void* smem_src, int c0, int c1, bool add) {
+  const CUtensorMap& tm = *static_cast<const CUtensorMap*>(desc);
+  const uint32_t src = smem_u32(smem_src) & 0xFFFFFFu, row_bytes = tm.box[0] * tm.elem_bytes;
+  for (uint32_t r = 0; r < tm.box[1]; ++r)
+    for (uint32_t byte = 0; byte < row_bytes; byte += tm.elem_bytes) {
+      const int64_t x0 = int64_t(c0) + byte / tm.elem_bytes, x1 = int64_t(c1) + r;
+      if (x0 < 0 || x1 < 0 || uint64_t(x0) >= tm.dims[0] || uint64_t(x1) >= tm.dims[1]) continue;
+      uint32_t a = src + r * row_bytes + byte;
+      if (tm.swizzle == CU_TENSOR_MAP_SWIZZLE_128B) a = cuda_emu::swizzle128(a);
+      uint8_t* g = const_cast<uint8_t*>(tm.base) + x0 * tm.elem_bytes + x1 * tm.strides[1];
+      const uint8_t* sp = cuda_emu::bm->smem + a;
+      if (add && tm.elem_bytes == 4) {
+        float v; std::memcpy(&v, sp, 4);
+        std::atomic_ref<float>(*reinterpret_cast<float*>(g)).fetch_add(v, std::memory_order_relaxed);
+      } else {
+        std::memcpy(g, sp, tm.elem_bytes);
+      }
+    }
+}
+inline void tma_store_2d(const void* desc, const void* smem_src, int c0, int c1) { tma_store_tile_2d(desc, smem_src, c0, c1, false); }
+inline void tma_reduce_add_2d(const void* desc, const void* smem_src, int c0, int c1) { tma_store_tile_2d(desc, smem_src, c0, c1, true); }
 inline void fence_proxy_async_global() {}
 inline void fence_proxy_async_all() {}
 inline void tma_store_commit() {}
@@ -164,11 +199,11 @@ struct SmemOperand {
         swizzle(uint32_t(d >> 61) & 7) {}
   // element (mn, k) of an operand tile, k in [0, 16).  K-major: rows of 128 bytes hold the reduction dim, 8-row atoms are
   // SBO apart.  MN-major: rows of 128 bytes hold 64 mn-elements, the next 64 are LBO apart, 8 k-rows are SBO apart.
-  uint16_t at(uint32_t mn, uint32_t k, bool mn_major) const {
+  uint16_t at(uint32_t mn, uint32_t k, bool mn_major, const cuda_emu::BlockModel* cta = nullptr) const {
     uint32_t a = mn_major ? start + (mn / 64) * lbo + (k / 8) * sbo + (k % 8) * 128 + (mn % 64) * 2
                           : start + (mn / 8) * sbo + (mn % 8) * 128 + k * 2;
     if (swizzle == kSwizzle128B) a = cuda_emu::swizzle128(a);
-    uint16_t v; std::memcpy(&v, cuda_emu::smem_ptr(a), 2);
+    uint16_t v; std::memcpy(&v, (cta ? cta : cuda_emu::bm)->smem + a, 2);     // descriptors hold CTA-local addresses
     return v;
   }
 };
@@ -186,8 +221,35 @@ inline void umma_store(uint32_t tmem_d, const IDesc& id, const std::vector<float
       slot = __float_as_uint((accumulate ? __uint_as_float(slot) : 0.f) + acc[m * id.N + n]);
     }
 }
+// cta_group::2 (issued by the leader): M = 256 rows, CTA r holds rows [128 r, 128 r + 128) of A and columns
+// [N/2 r, N/2 r + N/2) of B in its own shared memory at the descriptors' addresses, and receives its 128 rows of D
+// (all N columns) in its own tensor memory.
+inline void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  const IDesc id(idesc);
+  const SmemOperand A(desc_a), B(desc_b);
+  const uint32_t half_n = id.N / 2, col0 = tmem_d & 0xFFFF;
+  std::vector<float> b(16 * id.N);
+  for (uint32_t n = 0; n < id.N; ++n)
+    for (uint32_t k = 0; k < 16; ++k)
+      b[k * id.N + n] = cuda_emu::to_float16bits(B.at(n % half_n, k, id.b_mn, cuda_emu::bm->cluster[n / half_n]), id.b_bf16);
+  for (uint32_t r = 0; r < 2; ++r) {
+    cuda_emu::BlockModel* cta = cuda_emu::bm->cluster[r];
+    for (uint32_t m = 0; m < 128; ++m) {
+      std::vector<float> acc(id.N, 0.f);
+      for (uint32_t k = 0; k < 16; ++k) {
+        const float a = cuda_emu::to_float16bits(A.at(m, k, id.a_mn, cta), id.a_bf16);
+        for (uint32_t n = 0; n < id.N; ++n) acc[n] += a * b[k * id.N + n];
+      }
+      for (uint32_t n = 0; n < id.N; ++n) {
+        uint32_t& slot = cta->tmem[m * 512 + ((col0 + n) & 511)];
+        slot = __float_as_uint((accumulate ? __uint_as_float(slot) : 0.f) + acc[n]);
+      }
+    }
+  }
+}
 template <int G = 1>
 inline void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  if constexpr (G == 2) { umma_f16_ss_pair(tmem_d, desc_a, desc_b, idesc, accumulate); return; }
   const IDesc id(idesc);
   const SmemOperand A(desc_a), B(desc_b);
   std::vector<float> acc(id.M * id.N, 0.f), b(16 * id.N);
@@ -216,7 +278,10 @@ inline void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint3
     }
   umma_store(tmem_d, id, acc, accumulate);
 }
-template <int G = 1> inline void umma_commit(uint64_t* bar) { mbar_arrive(bar); }     // the MMAs above already retired
+template <int G = 1> inline void umma_commit(uint64_t* bar) {     // the MMAs above already retired
+  if constexpr (G == 2) { mbar_arrive(cluster_peer_ptr(bar, 0)); mbar_arrive(cluster_peer_ptr(bar, 1)); }   // multicast
+  else mbar_arrive(bar);
+}
 
 // run-time 16-bit format helpers of the real header
 inline uint32_t pack_16x2(int fp16, float a, float b) { return fp16 ? pack_f16x2(a, b) : pack_bf16x2(a, b); }

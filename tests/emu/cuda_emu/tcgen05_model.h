@@ -78,17 +78,22 @@ struct BlockModel {
   uint8_t* smem = nullptr;             // 1024-byte aligned dynamic shared memory
   size_t smem_bytes = 0;
   std::vector<uint32_t> tmem;          // [128][512]
-  std::mutex mu;                       // mbarrier operations
   std::map<int, std::unique_ptr<std::barrier<>>> named;
+  // thread-block cluster (cta_group::2 kernels): the CTAs of the cluster, this CTA's rank, a barrier over all threads.
+  // Shared-memory addresses carry the CTA rank in bit 24 (what the kernels' "leader's copy" address arithmetic assumes).
+  BlockModel* cluster[2] = {this, nullptr};
+  uint32_t cluster_rank = 0;
+  std::barrier<>* cluster_bar = nullptr;
   BlockModel() : tmem(128 * 512, 0xDEADBEEFu) {}
 };
 inline thread_local BlockModel* bm = nullptr;
+inline std::mutex& mbar_mutex() { static std::mutex m; return m; }       // every mbarrier operation (any CTA)
 
 inline uint32_t& tmem_at(uint32_t lane, uint32_t col) { return bm->tmem[(lane & 127) * 512 + (col & 511)]; }
 
 // the 128-byte swizzle: 16-byte chunk index (address bits 4-6) XOR row-in-atom (address bits 7-9)
 inline uint32_t swizzle128(uint32_t addr) { return addr ^ (((addr >> 7) & 7u) << 4); }
-inline uint8_t* smem_ptr(uint32_t addr) { return bm->smem + addr; }
+inline uint8_t* smem_ptr(uint32_t addr) { return bm->cluster[(addr >> 24) & 1]->smem + (addr & 0xFFFFFFu); }
 
 struct MBar { uint8_t expected, pending, phase, pad; int32_t tx; };
 static_assert(sizeof(MBar) == 8, "an mbarrier occupies 8 bytes of shared memory");
@@ -99,7 +104,7 @@ inline void mbar_check(MBar* b) {
 inline void named_barrier(int id, int count) {
   std::barrier<>* b;
   {
-    std::lock_guard<std::mutex> g(bm->mu);
+    std::lock_guard<std::mutex> g(mbar_mutex());
     auto& slot = bm->named[id];
     if (!slot) slot.reset(new std::barrier<>(count));
     b = slot.get();
@@ -136,6 +141,44 @@ void launch_dyn(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
         std::free(model.smem);
       }
 }
+
+// clusters of two CTAs (__cluster_dims__(2, 1, 1)): the pair runs concurrently, pairs one after the other
+template <class F>
+void launch_cluster2(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
+  for (unsigned pair = 0; pair < grid.x / 2; ++pair) {
+    Block block0(threads), block1(threads);
+    Block* blocks[2] = {&block0, &block1};
+    BlockModel model[2];
+    std::barrier<> cbar(2 * threads);
+    for (int r = 0; r < 2; ++r) {
+      model[r].smem_bytes = smem_bytes;
+      model[r].smem = static_cast<uint8_t*>(std::aligned_alloc(1024, (smem_bytes + 1023) / 1024 * 1024 + 1024));
+      std::memset(model[r].smem, 0xCD, smem_bytes);
+      model[r].cluster[0] = &model[0]; model[r].cluster[1] = &model[1];
+      model[r].cluster_rank = r;
+      model[r].cluster_bar = &cbar;
+    }
+    std::vector<std::thread> pool;
+    pool.reserve(2 * threads);
+    for (unsigned r = 0; r < 2; ++r)
+      for (unsigned t = 0; t < threads; ++t)
+        pool.emplace_back([&, r, t] {
+          blk = blocks[r];
+          bm = &model[r];
+          threadIdx = uint3{t, 0, 0};
+          blockIdx = uint3{2 * pair + r, 0, 0};
+          blockDim = dim3(threads);
+          gridDim = grid;
+          kernel();
+          blocks[r]->warp_bar[t >> 5]->arrive_and_drop();
+          blocks[r]->block_bar.arrive_and_drop();
+          cbar.arrive_and_drop();
+        });
+    for (auto& th : pool) th.join();
+    for (int r = 0; r < 2; ++r) std::free(model[r].smem);
+  }
+}
+#define __cluster_dims__(...)
 
 inline float to_float16bits(uint16_t h, bool is_bf16) {
   if (is_bf16) { uint32_t u = uint32_t(h) << 16; float f; std::memcpy(&f, &u, 4); return f; }

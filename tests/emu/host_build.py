@@ -30,6 +30,7 @@ _PTX = [(re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2,
         (re.compile(r'asm volatile\(\s*"tcgen05\.st\.sync\.aligned\.32x32b\.x16\.b32.*?:\s*"memory"\);', re.S),
          r"mlb::tmem_st_n<16>(taddr, r);"),
         (re.compile(r'asm volatile\("bar\.sync (\d+), (\d+);" ::: "memory"\);'), r"cuda_emu::named_barrier(\1, \2);"),
+        (re.compile(r'asm volatile\("mov\.u64 %0, %%clock64;" : "=l"\((\w+)\)\);'), r"\1 = 0;"),
         (re.compile(r"extern __shared__ uint8_t smem_raw\[\];"), r"uint8_t* smem_raw = cuda_emu::bm->smem;"),
         # GEMM header (csrc/gemm_sm100.cuh): the bulk copies / multicast store of the fused modes.  Those modes need
         # co-resident CTAs and peers and are NOT run on the model; the statements only have to compile.
@@ -60,6 +61,7 @@ def _split_top_level(text):
 def launches_to_host(src: str) -> str:
     for pat, repl in _PTX:
         src = pat.sub(repl, src)
+    cluster2 = "__cluster_dims__(2, 1, 1)" in src          # every kernel of such a file is launched as CTA pairs
     out, i = [], 0
     while True:
         m = _LAUNCH.search(src, i)
@@ -77,7 +79,9 @@ def launches_to_host(src: str) -> str:
             if depth == 0:
                 break
         call = f"[&] {{ {m.group(1)}({src[k + 1:e]}); }}"
-        if len(cfg) > 2 and cfg[2] != "0":      # dynamic shared memory: a kernel of the tcgen05 / TMA model
+        if cluster2:
+            out.append(f"cuda_emu::launch_cluster2(dim3({cfg[0]}), dim3({cfg[1]}).x, {cfg[2]}, {call})")
+        elif len(cfg) > 2 and cfg[2] != "0":      # dynamic shared memory: a kernel of the tcgen05 / TMA model
             out.append(f"cuda_emu::launch_dyn(dim3({cfg[0]}), dim3({cfg[1]}).x, {cfg[2]}, {call})")
         else:
             out.append(f"cuda_emu::launch(dim3({cfg[0]}), dim3({cfg[1]}).x, {call})")

@@ -1,10 +1,14 @@
-"""The 1-CTA tcgen05 GEMM kernel (csrc/gemm_sm100.cuh / gemm_sm100.cu, plain mode) executed on the CPU on the
-functional model of TMA / mbarrier / tensor memory / tcgen05.mma (tests/emu/cuda_emu/tcgen05_model.h, see
-tests/test_attention_kernel_model.py): NT / NN / TN operand layouts (K-major and MN-major shared-memory descriptors for
-A and B), the four epilogues, both tile widths, ragged M / N / K edges (TMA zero fill, guarded stores), fp16 operands,
-a persistent CTA walking several tiles; and the barrier protocol under ThreadSanitizer.  The fused all-gather /
-reduce-scatter modes need co-resident CTAs and peers and are not run here; the 2-CTA kernel (cta_group::2, clusters)
-is outside the model."""
+"""The tcgen05 GEMM kernels (plain mode) executed on the CPU on the functional model of TMA / mbarrier / tensor memory /
+tcgen05.mma (tests/emu/cuda_emu/tcgen05_model.h, see tests/test_attention_kernel_model.py):
+  * the 1-CTA kernel (csrc/gemm_sm100.cuh): NT / NN / TN operand layouts (K-major and MN-major shared-memory
+    descriptors for A and B), the four epilogues, both tile widths, ragged M / N / K edges (TMA zero fill, guarded
+    stores), fp16 operands, a persistent CTA walking several tiles;
+  * the 2-CTA kernel (csrc/gemm2_sm100.cu, ``cta_group::2``, the GEMM of the training step): the two CTAs of a cluster
+    run concurrently -- each loads its half of A and B, the bytes of both complete on the leader's barriers, the leader's
+    MMAs read both shared memories and write both tensor memories, commits are multicast, the epilogue warps arrive
+    remotely, results leave through swizzled shared memory and TMA stores / fp32 reduce-adds clipped by the tensor map;
+and their barrier protocols under ThreadSanitizer.  The fused all-gather / reduce-scatter modes need co-resident puller
+CTAs and peers and are not run here."""
 import ctypes
 import os
 import subprocess
@@ -22,7 +26,7 @@ EPI_16, EPI_F32_ACCUM, EPI_F32, EPI_16_ACCUM = 0, 1, 2, 3
 
 @pytest.fixture(scope="module")
 def lib(tmp_path_factory):
-    return ctypes.CDLL(host_build.build(["gemm_sm100.cu"], str(tmp_path_factory.mktemp("emu_gemm"))))
+    return ctypes.CDLL(host_build.build(["gemm_sm100.cu", "gemm2_sm100.cu"], str(tmp_path_factory.mktemp("emu_gemm"))))
 
 
 @pytest.mark.parametrize("M,N,K,a_mn,b_mn,epi,block_n,dtype", [
@@ -53,7 +57,38 @@ def test_gemm_kernel_on_the_functional_model(lib, M, N, K, a_mn, b_mn, epi, bloc
     assert err < (1e-5 if out_dtype == torch.float32 else (3e-3 if dtype == torch.bfloat16 else 5e-4)), err
 
 
-def test_gemm_barrier_protocol_under_thread_sanitizer(tmp_path):
-    exe = host_build.build_race_driver(["gemm_sm100.cu"], str(tmp_path), name="gemm_race", driver="gemm_race_driver.cpp")
+@pytest.mark.parametrize("M,N,K,a_mn,b_mn,epi,dtype", [
+    (256, 256, 64, 0, 0, EPI_16, torch.bfloat16),               # one 256 x 256 tile on one CTA pair
+    (520, 264, 200, 0, 1, EPI_16, torch.bfloat16),              # NN, ragged: clipped TMA stores, zero-filled loads
+    (256, 512, 192, 1, 1, EPI_F32, torch.bfloat16),             # TN, fp32 output boxes
+    (264, 256, 128, 1, 1, EPI_F32_ACCUM, torch.bfloat16),       # wgrad: fp32 reduce-add into main_grad
+    (256, 264, 72, 0, 0, EPI_16_ACCUM, torch.bfloat16),         # 16-bit accumulate (register epilogue)
+    (768, 512, 128, 0, 0, EPI_16, torch.float16),               # 6 tiles on 2 pairs, fp16
+])
+def test_two_cta_gemm_kernel_on_the_functional_model(lib, M, N, K, a_mn, b_mn, epi, dtype):
+    torch.manual_seed(M + N + K)
+    A, B = torch.randn(M, K).to(dtype), torch.randn(N, K).to(dtype)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    out_dtype = dtype if epi in (EPI_16, EPI_16_ACCUM) else torch.float32
+    before = torch.randn(M, N).to(out_dtype) if epi in (EPI_F32_ACCUM, EPI_16_ACCUM) else None
+    c = before.clone() if before is not None else torch.full((M, N), float("nan"), dtype=out_dtype)
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    assert lib.mlb_gemm_bf16_2cta(p(a), p(b), p(c), M, N, K, a.stride(0), b.stride(0), c.stride(0), a_mn, b_mn, epi,
+                                  int(dtype == torch.float16), 4, None) == 0
+    ref = A.float() @ B.float().t()
+    if before is not None:
+        ref = ref + before.float()
+    err = ((c.float() - ref).norm() / ref.norm()).item()
+    assert err < (1e-5 if out_dtype == torch.float32 else (3e-3 if dtype == torch.bfloat16 else 5e-4)), err
+
+
+def test_gemm_barrier_protocols_under_thread_sanitizer(tmp_path):
+    exe = host_build.build_race_driver(["gemm_sm100.cu"], str(tmp_path / "one"), name="gemm_race", driver="gemm_race_driver.cpp")
     r = subprocess.run([exe], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, r.stderr[-3000:]
+    exe = host_build.build_race_driver(["gemm_sm100.cu", "gemm2_sm100.cu"], str(tmp_path / "two"), name="gemm2_race",
+                                       driver="gemm2_race_driver.cpp")
+    for epi in ("0", "1", "3"):
+        r = subprocess.run([exe, epi], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (epi, r.stderr[-3000:])
