@@ -63,6 +63,7 @@ inline void mbar_init(uint64_t* bar, uint32_t count) {
 inline void fence_barrier_init() {}
 inline void fence_proxy_async_smem() {}
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
+  cuda_emu::chaos();
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
   for (;;) {
     {
@@ -73,12 +74,14 @@ inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 inline void mbar_arrive(uint64_t* bar) {
+  cuda_emu::chaos();
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
   std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
   b->pending -= 1;
   cuda_emu::mbar_check(b);
 }
 inline void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  cuda_emu::chaos();
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
   std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
   b->tx += int32_t(bytes);
@@ -95,6 +98,7 @@ inline void mbar_complete_tx(uint64_t* bar, uint32_t bytes) {
 // ---- TMA: 4-D tiled load through the 128-byte swizzle
 inline void tma_prefetch_desc(const void*) {}
 inline void tma_load_tile(void* smem_dst, const void* desc, uint64_t* bar, const int (&c)[4]) {
+  cuda_emu::chaos();
   const CUtensorMap& tm = *static_cast<const CUtensorMap*>(desc);
   const uint32_t dst = smem_u32(smem_dst);
   const uint32_t row_bytes = tm.box[0] * tm.elem_bytes;
@@ -174,10 +178,12 @@ inline void tc_fence_after() {}
 inline void tmem_ld_wait() {}
 inline void tmem_st_wait() {}
 template <int N> inline void tmem_ld_n(uint32_t taddr, uint32_t (&r)[N]) {
+  cuda_emu::chaos();
   const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < N; ++i) r[i] = cuda_emu::tmem_at(lane, col + i);
 }
 template <int N> inline void tmem_st_n(uint32_t taddr, const uint32_t (&r)[N]) {
+  cuda_emu::chaos();
   const uint32_t lane = (taddr >> 16) + (threadIdx.x & 31), col = taddr & 0xFFFF;
   for (int i = 0; i < N; ++i) cuda_emu::tmem_at(lane, col + i) = r[i];
 }
@@ -225,6 +231,7 @@ inline void umma_store(uint32_t tmem_d, const IDesc& id, const std::vector<float
 // [N/2 r, N/2 r + N/2) of B in its own shared memory at the descriptors' addresses, and receives its 128 rows of D
 // (all N columns) in its own tensor memory.
 inline void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  cuda_emu::chaos();
   const IDesc id(idesc);
   const SmemOperand A(desc_a), B(desc_b);
   const uint32_t half_n = id.N / 2, col0 = tmem_d & 0xFFFF;
@@ -250,6 +257,7 @@ inline void umma_f16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, 
 template <int G = 1>
 inline void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
   if constexpr (G == 2) { umma_f16_ss_pair(tmem_d, desc_a, desc_b, idesc, accumulate); return; }
+  cuda_emu::chaos();
   const IDesc id(idesc);
   const SmemOperand A(desc_a), B(desc_b);
   std::vector<float> acc(id.M * id.N, 0.f), b(16 * id.N);
@@ -264,6 +272,7 @@ inline void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint3
 }
 // A from tensor memory: lane = row, 16 k-elements as 8 columns of 16-bit pairs (even element in the low half)
 inline void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  cuda_emu::chaos();
   const IDesc id(idesc);
   const SmemOperand B(desc_b);
   std::vector<float> acc(id.M * id.N, 0.f), b(16 * id.N);

@@ -15,7 +15,9 @@
 // right barrier phase reads stale data here as well.  What the model cannot show is asynchrony-only bugs (e.g. a missing
 // tcgen05.fence) and performance.
 #pragma once
+#include <chrono>
 #include <condition_variable>
+#include <cstdlib>
 #include <map>
 #include <mutex>
 
@@ -88,6 +90,22 @@ struct BlockModel {
 };
 inline thread_local BlockModel* bm = nullptr;
 inline std::mutex& mbar_mutex() { static std::mutex m; return m; }       // every mbarrier operation (any CTA)
+
+// Schedule fuzzing (MLB_EMU_CHAOS=<seed>): random short stalls in front of barrier operations, TMA loads, MMAs and tensor
+// memory accesses, different per thread and per run, so that warps drift apart by whole tiles -- the situations in which
+// a barrier protocol that only works "because the other side is always faster" gives wrong results or hangs.
+inline int chaos_seed() {
+  static const int seed = [] { const char* e = std::getenv("MLB_EMU_CHAOS"); return e ? std::atoi(e) : 0; }();
+  return seed;
+}
+inline void chaos() {
+  if (chaos_seed() == 0) return;
+  static thread_local uint32_t rng = 0;
+  if (rng == 0) rng = uint32_t(chaos_seed()) * 2654435761u ^ (uint32_t(std::hash<std::thread::id>()(std::this_thread::get_id())) | 1u);
+  rng ^= rng << 13; rng ^= rng >> 17; rng ^= rng << 5;
+  if ((rng & 7u) == 0) std::this_thread::sleep_for(std::chrono::microseconds((rng >> 8) % 300));
+  else if ((rng & 3u) == 1) std::this_thread::yield();
+}
 
 inline uint32_t& tmem_at(uint32_t lane, uint32_t col) { return bm->tmem[(lane & 127) * 512 + (col & 511)]; }
 

@@ -92,3 +92,23 @@ def test_gemm_barrier_protocols_under_thread_sanitizer(tmp_path):
     for epi in ("0", "1", "3"):
         r = subprocess.run([exe, epi], capture_output=True, text=True, timeout=900)
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (epi, r.stderr[-3000:])
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_tcgen05_kernels_survive_schedule_fuzzing(tmp_path_factory, seed):
+    """Attention (both forward kernels + backward, window, dropout) and both GEMM kernels with random stalls in front of
+    every barrier operation, TMA load, MMA and tensor-memory access (MLB_EMU_CHAOS): warps drift apart by whole tiles,
+    so a protocol that relied on relative speed -- like the o_done wait of the single-tile attention kernel before its
+    fix, which fails this check every time -- produces wrong numbers or hangs."""
+    import json
+    base = tmp_path_factory.getbasetemp()
+    attn = os.path.join(base, "chaos_attn", "emu_kernels.so")
+    gm = os.path.join(base, "chaos_gemm", "emu_kernels.so")
+    if not os.path.exists(attn):
+        host_build.build(["attention_sm100.cu", "attention_bwd_sm100.cu"], os.path.dirname(attn))
+        host_build.build(["gemm_sm100.cu", "gemm2_sm100.cu"], os.path.dirname(gm))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emu", "chaos_check.py"), attn, gm],
+                       env=dict(os.environ, MLB_EMU_CHAOS=str(seed)), capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
+    assert all(v == v and v < 6e-3 for v in res.values()), res
