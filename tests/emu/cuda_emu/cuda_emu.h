@@ -1,10 +1,11 @@
-// Minimal CUDA execution model on CPU threads, enough to RUN the repo's SIMT kernels (not the tcgen05 / TMA ones) in the
-// CPU test suite: one std::thread per CUDA thread of a block, blocks one after the other,
+// Minimal CUDA execution model on CPU threads, enough to RUN the repo's kernels in the CPU test suite (overview:
+// docs/guide/testing.md): one std::thread per CUDA thread of a block, blocks one after the other,
 //   __shared__        -> a static (one block is alive at a time)
 //   __syncthreads()   -> std::barrier over the block          __syncwarp() -> std::barrier over the warp
 //   __shfl_xor_sync   -> exchange through a per-warp buffer between two warp barriers
 // A thread that returns from the kernel drops out of its barriers, so early exits of whole warps do not dead-lock.
-// The fake <cuda_runtime.h> / <cuda_bf16.h> / <cuda_fp16.h> next to this file all include it.
+// The fake <cuda_runtime.h> / <cuda_bf16.h> / <cuda_fp16.h> next to this file all include it.  This header alone serves
+// the SIMT kernels; the tcgen05 / TMA / mbarrier kernels additionally run on tcgen05_model.h + ptx.cuh.
 #pragma once
 #include <algorithm>
 #include <atomic>

@@ -1,9 +1,17 @@
-"""Build a host (CPU) shared library out of the repo's SIMT ``.cu`` files for tests/test_kernel_emulation.py.
+"""Build host (CPU) libraries / executables out of the repo's ``.cu`` files for the emulation tests
+(tests/test_kernel_emulation.py, test_attention_kernel_model.py, test_gemm_kernel_model.py; overview in
+docs/guide/testing.md).
 
-The kernel source is used as is.  The only textual change is the launch syntax, which a C++ compiler cannot parse:
-``kernel<<<grid, threads, smem, stream>>>(args)`` becomes ``cuda_emu::launch(dim3(grid), dim3(threads).x, [&] {
-kernel(args); })``, so the real ``extern "C"`` launchers (grid / block selection, dtype dispatch) run too.  Everything
-else -- threadIdx, __shared__, __syncthreads, shuffles, the 16-bit types -- comes from ``cuda_emu/cuda_emu.h``."""
+The kernel source is used as is.  The textual changes are:
+  * the launch syntax, which a C++ compiler cannot parse: ``kernel<<<grid, threads, smem, stream>>>(args)`` becomes
+    ``cuda_emu::launch[_dyn | _cluster2](dim3(grid), dim3(threads).x, [smem,] [&] { kernel(args); })``, so the real
+    ``extern "C"`` launchers (grid / block selection, dtype and flag dispatch, tensor-map construction) run too;
+  * the handful of inline-PTX statements listed in ``_PTX`` below, replaced by their meaning on the model;
+  * ``extern __shared__`` (dynamic shared memory) becomes the block's buffer.
+Everything else -- threadIdx, __shared__, __syncthreads, shuffles, the 16-bit types (cuda_emu/cuda_emu.h); mbarrier,
+TMA, tensor memory, tcgen05.mma, clusters (cuda_emu/tcgen05_model.h, ptx.cuh) -- comes from headers that shadow the
+CUDA ones on the include path.  The descriptor builders of the real ptx.cuh are copied verbatim (``ptx_real_extract.h``)
+so the model decodes exactly what the kernels encode."""
 import os
 import re
 import subprocess
@@ -11,7 +19,7 @@ import subprocess
 EMU = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(os.path.dirname(os.path.dirname(EMU)), "megatron_llm_b200", "csrc")
 _LAUNCH = re.compile(r"((?:mlb::)?\w+(?:<[^<>;()]*>)?)\s*<<<")
-# the few inline-PTX statements of the SIMT files, replaced by their host meaning
+# the inline-PTX statements of the translated files, replaced by their host / model meaning
 _PTX = [(re.compile(r'asm volatile\("red\.global\.add\.v4\.f32 \[%0\], \{%1, %2, %3, %4\};"\s*::\s*"l"\((\w+)\), "f"\((\w+)\), '
                     r'"f"\((\w+)\), "f"\((\w+)\), "f"\((\w+)\)\s*:\s*"memory"\);'),
          r"cuda_emu::atomic_add4(\1, \2, \3, \4, \5);"),
