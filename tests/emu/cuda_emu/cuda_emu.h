@@ -14,6 +14,8 @@
 #include <cstdint>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <mutex>
 #include <memory>
 #include <thread>
 #include <vector>
@@ -76,12 +78,25 @@ struct Block {
   std::barrier<> block_bar;
   std::vector<std::unique_ptr<std::barrier<>>> warp_bar;
   std::vector<uint32_t> shfl;     // [n_warps][32]
+  std::map<int, std::unique_ptr<uint8_t[]>> statics;     // scalar __shared__ variables of kernels whose CTAs overlap
+  std::mutex statics_mu;
   explicit Block(unsigned n) : n_threads(n), n_warps((n + 31) / 32), block_bar(n), shfl(((n + 31) / 32) * 32) {
     for (unsigned w = 0; w < n_warps; ++w)
       warp_bar.emplace_back(new std::barrier<>(std::min(32u, n - w * 32)));
   }
 };
 inline thread_local Block* blk = nullptr;
+}  // namespace cuda_emu
+
+namespace cuda_emu {
+// a scalar `__shared__ T name;` of a kernel that runs with several CTAs alive at once (clusters, concurrent blocks):
+// one instance per block instead of the `static` the plain __shared__ macro gives (host_build.py rewrites those)
+template <class T> inline T& block_static(int key) {
+  std::lock_guard<std::mutex> g(blk->statics_mu);
+  auto& slot = blk->statics[key];
+  if (!slot) slot.reset(new uint8_t[sizeof(T)]());
+  return *reinterpret_cast<T*>(slot.get());
+}
 }  // namespace cuda_emu
 
 inline thread_local uint3 threadIdx{0, 0, 0}, blockIdx{0, 0, 0};

@@ -130,9 +130,45 @@ inline void named_barrier(int id, int count) {
   b->arrive_and_wait();
 }
 
+// All blocks of a 1-D grid at once (MLB_EMU_CONCURRENT_BLOCKS=1): for launches whose CTAs wait for each other -- the
+// puller CTAs and the compute CTAs of the fused all-gather -> GEMM kernel.  (Kernels with `static` __shared__ variables
+// must not be run this way; the fused all-gather path has none.)
+template <class F>
+void launch_dyn_concurrent(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
+  const unsigned nb = grid.x;
+  std::vector<std::unique_ptr<Block>> blocks;
+  std::vector<std::unique_ptr<BlockModel>> models;
+  for (unsigned b = 0; b < nb; ++b) {
+    blocks.emplace_back(new Block(threads));
+    models.emplace_back(new BlockModel());
+    models[b]->smem_bytes = smem_bytes;
+    models[b]->smem = static_cast<uint8_t*>(std::aligned_alloc(1024, (smem_bytes + 1023) / 1024 * 1024 + 1024));
+    std::memset(models[b]->smem, 0xCD, smem_bytes);
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(size_t(nb) * threads);
+  for (unsigned b = 0; b < nb; ++b)
+    for (unsigned t = 0; t < threads; ++t)
+      pool.emplace_back([&, b, t] {
+        blk = blocks[b].get();
+        bm = models[b].get();
+        threadIdx = uint3{t, 0, 0};
+        blockIdx = uint3{b, 0, 0};
+        blockDim = dim3(threads);
+        gridDim = grid;
+        kernel();
+        blocks[b]->warp_bar[t >> 5]->arrive_and_drop();
+        blocks[b]->block_bar.arrive_and_drop();
+      });
+  for (auto& th : pool) th.join();
+  for (auto& m : models) std::free(m->smem);
+}
+
 // launch with dynamic shared memory and the block model
 template <class F>
 void launch_dyn(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
+  static const bool concurrent = std::getenv("MLB_EMU_CONCURRENT_BLOCKS") != nullptr;
+  if (concurrent && grid.y == 1 && grid.z == 1) { launch_dyn_concurrent(grid, threads, smem_bytes, kernel); return; }
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
       for (unsigned bx = 0; bx < grid.x; ++bx) {

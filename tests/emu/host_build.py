@@ -99,12 +99,21 @@ def launches_to_host(src: str) -> str:
 _MODEL_HEADERS = ("attention_common.cuh", "gemm_sm100.cuh")       # csrc headers with inline PTX: transformed copies shadow the originals
 
 
+_SHARED_SCALAR = re.compile(r"__shared__\s+(int|unsigned|uint32_t|float|bool)\s+(\w+)\s*;")
+
+
+def _per_block_shared_scalars(src):
+    """`__shared__ int x;` -> one instance per block (the files of the tcgen05 model run CTA pairs / all blocks of a
+    launch concurrently, where the `static` of the plain __shared__ macro would be shared between CTAs)."""
+    return _SHARED_SCALAR.sub(lambda m: f"{m.group(1)}& {m.group(2)} = cuda_emu::block_static<{m.group(1)}>(__LINE__);", src)
+
+
 def _write_model_headers(out_dir):
     """For the kernels that run on the functional tcgen05 / TMA model: a transformed copy of the csrc headers that carry
     inline PTX, and the descriptor builders of the REAL ptx.cuh (the model decodes what the real code encodes)."""
     for h in _MODEL_HEADERS:
         with open(os.path.join(out_dir, h), "w") as fh:
-            fh.write(launches_to_host(open(os.path.join(CSRC, h)).read()))
+            fh.write(_per_block_shared_scalars(launches_to_host(open(os.path.join(CSRC, h)).read())))
     real = open(os.path.join(CSRC, "ptx.cuh")).read()
     a = real.index("// ---------------------------------------------------------------- UMMA descriptors")
     b = real.index("// ---------------------------------------------------------------- cluster")
@@ -147,4 +156,13 @@ def build_race_driver(cu_files, out_dir, name="race_driver", mutate=None, define
     subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fsanitize=thread", "-pthread", "-w",
                            *["-D" + d for d in defines], "-I" + out_dir, "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources,
                            os.path.join(EMU, driver), "-o", exe])
+    return exe
+
+
+def build_executable(cu_files, driver, out_dir, name):
+    """The kernels plus a C++ driver from tests/emu as a plain executable (one emulated rank per process)."""
+    sources = _host_sources(cu_files, out_dir)
+    exe = os.path.join(out_dir, name)
+    subprocess.check_call(["g++", "-O1", "-std=c++20", "-pthread", "-w", "-I" + out_dir,
+                           "-I" + os.path.join(EMU, "cuda_emu"), "-I" + CSRC, *sources, os.path.join(EMU, driver), "-o", exe])
     return exe

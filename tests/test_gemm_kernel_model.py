@@ -112,3 +112,82 @@ def test_tcgen05_kernels_survive_schedule_fuzzing(tmp_path_factory, seed):
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][7:])
     assert all(v == v and v < 6e-3 for v in res.values()), res
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# fused GEMM -> reduce-scatter / all-reduce between emulated tensor-parallel ranks (tests/emu/fused_rank.cpp)
+# ------------------------------------------------------------------------------------------------------------------
+
+@pytest.fixture(scope="module")
+def fused_rank_exe(tmp_path_factory):
+    return host_build.build_executable(["gemm_sm100.cu", "gemm2_sm100.cu"], "fused_rank.cpp",
+                                       str(tmp_path_factory.mktemp("emu_fused")), "fused_rank")
+
+
+def _fused_ranks(exe, d, world, m, N, K, mode, calls, chaos=None):
+    import numpy as np
+    os.makedirs(d, exist_ok=True)
+    for r in range(world):
+        np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(d, f"slots{r}.bin"))
+        np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(d, f"arout{r}.bin"))
+        np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
+    env = dict(os.environ, **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}))
+    procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), mode, str(calls)], env=env,
+                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    return [(p.wait(timeout=900), p.stderr.read()[-300:]) for p in procs]
+
+
+@pytest.mark.parametrize("mode,world,m,N,K,calls,chaos", [
+    ("rs1", 2, 256, 128, 128, 3, None),      # 1-CTA kernel: epilogue stores into the peer's slot, arrival counters,
+    ("rs1", 3, 128, 128, 64, 2, 5),          #   slot reduction, PAD_RS_FREE on the third call; with schedule fuzzing
+    ("ar1", 3, 128, 128, 64, 2, None),       # GEMM -> all-reduce: the reduced slice stored into every rank's output
+    ("rs2", 2, 256, 256, 128, 3, None),      # 2-CTA kernel: TMA stores into peer slots, signalling one tile late
+    ("rs2", 2, 512, 256, 64, 2, 9),
+])
+def test_fused_gemm_reduce_scatter_between_emulated_ranks(fused_rank_exe, tmp_path, mode, world, m, N, K, calls, chaos):
+    """Row-parallel forward Y = sum_r X_r W_r^T with the reduce-scatter (or all-reduce) fused into the GEMM kernel: every
+    rank is a process running the real kernel source on the functional model (one CTA / one CTA pair per rank), receive
+    slots and signal pads are files all ranks map.  Each rank checks its rows against a reference it recomputes from
+    the seeds and that none of its bounded spins timed out; several calls alternate the slot parities."""
+    res = _fused_ranks(fused_rank_exe, tmp_path, world, m, N, K, mode, calls, chaos)
+    assert all(rc == 0 for rc, _ in res), res
+
+
+def _ag_ranks(exe, d, world, m, N, K, pullers, calls, chaos=None):
+    import numpy as np
+    os.makedirs(d, exist_ok=True)
+    for r in range(world):
+        np.zeros(m * K, dtype=np.uint16).tofile(os.path.join(d, f"shard{r}.bin"))
+        np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
+    env = dict(os.environ, MLB_EMU_CONCURRENT_BLOCKS="1", **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}))
+    procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), str(pullers), str(calls)], env=env,
+                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    return [(p.wait(timeout=900), p.stderr.read()[-300:]) for p in procs]
+
+
+@pytest.mark.parametrize("world,m,N,K,pullers,calls,chaos", [(2, 256, 256, 128, 2, 3, None), (3, 256, 128, 320, 3, 2, 4),
+                                                            (2, 128, 136, 72, 1, 2, 8)])
+def test_fused_all_gather_gemm_between_emulated_ranks(tmp_path_factory, tmp_path, world, m, N, K, pullers, calls, chaos):
+    """Column-parallel forward out_r = all_gather(X) W_r^T with the all-gather fused into the GEMM launch: puller CTAs
+    (bulk copies of the peers' published shards through shared memory, one flag per 128-row chunk, read
+    acknowledgements) and compute CTAs (TMA producers that wait for the chunk they are about to read) run
+    concurrently inside every rank; ranks are processes over mapped files."""
+    base = str(tmp_path_factory.getbasetemp())
+    exe = os.path.join(base, "emu_fused_ag", "fused_ag_rank")
+    if not os.path.exists(exe):
+        host_build.build_executable(["gemm_sm100.cu", "gemm2_sm100.cu"], "fused_ag_rank.cpp", os.path.dirname(exe), "fused_ag_rank")
+    res = _ag_ranks(exe, tmp_path, world, m, N, K, pullers, calls, chaos)
+    assert all(rc == 0 for rc, _ in res), res
+
+
+def test_fused_kernels_between_ranks_under_thread_sanitizer(tmp_path):
+    """The same rank programs built with ThreadSanitizer (it sees the accesses inside a rank: pullers vs. compute CTAs,
+    epilogue vs. slot reduction; the peers' stores arrive through the mapped files)."""
+    files = ["gemm_sm100.cu", "gemm2_sm100.cu"]
+    ag = host_build.build_race_driver(files, str(tmp_path / "ag"), name="ag_rank_tsan", driver="fused_ag_rank.cpp")
+    res = _ag_ranks(ag, tmp_path / "ag_run", 2, 128, 128, 128, 2, 2)
+    assert all(rc == 0 and "ThreadSanitizer" not in err for rc, err in res), res
+    rs = host_build.build_race_driver(files, str(tmp_path / "rs"), name="rs_rank_tsan", driver="fused_rank.cpp")
+    for mode, m, N in (("rs1", 128, 128), ("rs2", 256, 256)):
+        res = _fused_ranks(rs, tmp_path / ("rs_run_" + mode), 2, m, N, 64, mode, 2)
+        assert all(rc == 0 and "ThreadSanitizer" not in err for rc, err in res), (mode, res)
