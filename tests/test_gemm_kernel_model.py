@@ -94,7 +94,7 @@ def test_gemm_barrier_protocols_under_thread_sanitizer(tmp_path):
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (epi, r.stderr[-3000:])
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3])
+@pytest.mark.parametrize("seed", [1, 2])
 def test_tcgen05_kernels_survive_schedule_fuzzing(tmp_path_factory, seed):
     """Attention (both forward kernels + backward, window, dropout) and both GEMM kernels with random stalls in front of
     every barrier operation, TMA load, MMA and tensor-memory access (MLB_EMU_CHAOS): warps drift apart by whole tiles,
