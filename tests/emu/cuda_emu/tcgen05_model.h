@@ -196,9 +196,54 @@ void launch_dyn(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
       }
 }
 
+// all CTA pairs of the grid at once (MLB_EMU_CONCURRENT_BLOCKS=1): puller clusters next to compute clusters
+template <class F>
+void launch_cluster2_concurrent(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
+  const unsigned pairs = grid.x / 2;
+  std::vector<std::unique_ptr<Block>> blocks;
+  std::vector<std::unique_ptr<BlockModel>> models;
+  std::vector<std::unique_ptr<std::barrier<>>> cbars;
+  for (unsigned b = 0; b < 2 * pairs; ++b) {
+    blocks.emplace_back(new Block(threads));
+    models.emplace_back(new BlockModel());
+    models[b]->smem_bytes = smem_bytes;
+    models[b]->smem = static_cast<uint8_t*>(std::aligned_alloc(1024, (smem_bytes + 1023) / 1024 * 1024 + 1024));
+    std::memset(models[b]->smem, 0xCD, smem_bytes);
+  }
+  for (unsigned pr = 0; pr < pairs; ++pr) {
+    cbars.emplace_back(new std::barrier<>(2 * threads));
+    for (unsigned r = 0; r < 2; ++r) {
+      BlockModel* m = models[2 * pr + r].get();
+      m->cluster[0] = models[2 * pr].get(); m->cluster[1] = models[2 * pr + 1].get();
+      m->cluster_rank = r;
+      m->cluster_bar = cbars[pr].get();
+    }
+  }
+  std::vector<std::thread> pool;
+  pool.reserve(size_t(2 * pairs) * threads);
+  for (unsigned b = 0; b < 2 * pairs; ++b)
+    for (unsigned t = 0; t < threads; ++t)
+      pool.emplace_back([&, b, t] {
+        blk = blocks[b].get();
+        bm = models[b].get();
+        threadIdx = uint3{t, 0, 0};
+        blockIdx = uint3{b, 0, 0};
+        blockDim = dim3(threads);
+        gridDim = grid;
+        kernel();
+        blocks[b]->warp_bar[t >> 5]->arrive_and_drop();
+        blocks[b]->block_bar.arrive_and_drop();
+        cbars[b / 2]->arrive_and_drop();
+      });
+  for (auto& th : pool) th.join();
+  for (auto& m : models) std::free(m->smem);
+}
+
 // clusters of two CTAs (__cluster_dims__(2, 1, 1)): the pair runs concurrently, pairs one after the other
 template <class F>
 void launch_cluster2(dim3 grid, unsigned threads, size_t smem_bytes, F kernel) {
+  static const bool concurrent = std::getenv("MLB_EMU_CONCURRENT_BLOCKS") != nullptr;
+  if (concurrent) { launch_cluster2_concurrent(grid, threads, smem_bytes, kernel); return; }
   for (unsigned pair = 0; pair < grid.x / 2; ++pair) {
     Block block0(threads), block1(threads);
     Block* blocks[2] = {&block0, &block1};

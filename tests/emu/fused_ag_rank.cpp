@@ -2,7 +2,8 @@
 // kernel) on the functional model: the puller CTAs and the compute CTAs of the launch run concurrently
 // (MLB_EMU_CONCURRENT_BLOCKS=1), ranks are processes, the published shards and the signal pads are files all ranks map.
 //
-//     fused_ag_rank <dir> <rank> <world> <rows_per_rank> <N> <K> <pullers> <calls>
+//     fused_ag_rank <dir> <rank> <world> <rows_per_rank> <N> <K> <pullers> <calls> [2cta]
+// (with "2cta": csrc/gemm2_sm100.cu -- puller CLUSTERS next to compute clusters, rows per rank a multiple of 256)
 //
 // Column-parallel forward under sequence parallelism: rank r owns the activation shard X_r [m, K] and the weight shard
 // W_r [N, K]; out_r = concat_p(X_p) W_r^T.  The own rows are placed by the host before the launch (as the real caller
@@ -27,8 +28,12 @@
 #include "gemm_types.h"
 
 typedef void* cudaStream_t;
-extern "C" int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb,
-                                   int ldc, int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+extern "C" {
+int mlb_gemm_bf16_fused(int mode, const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                        int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+int mlb_gemm_bf16_2cta_ag(const void* A, const void* B, void* C, int M, int N, int K, int lda, int ldb, int ldc,
+                          int b_mn_major, const mlb::GemmComm* comm, int num_sms, cudaStream_t stream);
+}
 
 static uint16_t f2bf(float f) { uint32_t u; memcpy(&u, &f, 4); u += 0x7fffu + ((u >> 16) & 1u); return uint16_t(u >> 16); }
 static float bf2f(uint16_t h) { uint32_t u = uint32_t(h) << 16; float f; memcpy(&f, &u, 4); return f; }
@@ -56,6 +61,7 @@ int main(int argc, char** argv) {
   const std::string dir = argv[1];
   const int rank = atoi(argv[2]), world = atoi(argv[3]), m = atoi(argv[4]), N = atoi(argv[5]), K = atoi(argv[6]);
   const int pullers = atoi(argv[7]), calls = atoi(argv[8]), M = m * world;
+  const bool two_cta = argc > 9 && !strcmp(argv[9], "2cta");
   std::vector<uint16_t*> shard(world);
   std::vector<int*> pads(world);
   for (int r = 0; r < world; ++r) {
@@ -85,7 +91,9 @@ int main(int argc, char** argv) {
     c.ag_chunk_flags = chunk_flags.data();
     c.ag_read_counters = read_counters.data();
     c.pad_local = pads[rank];
-    const int e = mlb_gemm_bf16_fused(mlb::MODE_AG_GEMM, G, W.data(), out.data(), M, N, K, K, K, N, 0, &c, 2 + pullers, nullptr);
+    c.m_group_blocks = 1;
+    const int e = two_cta ? mlb_gemm_bf16_2cta_ag(G, W.data(), out.data(), M, N, K, K, K, N, 0, &c, 4 + pullers, nullptr)
+                          : mlb_gemm_bf16_fused(mlb::MODE_AG_GEMM, G, W.data(), out.data(), M, N, K, K, K, N, 0, &c, 2 + pullers, nullptr);
     if (e) { fprintf(stderr, "fused ag -> %d\n", e); return 3; }
     if (pads[rank][mlb::PAD_ERROR]) { fprintf(stderr, "rank %d: a spin-wait timed out\n", rank); return 4; }
     double worst = 0;

@@ -153,21 +153,26 @@ def test_fused_gemm_reduce_scatter_between_emulated_ranks(fused_rank_exe, tmp_pa
     assert all(rc == 0 for rc, _ in res), res
 
 
-def _ag_ranks(exe, d, world, m, N, K, pullers, calls, chaos=None):
+def _ag_ranks(exe, d, world, m, N, K, pullers, calls, chaos=None, two_cta=False):
     import numpy as np
     os.makedirs(d, exist_ok=True)
     for r in range(world):
         np.zeros(m * K, dtype=np.uint16).tofile(os.path.join(d, f"shard{r}.bin"))
         np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
     env = dict(os.environ, MLB_EMU_CONCURRENT_BLOCKS="1", **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}))
-    procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), str(pullers), str(calls)], env=env,
-                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), str(pullers), str(calls)] +
+                              (["2cta"] if two_cta else []), env=env, stderr=subprocess.PIPE, text=True)
+             for r in range(world)]
     return [(p.wait(timeout=900), p.stderr.read()[-300:]) for p in procs]
 
 
-@pytest.mark.parametrize("world,m,N,K,pullers,calls,chaos", [(2, 256, 256, 128, 2, 3, None), (3, 256, 128, 320, 3, 2, 4),
-                                                            (2, 128, 136, 72, 1, 2, 8)])
-def test_fused_all_gather_gemm_between_emulated_ranks(tmp_path_factory, tmp_path, world, m, N, K, pullers, calls, chaos):
+@pytest.mark.parametrize("world,m,N,K,pullers,calls,chaos,two_cta", [
+    (2, 256, 256, 128, 2, 3, None, False), (3, 256, 128, 320, 3, 2, 4, False), (2, 128, 136, 72, 1, 2, 8, False),
+    (2, 256, 256, 128, 2, 2, None, True),          # 2-CTA kernel: puller clusters next to compute clusters
+    (2, 512, 264, 72, 2, 3, 3, True),
+])
+def test_fused_all_gather_gemm_between_emulated_ranks(tmp_path_factory, tmp_path, world, m, N, K, pullers, calls, chaos,
+                                                      two_cta):
     """Column-parallel forward out_r = all_gather(X) W_r^T with the all-gather fused into the GEMM launch: puller CTAs
     (bulk copies of the peers' published shards through shared memory, one flag per 128-row chunk, read
     acknowledgements) and compute CTAs (TMA producers that wait for the chunk they are about to read) run
@@ -176,7 +181,7 @@ def test_fused_all_gather_gemm_between_emulated_ranks(tmp_path_factory, tmp_path
     exe = os.path.join(base, "emu_fused_ag", "fused_ag_rank")
     if not os.path.exists(exe):
         host_build.build_executable(["gemm_sm100.cu", "gemm2_sm100.cu"], "fused_ag_rank.cpp", os.path.dirname(exe), "fused_ag_rank")
-    res = _ag_ranks(exe, tmp_path, world, m, N, K, pullers, calls, chaos)
+    res = _ag_ranks(exe, tmp_path, world, m, N, K, pullers, calls, chaos, two_cta)
     assert all(rc == 0 for rc, _ in res), res
 
 
