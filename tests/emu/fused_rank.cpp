@@ -2,7 +2,8 @@
 // MODE_GEMM_RS with one CTA, csrc/gemm2_sm100.cu with one CTA pair), on the functional tcgen05 model.  Ranks are
 // processes; symmetric memory (receive slots, signal pads, all-reduce outputs) is a set of files every rank maps:
 //
-//     fused_rank <dir> <rank> <world> <rows_per_rank> <N> <K> <mode: rs1 | rs2 | ar1> <calls>
+//     fused_rank <dir> <rank> <world> <rows_per_rank> <N> <K> <mode: rs1 | rs2 | ar1> <calls> [CTAs (pairs) per rank]
+// (more than one CTA / pair per rank needs MLB_EMU_CONCURRENT_BLOCKS=1: the slot reduction waits for all of them)
 //
 // Row-parallel forward: rank r holds X_r [M, K] and W_r [N, K] (its K-shard); Y = sum_r X_r W_r^T; rank d ends up with
 // rows [d m, d m + m) of Y (reduce-scatter) or all of Y (all-reduce).  Tiles travel from the epilogue of every rank into
@@ -53,7 +54,7 @@ int main(int argc, char** argv) {
   if (argc < 9) return 8;
   const std::string dir = argv[1], mode = argv[7];
   const int rank = atoi(argv[2]), world = atoi(argv[3]), m = atoi(argv[4]), N = atoi(argv[5]), K = atoi(argv[6]);
-  const int calls = atoi(argv[8]), M = m * world;
+  const int calls = atoi(argv[8]), M = m * world, ctas = argc > 9 ? atoi(argv[9]) : 1;
   const bool all_reduce = mode == "ar1", two_cta = mode == "rs2";
   const size_t slot_elems = (size_t)world * m * N;                       // one parity: [world][m][N] bf16
   std::vector<uint16_t*> slots(world), arout(world);
@@ -90,14 +91,14 @@ int main(int argc, char** argv) {
     c.rs_reduce_counter = &reduce_counter;
     c.pad_local = pads[rank];
     if (two_cta) {
-      const int got = mlb_gemm_bf16_2cta_rs(X[rank].data(), W[rank].data(), M, N, K, K, K, 0, &c, total, 2, nullptr);
+      const int got = mlb_gemm_bf16_2cta_rs(X[rank].data(), W[rank].data(), M, N, K, K, K, 0, &c, total, 2 * ctas, nullptr);
       if (got <= 0) { fprintf(stderr, "2cta rs -> %d\n", got); return 3; }
       total += got;
     } else {
       const int tiles = (m / mlb::GEMM_BLOCK_M) * ((N + 127) / 128);                // N <= 128 here: one column of tiles
       c.rs_expected_total = total + tiles;
       total += tiles;
-      const int e = mlb_gemm_bf16_fused(mlb::MODE_GEMM_RS, X[rank].data(), W[rank].data(), nullptr, M, N, K, K, K, N, 0, &c, 1, nullptr);
+      const int e = mlb_gemm_bf16_fused(mlb::MODE_GEMM_RS, X[rank].data(), W[rank].data(), nullptr, M, N, K, K, K, N, 0, &c, ctas, nullptr);
       if (e) { fprintf(stderr, "fused -> %d\n", e); return 3; }
     }
     if (pads[rank][mlb::PAD_ERROR]) { fprintf(stderr, "rank %d: a spin-wait timed out\n", rank); return 4; }

@@ -124,32 +124,37 @@ def fused_rank_exe(tmp_path_factory):
                                        str(tmp_path_factory.mktemp("emu_fused")), "fused_rank")
 
 
-def _fused_ranks(exe, d, world, m, N, K, mode, calls, chaos=None):
+def _fused_ranks(exe, d, world, m, N, K, mode, calls, chaos=None, ctas=1):
     import numpy as np
     os.makedirs(d, exist_ok=True)
     for r in range(world):
         np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(d, f"slots{r}.bin"))
         np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(d, f"arout{r}.bin"))
         np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
-    env = dict(os.environ, **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}))
-    procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), mode, str(calls)], env=env,
-                              stderr=subprocess.PIPE, text=True) for r in range(world)]
+    env = dict(os.environ, **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}),
+               **({"MLB_EMU_CONCURRENT_BLOCKS": "1"} if ctas > 1 else {}))
+    procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), mode, str(calls), str(ctas)],
+                              env=env, stderr=subprocess.PIPE, text=True) for r in range(world)]
     return [(p.wait(timeout=900), p.stderr.read()[-300:]) for p in procs]
 
 
-@pytest.mark.parametrize("mode,world,m,N,K,calls,chaos", [
-    ("rs1", 2, 256, 128, 128, 3, None),      # 1-CTA kernel: epilogue stores into the peer's slot, arrival counters,
-    ("rs1", 3, 128, 128, 64, 2, 5),          #   slot reduction, PAD_RS_FREE on the third call; with schedule fuzzing
-    ("ar1", 3, 128, 128, 64, 2, None),       # GEMM -> all-reduce: the reduced slice stored into every rank's output
-    ("rs2", 2, 256, 256, 128, 3, None),      # 2-CTA kernel: TMA stores into peer slots, signalling one tile late
-    ("rs2", 2, 512, 256, 64, 2, 9),
+@pytest.mark.parametrize("mode,world,m,N,K,calls,chaos,ctas", [
+    ("rs1", 2, 256, 128, 128, 3, None, 1),   # 1-CTA kernel: epilogue stores into the peer's slot, arrival counters,
+    ("rs1", 3, 128, 128, 64, 2, 5, 1),       #   slot reduction, PAD_RS_FREE on the third call; with schedule fuzzing
+    ("ar1", 3, 128, 128, 64, 2, None, 1),    # GEMM -> all-reduce: the reduced slice stored into every rank's output
+    ("rs2", 2, 256, 256, 128, 3, None, 1),   # 2-CTA kernel: TMA stores into peer slots, signalling one tile late
+    ("rs2", 2, 512, 256, 64, 2, 9, 1),
+    ("rs1", 2, 256, 128, 128, 3, None, 3),   # several CTAs (pairs) per rank running concurrently: the slot reduction is
+    ("rs2", 2, 512, 256, 128, 3, 6, 2),      #   spread over them and the last one out hands the slots back
+    ("ar1", 3, 256, 128, 64, 2, 2, 2),
 ])
-def test_fused_gemm_reduce_scatter_between_emulated_ranks(fused_rank_exe, tmp_path, mode, world, m, N, K, calls, chaos):
+def test_fused_gemm_reduce_scatter_between_emulated_ranks(fused_rank_exe, tmp_path, mode, world, m, N, K, calls, chaos,
+                                                          ctas):
     """Row-parallel forward Y = sum_r X_r W_r^T with the reduce-scatter (or all-reduce) fused into the GEMM kernel: every
     rank is a process running the real kernel source on the functional model (one CTA / one CTA pair per rank), receive
     slots and signal pads are files all ranks map.  Each rank checks its rows against a reference it recomputes from
     the seeds and that none of its bounded spins timed out; several calls alternate the slot parities."""
-    res = _fused_ranks(fused_rank_exe, tmp_path, world, m, N, K, mode, calls, chaos)
+    res = _fused_ranks(fused_rank_exe, tmp_path, world, m, N, K, mode, calls, chaos, ctas)
     assert all(rc == 0 for rc, _ in res), res
 
 
