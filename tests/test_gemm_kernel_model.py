@@ -201,3 +201,20 @@ def test_fused_kernels_between_ranks_under_thread_sanitizer(tmp_path):
     for mode, m, N in (("rs1", 128, 128), ("rs2", 256, 256)):
         res = _fused_ranks(rs, tmp_path / ("rs_run_" + mode), 2, m, N, 64, mode, 2)
         assert all(rc == 0 and "ThreadSanitizer" not in err for rc, err in res), (mode, res)
+
+
+def test_fused_kernel_with_a_lost_peer_times_out_instead_of_hanging(fused_rank_exe, tmp_path):
+    """A tensor-parallel peer that dies before delivering its tiles: the bounded spins of the fused GEMM -> reduce-scatter
+    kernel end, the timeout is recorded in the signal pad (``symm.check_timeouts`` makes it fatal once per training step)
+    and the kernel retires -- the rank program reports it (exit code 4) instead of hanging."""
+    import numpy as np
+    world, m, N, K = 2, 128, 128, 64
+    for r in range(world):
+        np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(tmp_path, f"slots{r}.bin"))
+        np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(tmp_path, f"arout{r}.bin"))
+        np.zeros(64, dtype=np.int32).tofile(os.path.join(tmp_path, f"pad{r}.bin"))
+    open(os.path.join(tmp_path, "ready1"), "w").close()            # rank 1 "arrived" at the rendezvous, then vanished
+    r = subprocess.run([fused_rank_exe, str(tmp_path), "0", str(world), str(m), str(N), str(K), "rs1", "1"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 4 and "timed out" in r.stderr, (r.returncode, r.stderr[-500:])
+    assert np.fromfile(os.path.join(tmp_path, "pad0.bin"), dtype=np.int32)[32] == 1
