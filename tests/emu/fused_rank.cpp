@@ -69,6 +69,10 @@ int main(int argc, char** argv) {
   for (int r = 0; r < world; ++r)
     while (access((dir + "/ready" + std::to_string(r)).c_str(), F_OK) != 0) std::this_thread::sleep_for(std::chrono::milliseconds(1));
 
+  // FUSED_RANK_GRAPH_STATE=1: like a replayed CUDA graph -- the launch arguments stay those of the "capture" (epoch of
+  // the parity's first call, arrivals of one call) and the live epoch / arrival total come from GemmComm::state
+  const bool graph_state = getenv("FUSED_RANK_GRAPH_STATE") != nullptr;
+  int state[3] = {0, 0, 0};
   int reduce_counter = 0, total = 0, rc = 0;
   for (int call = 1; call <= calls && rc == 0; ++call) {
     const int parity = call & 1;
@@ -78,6 +82,13 @@ int main(int argc, char** argv) {
     mlb::GemmComm c;
     memset(&c, 0, sizeof(c));
     c.rank = rank; c.world = world; c.epoch = call;
+    const int prev_total = total;
+    if (graph_state) {
+      c.epoch = 2 - parity;                                   // the epoch this parity's kernel node was captured with
+      state[1] = call - c.epoch;                              // STATE_RS_EPOCH
+      state[2] = prev_total;                                  // STATE_RS_TOTAL (the captured node expects one call's arrivals)
+      c.state = state;
+    }
     c.m_rotate_blocks = ((rank + 1) % world) * m / mlb::GEMM_BLOCK_M;            // remote chunks first
     c.m_group_blocks = 1;
     for (int d = 0; d < world; ++d) {
@@ -91,12 +102,12 @@ int main(int argc, char** argv) {
     c.rs_reduce_counter = &reduce_counter;
     c.pad_local = pads[rank];
     if (two_cta) {
-      const int got = mlb_gemm_bf16_2cta_rs(X[rank].data(), W[rank].data(), M, N, K, K, K, 0, &c, total, 2 * ctas, nullptr);
+      const int got = mlb_gemm_bf16_2cta_rs(X[rank].data(), W[rank].data(), M, N, K, K, K, 0, &c, graph_state ? 0 : total, 2 * ctas, nullptr);
       if (got <= 0) { fprintf(stderr, "2cta rs -> %d\n", got); return 3; }
       total += got;
     } else {
       const int tiles = (m / mlb::GEMM_BLOCK_M) * ((N + 127) / 128);                // N <= 128 here: one column of tiles
-      c.rs_expected_total = total + tiles;
+      c.rs_expected_total = (graph_state ? 0 : total) + tiles;
       total += tiles;
       const int e = mlb_gemm_bf16_fused(mlb::MODE_GEMM_RS, X[rank].data(), W[rank].data(), nullptr, M, N, K, K, K, N, 0, &c, ctas, nullptr);
       if (e) { fprintf(stderr, "fused -> %d\n", e); return 3; }

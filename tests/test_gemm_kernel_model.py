@@ -124,7 +124,7 @@ def fused_rank_exe(tmp_path_factory):
                                        str(tmp_path_factory.mktemp("emu_fused")), "fused_rank")
 
 
-def _fused_ranks(exe, d, world, m, N, K, mode, calls, chaos=None, ctas=1):
+def _fused_ranks(exe, d, world, m, N, K, mode, calls, chaos=None, ctas=1, graph_state=False):
     import numpy as np
     os.makedirs(d, exist_ok=True)
     for r in range(world):
@@ -132,7 +132,8 @@ def _fused_ranks(exe, d, world, m, N, K, mode, calls, chaos=None, ctas=1):
         np.zeros(2 * world * m * N, dtype=np.uint16).tofile(os.path.join(d, f"arout{r}.bin"))
         np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
     env = dict(os.environ, **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}),
-               **({"MLB_EMU_CONCURRENT_BLOCKS": "1"} if ctas > 1 else {}))
+               **({"MLB_EMU_CONCURRENT_BLOCKS": "1"} if ctas > 1 else {}),
+               **({"FUSED_RANK_GRAPH_STATE": "1"} if graph_state else {}))
     procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), mode, str(calls), str(ctas)],
                               env=env, stderr=subprocess.PIPE, text=True) for r in range(world)]
     return [(p.wait(timeout=900), p.stderr.read()[-300:]) for p in procs]
@@ -218,3 +219,12 @@ def test_fused_kernel_with_a_lost_peer_times_out_instead_of_hanging(fused_rank_e
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 4 and "timed out" in r.stderr, (r.returncode, r.stderr[-500:])
     assert np.fromfile(os.path.join(tmp_path, "pad0.bin"), dtype=np.int32)[32] == 1
+
+
+@pytest.mark.parametrize("mode,m,N", [("rs1", 128, 128), ("rs2", 256, 256)])
+def test_fused_kernels_follow_device_resident_epoch_offsets(fused_rank_exe, tmp_path, mode, m, N):
+    """What a replayed CUDA graph does (``GraphedMicrobatch``): the kernel arguments stay those of the capture and the
+    live epoch / cumulative arrival count come from ``GemmComm::state`` in device memory -- five calls over both
+    parities with frozen arguments."""
+    res = _fused_ranks(fused_rank_exe, tmp_path, 2, m, N, 64, mode, 5, graph_state=True)
+    assert all(rc == 0 for rc, _ in res), res
