@@ -160,14 +160,19 @@ def test_fused_gemm_reduce_scatter_between_emulated_ranks(fused_rank_exe, tmp_pa
 
 
 def _ag_ranks(exe, d, world, m, N, K, pullers, calls, chaos=None, two_cta=False):
+    """``two_cta``: False (1-CTA kernel), True (2-CTA kernel, pull transport) or "nvls" (2-CTA kernel, push transport)."""
     import numpy as np
     os.makedirs(d, exist_ok=True)
     for r in range(world):
         np.zeros(m * K, dtype=np.uint16).tofile(os.path.join(d, f"shard{r}.bin"))
         np.zeros(64, dtype=np.int32).tofile(os.path.join(d, f"pad{r}.bin"))
+        if two_cta == "nvls":
+            np.zeros(2 * world * m * K, dtype=np.uint16).tofile(os.path.join(d, f"gather{r}.bin"))
+            np.zeros(2 * (world * m // 128), dtype=np.int32).tofile(os.path.join(d, f"gflags{r}.bin"))
     env = dict(os.environ, MLB_EMU_CONCURRENT_BLOCKS="1", **({"MLB_EMU_CHAOS": str(chaos)} if chaos else {}))
     procs = [subprocess.Popen([exe, str(d), str(r), str(world), str(m), str(N), str(K), str(pullers), str(calls)] +
-                              (["2cta"] if two_cta else []), env=env, stderr=subprocess.PIPE, text=True)
+                              ([two_cta if two_cta == "nvls" else "2cta"] if two_cta else []), env=env,
+                              stderr=subprocess.PIPE, text=True)
              for r in range(world)]
     return [(p.wait(timeout=900), p.stderr.read()[-300:]) for p in procs]
 
@@ -176,6 +181,8 @@ def _ag_ranks(exe, d, world, m, N, K, pullers, calls, chaos=None, two_cta=False)
     (2, 256, 256, 128, 2, 3, None, False), (3, 256, 128, 320, 3, 2, 4, False), (2, 128, 136, 72, 1, 2, 8, False),
     (2, 256, 256, 128, 2, 2, None, True),          # 2-CTA kernel: puller clusters next to compute clusters
     (2, 512, 264, 72, 2, 3, 3, True),
+    (2, 256, 256, 128, 2, 4, None, "nvls"),        # push transport: multimem.st into every rank's gather buffer
+    (2, 512, 256, 64, 4, 3, 5, "nvls"),
 ])
 def test_fused_all_gather_gemm_between_emulated_ranks(tmp_path_factory, tmp_path, world, m, N, K, pullers, calls, chaos,
                                                       two_cta):
