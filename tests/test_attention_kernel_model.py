@@ -135,3 +135,40 @@ def test_attention_barrier_protocol_under_thread_sanitizer(tmp_path):
     for args in (["384", "128"], ["512", "64"]):
         r = subprocess.run([exe] + args, capture_output=True, text=True, timeout=900)
         assert r.returncode == 0 and "ThreadSanitizer" not in r.stderr, (args, r.stderr[-3000:])
+
+
+def test_python_attention_path_on_the_real_kernels(monkeypatch, tmp_path_factory):
+    """ops/attention_sm100.py driven end to end on CPU tensors with the REAL kernel sources behind the extension API
+    (tests/emu/emu_extension.py): the first-use self-tests of the fp16 / dropout / decode variants pass with their
+    production thresholds, and ``attention()`` -- zero-padding of a ragged length, dropout seed plumbing, autograd --
+    reproduces the fp32 oracle with the same mask."""
+    import emu_extension
+    from megatron_llm_b200.ops import _ext, attention_sm100
+    ext = emu_extension.EmuExtension(str(tmp_path_factory.mktemp("emu_ext")))
+    monkeypatch.setattr(_ext, "load", lambda: ext)
+    monkeypatch.setattr(attention_sm100, "_feature_state", {})
+    for var in ("MLB200_ATTN", "MLB200_DISABLE_KERNELS", "MLB200_ATTN_FP16", "MLB200_ATTN_DROPOUT", "MLB200_ATTN_DECODE"):
+        monkeypatch.delenv(var, raising=False)
+    dev = torch.device("cpu")
+    assert attention_sm100.feature_ok("dropout", 128, torch.bfloat16, dev)
+    assert attention_sm100.feature_ok("fp16", 64, torch.float16, dev)
+    assert attention_sm100.feature_ok("decode", 128, torch.bfloat16, dev)
+    monkeypatch.setattr(attention_sm100, "_draw_seed", lambda p, n: SEED if p > 0 else 0)
+    torch.manual_seed(5)
+    b, s, n, nkv, hn, window, p = 1, 200, 4, 2, 128, 150, 0.1
+    q, k, v = (torch.randn(b, s, h, hn).bfloat16().requires_grad_() for h in (n, nkv, nkv))
+    do = torch.randn(b, s, n, hn).bfloat16()
+    assert attention_sm100.supported(q, k, v, True, window, p)
+    out = attention_sm100.attention(q, k, v, True, window, None, p)
+    out.backward(do)
+    qf, kf, vf = (t.detach().float().requires_grad_() for t in (q, k, v))
+    ref = attention_reference(qf, kf, vf, True, window, None, p, dropout_keep_mask(SEED, p, b, n, s, s))
+    ref.backward(do.float())
+    assert _rel(out, ref) < 6e-3 and _rel(q.grad, qf.grad) < 6e-3 and _rel(k.grad, kf.grad) < 6e-3 and _rel(v.grad, vf.grad) < 6e-3
+    with torch.no_grad():                                       # the decode step through decode_supported / decode_attention
+        kc, vc = (torch.randn(97, b, nkv, hn).bfloat16() for _ in range(2))
+        q1 = torch.randn(b, 1, n, hn).bfloat16()
+        kk, vv = kc.transpose(0, 1), vc.transpose(0, 1)
+        assert attention_sm100.decode_supported(q1, kk, vv, True, 0.0)
+        o1 = attention_sm100.decode_attention(q1, kk, vv, None, None)
+        assert _rel(o1, attention_reference(q1.float(), kk.float(), vv.float(), True)) < 6e-3
