@@ -172,3 +172,25 @@ def test_python_attention_path_on_the_real_kernels(monkeypatch, tmp_path_factory
         assert attention_sm100.decode_supported(q1, kk, vv, True, 0.0)
         o1 = attention_sm100.decode_attention(q1, kk, vv, None, None)
         assert _rel(o1, attention_reference(q1.float(), kk.float(), vv.float(), True)) < 6e-3
+
+
+def test_hardware_check_scripts_run_on_the_model(tmp_path_factory):
+    """The scripts of tests/test_z_attention_variants_gpu.py (the first hardware run of the new attention variants) are
+    themselves executed here, on CPU tensors against the emulated extension, so that a mistake in a script cannot be
+    mistaken for a kernel failure on the device.  One script runs in the suite; all of the direct-kernel ones
+    (fp16_training, dropout_training, packed_dropout, decode, single_tile_forward_kernel) passed this way when they
+    were written (about six minutes)."""
+    import importlib.util
+    import emu_extension
+    spec = importlib.util.spec_from_file_location("tz", os.path.join(ROOT, "tests", "test_z_attention_variants_gpu.py"))
+    tz = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(tz)
+    ext = emu_extension.EmuExtension(str(tmp_path_factory.mktemp("emu_ext_z")))
+    prelude = (tz.PRELUDE % {"root": tz.ROOT}).replace("mod = _ext.load()", "mod = _EMU_EXT") \
+        .replace('dev = torch.device("cuda:0")', 'dev = torch.device("cpu")')
+    assert "_EMU_EXT" in prelude and '"cpu"' in prelude
+    for name in os.environ.get("MLB200_ZCHECKS_ON_MODEL", "packed_dropout").split(","):
+        env = {"_EMU_EXT": ext}
+        exec(compile(prelude + tz.CHECKS[name], name, "exec"), env)
+        bad = {f"{c}.{k}": v for c, d in env["res"].items() for k, v in d.items() if not (v == v and v < 2e-2)}
+        assert not bad, (name, bad)

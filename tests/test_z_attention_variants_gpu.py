@@ -3,7 +3,9 @@ operands and attention dropout in the tcgen05 forward / dK,dV / dQ kernels, the 
 of sequence lengths that are not a multiple of the tile (ragged prompts, variable-length training).  (CPU-side evidence: the bf16 / no-dropout instantiations of the hot-path kernels are SASS-identical to the validated
 build; the real source of ALL attention kernels, these variants included, runs against the fp32 oracle and under
 ThreadSanitizer on a functional model of TMA / mbarrier / tensor memory / tcgen05.mma in
-tests/test_attention_kernel_model.py; the decode kernel source runs on CPU threads in tests/test_kernel_emulation.py.)
+tests/test_attention_kernel_model.py; the decode kernel source runs on CPU threads in tests/test_kernel_emulation.py.
+The direct-kernel scripts below (fp16_training, dropout_training, packed_dropout, decode, single_tile_forward_kernel)
+were themselves run on CPU tensors against that emulated extension and pass there.)
 
 Every check runs in its own process with a hard timeout, so a fault or a hang in one of these first runs cannot take
 the rest of the GPU suite with it.  A check that passes is an ordinary PASS (= validated on hardware); one that fails
