@@ -4,7 +4,8 @@
 #   tools/profiling/sanitize.sh [tool ...]        default: memcheck synccheck
 # The tcgen05 / TMA kernels synchronise through mbarriers and the async proxy, which racecheck does not model: expect
 # false positives there and read its report per kernel.  Sizes are the small cases of tests/ (seconds each natively,
-# minutes under the sanitizer).
+# minutes under the sanitizer).  Without a GPU: the barrier protocols of exactly those kernels (mbarrier phases included)
+# are checked by ThreadSanitizer on the functional model -- python -m pytest tests -q -k "thread_sanitizer or races".
 out=gpurun_out/sanitize; mkdir -p $out
 tools=${@:-memcheck synccheck}
 for t in $tools; do
