@@ -121,28 +121,34 @@ inline float __shfl_xor_sync(unsigned, float v, int o) {
 inline int __shfl_xor_sync(unsigned, int v, int o) { return int(emu_shfl_bits(uint32_t(v), int(threadIdx.x & 31) ^ o)); }
 
 namespace cuda_emu {
-// run `kernel()` for every thread of every block of a 1-D-thread-block grid
+// run `kernel()` for every thread of every block of a 1-D-thread-block grid.  The OS threads are created once per
+// launch and walk the blocks together (an outer barrier separates consecutive blocks), which keeps launches with
+// thousands of small blocks cheap.
 template <class F>
 void launch(dim3 grid, unsigned threads, F kernel) {
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        Block block(threads);
-        std::vector<std::thread> pool;
-        pool.reserve(threads);
-        for (unsigned t = 0; t < threads; ++t)
-          pool.emplace_back([&, t] {
-            blk = &block;
-            threadIdx = uint3{t, 0, 0};
-            blockIdx = uint3{bx, by, bz};
-            blockDim = dim3(threads);
-            gridDim = grid;
-            kernel();
-            block.warp_bar[t >> 5]->arrive_and_drop();
-            block.block_bar.arrive_and_drop();
-          });
-        for (auto& th : pool) th.join();
+  const unsigned nb = grid.x * grid.y * grid.z;
+  if (nb == 0) return;
+  std::vector<std::unique_ptr<Block>> blocks(nb);
+  for (auto& b : blocks) b.reset(new Block(threads));
+  std::barrier<> between(threads);
+  std::vector<std::thread> pool;
+  pool.reserve(threads);
+  for (unsigned t = 0; t < threads; ++t)
+    pool.emplace_back([&, t] {
+      threadIdx = uint3{t, 0, 0};
+      blockDim = dim3(threads);
+      gridDim = grid;
+      for (unsigned b = 0; b < nb; ++b) {
+        Block& block = *blocks[b];
+        blk = &block;
+        blockIdx = uint3{b % grid.x, (b / grid.x) % grid.y, b / (grid.x * grid.y)};
+        kernel();
+        block.warp_bar[t >> 5]->arrive_and_drop();
+        block.block_bar.arrive_and_drop();
+        between.arrive_and_wait();                 // the next block starts when every thread has left this one
       }
+    });
+  for (auto& th : pool) th.join();
 }
 }  // namespace cuda_emu
 

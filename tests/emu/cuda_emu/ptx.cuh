@@ -65,12 +65,14 @@ inline void fence_proxy_async_smem() {}
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   cuda_emu::chaos();
   auto* b = reinterpret_cast<cuda_emu::MBar*>(bar);
-  for (;;) {
+  for (unsigned spins = 0;; ++spins) {
     {
       std::lock_guard<std::mutex> g(cuda_emu::mbar_mutex());
       if (b->phase != (parity & 1)) return;
     }
-    std::this_thread::yield();
+    // hundreds of waiters per block: yield a few times, then sleep so that the threads doing the work get the cores
+    if (spins < 16) std::this_thread::yield();
+    else std::this_thread::sleep_for(std::chrono::microseconds(spins < 256 ? 20 : 200));
   }
 }
 inline void mbar_arrive(uint64_t* bar) {

@@ -97,3 +97,159 @@ class EmuExtension:
                                       _p(out), None)
         assert rc == 0, rc
         return out
+
+
+DT = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}
+
+
+def _o(t):
+    return ctypes.c_void_p(None if t is None else t.data_ptr())
+
+
+class FullEmuExtension(EmuExtension):
+    """Every binding the training stack calls (csrc/bindings.cpp), on the CPU models: the tcgen05 GEMMs (1-CTA / 2-CTA),
+    attention, and the SIMT kernels.  With ``ops._ext.load`` pointing here and the ``is_cuda`` predicates of
+    ``ops/__init__.py`` lifted (see tests/test_model_on_emulated_kernels.py), a whole training step runs through the real
+    kernel sources on CPU tensors."""
+
+    def __init__(self, build_dir):
+        super().__init__(build_dir)
+        self.gm = ctypes.CDLL(host_build.build(["gemm_sm100.cu", "gemm2_sm100.cu"], os.path.join(build_dir, "gemm")))
+        self.simt = ctypes.CDLL(host_build.build(["ce.cu", "softmax.cu", "norm.cu", "elementwise.cu", "optim.cu", "embedding.cu"],
+                                                 os.path.join(build_dir, "simt")))
+        self.calls = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    def num_sms(self):
+        return 4
+
+    def gemm(self, A, B, C, M, N, K, lda, ldb, ldc, a_mn, b_mn, epilogue, block_n, comm, sms):
+        assert comm is None
+        self._count("gemm")
+        fp16 = int(A.dtype == torch.float16)
+        out_bytes = 2 if epilogue in (0, 3) else 4
+        if block_n == 512 and (ldc * out_bytes) % 16 == 0:
+            rc = self.gm.mlb_gemm_bf16_2cta(_p(A), _p(B), _p(C), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), epilogue, fp16, 4, None)
+        else:
+            rc = self.gm.mlb_gemm_bf16(_p(A), _p(B), _p(C), M, N, K, lda, ldb, ldc, int(a_mn), int(b_mn), epilogue,
+                                       0 if block_n == 512 else block_n, fp16, 4, None)
+        assert rc == 0, rc
+
+    def norm_fwd(self, x, res_in, w, b, y, res_out, mean, rstd, eps, rms):
+        self._count("norm_fwd")
+        H = x.size(-1)
+        assert self.simt.mlb_norm_fwd(DT[x.dtype], _p(x), _o(res_in), _p(w), _o(b), _p(y), _o(res_out), _o(mean), _p(rstd),
+                                      x.numel() // H, H, ctypes.c_float(eps), int(rms), None) == 0
+
+    def norm_bwd(self, dy, x, w, mean, rstd, dres, dx, dw, db, workspace, parts, rms):
+        self._count("norm_bwd")
+        H = x.size(-1)
+        assert self.simt.mlb_norm_bwd(DT[x.dtype], _p(dy), _p(x), _p(w), _o(mean), _p(rstd), _o(dres), _p(dx), _p(dw), _o(db),
+                                      _p(workspace), int(parts), x.numel() // H, H, int(rms), None) == 0
+
+    def rope_qkv(self, qkv, freqs, pos, tokens, batch, n_groups, heads_per_group, hn, pos_offset, inverse, token_stride):
+        self._count("rope_qkv")
+        assert self.simt.mlb_rope_qkv(DT[qkv.dtype], _p(qkv), _p(freqs), _o(pos), tokens, batch, n_groups, heads_per_group, hn,
+                                      pos_offset, int(inverse), ctypes.c_longlong(token_stride), None) == 0
+
+    def glu_fwd(self, x, y, kind):
+        self._count("glu_fwd")
+        F = y.size(-1)
+        assert self.simt.mlb_glu_fwd(DT[x.dtype], _p(x), _p(y), ctypes.c_longlong(y.numel() // F), F, kind, None) == 0
+
+    def glu_bwd(self, dy, x, dx, kind):
+        self._count("glu_bwd")
+        F = dy.size(-1)
+        assert self.simt.mlb_glu_bwd(DT[x.dtype], _p(dy), _p(x), _p(dx), ctypes.c_longlong(dy.numel() // F), F, kind, None) == 0
+
+    def gelu(self, x, bias, dy, out, approx, backward):
+        self._count("gelu")
+        F = x.size(-1)
+        assert self.simt.mlb_gelu(DT[x.dtype], _p(x), _o(bias), _o(dy), _p(out), ctypes.c_longlong(x.numel() // F), F,
+                                  int(approx), int(backward), None) == 0
+
+    def bias_dropout_add(self, x, bias, residual, out, p, seed, backward):
+        self._count("bias_dropout_add")
+        F = x.size(-1)
+        assert self.simt.mlb_bias_dropout_add(DT[x.dtype], _p(x), _o(bias), _o(residual), _p(out), ctypes.c_longlong(x.numel() // F),
+                                              F, ctypes.c_float(p), ctypes.c_ulonglong(seed), int(backward), None) == 0
+
+    def embedding_fwd(self, ids, weight, out, vocab_start, sbh):
+        self._count("embedding_fwd")
+        assert self.simt.mlb_embedding_fwd(DT[weight.dtype], _p(ids), _p(weight), _p(out), ids.size(0), ids.size(1), weight.size(1),
+                                           ctypes.c_longlong(vocab_start), ctypes.c_longlong(weight.size(0)), int(sbh), None) == 0
+
+    def embedding_bwd(self, ids, dout, dweight, vocab_start, sbh):
+        self._count("embedding_bwd")
+        assert self.simt.mlb_embedding_bwd(DT[dout.dtype], _p(ids), _p(dout), _p(dweight), ids.size(0), ids.size(1), dweight.size(1),
+                                           ctypes.c_longlong(vocab_start), ctypes.c_longlong(dweight.size(0)), int(sbh), None) == 0
+
+    def ce_stats(self, logits, target, stats, vocab_start):
+        self._count("ce_stats")
+        assert self.simt.mlb_ce_stats(DT[logits.dtype], _p(logits), _p(target), _p(stats), logits.size(0), logits.size(1),
+                                      int(vocab_start), ctypes.c_longlong(logits.stride(0)), None) == 0
+
+    def ce_bwd(self, logits, out, target, M, logS, g, vocab_start, smoothing, vocab_size):
+        self._count("ce_bwd")
+        assert self.simt.mlb_ce_bwd(DT[logits.dtype], _p(logits), _p(out), _p(target), _p(M), _p(logS), _p(g), logits.size(0),
+                                    logits.size(1), int(vocab_start), ctypes.c_float(smoothing), int(vocab_size),
+                                    ctypes.c_longlong(logits.stride(0)), None) == 0
+
+    def adamw_flat(self, p, g, m, v, p16, global_offset, seg_start, seg_wd, seg_lr_mult, lr, beta1, beta2, eps, bc1, bc2,
+                   grad_scale, skip, p16_peers):
+        self._count("adamw_flat")
+        assert not p16_peers
+        f = ctypes.c_float
+        assert self.simt.mlb_adamw_flat(_p(p), _p(g), _p(m), _p(v), _o(p16), DT[p16.dtype] if p16 is not None else 0,
+                                        ctypes.c_longlong(p.numel()), ctypes.c_longlong(global_offset), _p(seg_start), _p(seg_wd),
+                                        _o(seg_lr_mult), seg_wd.numel(), f(lr), f(beta1), f(beta2), f(eps), f(bc1), f(bc2),
+                                        _o(grad_scale), _o(skip), None, 0, None) == 0
+
+    def sqnorm_flat(self, x, global_offset, seg_start, seg_weight, workspace, out, accumulate):
+        self._count("sqnorm_flat")
+        assert self.simt.mlb_sqnorm_flat(DT[x.dtype], _p(x), ctypes.c_longlong(x.numel()), ctypes.c_longlong(global_offset),
+                                         _o(seg_start), _o(seg_weight), seg_weight.numel() if seg_weight is not None else 0,
+                                         _p(workspace), _p(out), int(accumulate), None) == 0
+
+    def clip_coef(self, total_sq, max_norm, norm_out, coef_out, found_inf, extra_scale):
+        self._count("clip_coef")
+        assert self.simt.mlb_clip_coef(_p(total_sq), ctypes.c_float(max_norm), _p(norm_out), _p(coef_out), _o(found_inf),
+                                       ctypes.c_float(extra_scale), None) == 0
+
+    def scale_cast(self, x, y, scale, scale_ptr):
+        self._count("scale_cast")
+        assert self.simt.mlb_scale_cast(DT[x.dtype], DT[y.dtype], _p(x), _p(y), ctypes.c_longlong(x.numel()), ctypes.c_float(scale),
+                                        _o(scale_ptr), None) == 0
+
+    def accumulate(self, x, y):
+        self._count("accumulate")
+        assert self.simt.mlb_accumulate(DT[x.dtype], _p(x), _p(y), ctypes.c_longlong(x.numel()), None) == 0
+
+    def softmax_fwd(self, x, y, mask, scale, sq, sk, np_, mode):
+        self._count("softmax_fwd")
+        assert self.simt.mlb_softmax_fwd(DT[x.dtype], _p(x), _p(y), _o(mask), ctypes.c_float(scale), ctypes.c_longlong(x.numel() // sk),
+                                         sq, sk, np_, mask.size(0) if mask is not None else 1, mode, None) == 0
+
+    def softmax_bwd(self, dy, y, scale, sk):
+        self._count("softmax_bwd")
+        assert self.simt.mlb_softmax_bwd(DT[y.dtype], _p(dy), _p(y), ctypes.c_float(scale), ctypes.c_longlong(y.numel() // sk), sk,
+                                         None) == 0
+
+    # attention entry points: count them too
+    def attn_fwd(self, *a, **k):
+        self._count("attn_fwd")
+        return super().attn_fwd(*a, **k)
+
+    def attn_bwd(self, *a, **k):
+        self._count("attn_bwd")
+        return super().attn_bwd(*a, **k)
+
+    def attn_fwd_packed(self, *a, **k):
+        self._count("attn_fwd_packed")
+        return super().attn_fwd_packed(*a, **k)
+
+    def attn_bwd_packed(self, *a, **k):
+        self._count("attn_bwd_packed")
+        return super().attn_bwd_packed(*a, **k)
