@@ -8,8 +8,10 @@ the tcgen05 kernels, with lengths that are not a multiple of the 128-row tile ze
 
 Kernel variants that could not be run on hardware before they were merged (``_FEATURES``) are guarded by a one-time
 numerical self-test against the fp32 oracle on first use: a variant that fails it is reported loudly and the call falls
-back to the ``flash_attn`` library instead of producing wrong numbers.  ``MLB200_ATTN_<FEATURE>=1`` skips the self-test,
-``=0`` disables the variant."""
+back to the ``flash_attn`` library instead of producing wrong numbers.  On a GPU the self-test runs in a throw-away
+child process with a time limit (``_selftest_isolated``), so that a faulting or dead-locked first launch cannot poison
+the CUDA context of the job; the verdict is handed to the processes started afterwards through the environment.
+``MLB200_ATTN_<FEATURE>=1`` skips the self-test, ``=0`` disables the variant."""
 from __future__ import annotations
 
 import math
@@ -75,6 +77,45 @@ def _selftest_decode(hn: int, dtype, device) -> float:
     return worst
 
 
+def _selftest(feature: str, hn: int, device) -> float:
+    with torch.no_grad():
+        if feature == "decode":
+            return max(_selftest_decode(hn, torch.bfloat16, device), _selftest_decode(hn, torch.float16, device))
+        if feature == "fp16":
+            return _selftest_training(hn, torch.float16, 0.0, device)
+        return _selftest_training(hn, torch.bfloat16, 0.1, device)
+
+
+def _verdict_env(feature: str, hn: int) -> str:
+    return f"MLB200_ATTN_SELFTEST_{feature.upper()}_HD{hn}"
+
+
+def _selftest_isolated(feature: str, hn: int, device) -> float:
+    """The self-test in a short-lived child process with a time limit.  A first-ever launch of a kernel variant that
+    faults leaves a sticky error in its CUDA context and one that dead-locks never returns; neither may take the
+    training job (or a test session) with it, so the context that finds out is a throw-away one."""
+    import subprocess
+    dev = torch.device(device)
+    index = dev.index if dev.index is not None else torch.cuda.current_device()
+    root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    env = dict(os.environ)
+    env["PYTHONPATH"] = root + os.pathsep + env.get("PYTHONPATH", "")
+    env["MLB200_ATTN_SELFTEST_INPROC"] = "1"
+    for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
+        env.pop(k, None)
+    limit = float(os.environ.get("MLB200_ATTN_SELFTEST_TIMEOUT", "300"))
+    try:
+        r = subprocess.run([sys.executable, "-m", "megatron_llm_b200.ops.attention_sm100", feature, str(hn), str(index)],
+                           env=env, capture_output=True, text=True, timeout=limit)
+    except subprocess.TimeoutExpired:
+        raise RuntimeError(f"self-test did not finish within {limit:.0f} s (killed)") from None
+    for line in reversed(r.stdout.splitlines()):
+        if line.startswith("MLB200_SELFTEST_ERR "):
+            return float(line.split()[1])
+    tail = (r.stderr or r.stdout).strip().splitlines()[-3:]
+    raise RuntimeError(f"self-test process exited with code {r.returncode}: " + " | ".join(tail))
+
+
 def feature_ok(feature: str, hn: int, dtype, device) -> bool:
     """May this kernel variant be used?  Decided once per process and (variant, head_dim) -- see the module docstring."""
     key = (feature, hn)
@@ -86,19 +127,21 @@ def feature_ok(feature: str, hn: int, dtype, device) -> bool:
         return _feature_state[key]
     if torch.device(device).type == "cuda" and torch.cuda.is_current_stream_capturing():
         return False                        # cannot self-test inside a graph capture; decided on the next eager call
+    inherited = os.environ.get(_verdict_env(feature, hn))      # a parent process of this job has already decided
+    if inherited in ("0", "1"):
+        _feature_state[key] = inherited == "1"
+        return _feature_state[key]
     try:
-        with torch.no_grad():
-            if feature == "decode":
-                err = max(_selftest_decode(hn, torch.bfloat16, device), _selftest_decode(hn, torch.float16, device))
-            elif feature == "fp16":
-                err = _selftest_training(hn, torch.float16, 0.0, device)
-            else:
-                err = _selftest_training(hn, torch.bfloat16, 0.1, device)
+        if torch.device(device).type == "cuda" and os.environ.get("MLB200_ATTN_SELFTEST_INPROC", "0") != "1":
+            err = _selftest_isolated(feature, hn, device)
+        else:
+            err = _selftest(feature, hn, device)
         ok = err == err and err < 3e-2
         detail = f"relative error {err:.3e}"
     except Exception as e:                  # a launch / binding failure is a failed self-test, not a crash
         ok, detail = False, f"{type(e).__name__}: {e}"
     _feature_state[key] = ok
+    os.environ[_verdict_env(feature, hn)] = "1" if ok else "0"      # ranks / tools started from here inherit it
     if not ok:
         msg = (f"megatron_llm_b200: the sm_100a attention variant '{feature}' (head_dim {hn}) FAILED its self-test "
                f"({detail}); falling back to the flash_attn library for it")
@@ -245,3 +288,11 @@ def packed_attention(mixed, nkv, g, window=None, scale=None, hn=None, dropout_p:
     scale = scale if scale is not None else 1.0 / math.sqrt(hn)
     seed = _draw_seed(dropout_p, mixed.size(1) * nkv * g * mixed.size(0) * mixed.size(0))
     return _PackedAttnFn.apply(mixed, nkv, g, window, scale, hn, dropout_p, seed)
+
+
+if __name__ == "__main__":      # child of _selftest_isolated: <feature> <head_dim> <cuda device index>
+    _feature, _hn, _index = sys.argv[1], int(sys.argv[2]), int(sys.argv[3])
+    torch.cuda.set_device(_index)
+    _err = _selftest(_feature, _hn, torch.device("cuda", _index))
+    torch.cuda.synchronize()
+    print(f"MLB200_SELFTEST_ERR {_err:.6e}", flush=True)

@@ -98,7 +98,12 @@ def fake(monkeypatch, decode_lib):
     monkeypatch.setattr(attention_sm100, "_feature_state", {})
     for var in ("MLB200_ATTN", "MLB200_DISABLE_KERNELS", "MLB200_ATTN_FP16", "MLB200_ATTN_DROPOUT", "MLB200_ATTN_DECODE"):
         monkeypatch.delenv(var, raising=False)
-    return ext
+    verdicts = lambda: [k for k in os.environ if k.startswith("MLB200_ATTN_SELFTEST_")]
+    for var in verdicts():
+        monkeypatch.delenv(var, raising=False)
+    yield ext
+    for var in verdicts():      # feature_ok publishes its verdicts to child processes through the environment
+        os.environ.pop(var, None)
 
 
 def test_selftests_admit_working_kernels_and_reject_broken_ones(fake, monkeypatch):
@@ -119,6 +124,12 @@ def test_selftests_admit_working_kernels_and_reject_broken_ones(fake, monkeypatc
         for feature in ("fp16", "dropout", "decode"):
             assert not attention_sm100.feature_ok(feature, 128, torch.bfloat16, dev), feature
     assert len(w) == 3 and all("FAILED its self-test" in str(x.message) for x in w)
+    # the verdicts are published to processes started from here (ranks, tools): they do not test again
+    assert os.environ["MLB200_ATTN_SELFTEST_FP16_HD64"] == "1" and os.environ["MLB200_ATTN_SELFTEST_DECODE_HD128"] == "0"
+    monkeypatch.setattr(attention_sm100, "_feature_state", {})
+    n = len(fake.calls)
+    assert not attention_sm100.feature_ok("decode", 128, torch.bfloat16, dev) and len(fake.calls) == n
+    monkeypatch.delenv("MLB200_ATTN_SELFTEST_DECODE_HD128")
     # ... and so is one that raises; the environment switch overrides both ways
     monkeypatch.setattr(attention_sm100, "_feature_state", {})
     monkeypatch.setattr(fake, "attn_decode", lambda *a: (_ for _ in ()).throw(RuntimeError("launch failed")))
@@ -131,6 +142,32 @@ def test_selftests_admit_working_kernels_and_reject_broken_ones(fake, monkeypatc
     monkeypatch.setattr(attention_sm100, "_feature_state", {})
     monkeypatch.setenv("MLB200_ATTN_DECODE", "0")
     assert not attention_sm100.feature_ok("decode", 128, torch.bfloat16, dev)
+
+
+def test_selftest_on_a_cuda_device_runs_in_a_throwaway_process(fake, monkeypatch):
+    """On a GPU the first launch of a never-run kernel variant happens in a child process with a time limit: a sticky
+    CUDA error or a dead-locked kernel costs that child, not the job.  Here (no GPU) the child cannot pass -- what is
+    checked is that a crashing child and one that overruns its limit both come back as a clean, loud 'no'."""
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    monkeypatch.setattr(torch.cuda, "current_device", lambda: 0)
+    dev = torch.device("cuda", 0)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert not attention_sm100.feature_ok("fp16", 128, torch.float16, dev)
+    assert len(w) == 1 and "self-test process exited with code" in str(w[0].message)
+    assert not fake.calls                                       # nothing ran in this process
+    assert os.environ["MLB200_ATTN_SELFTEST_FP16_HD128"] == "0"
+    monkeypatch.setenv("MLB200_ATTN_SELFTEST_TIMEOUT", "0.05")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        assert not attention_sm100.feature_ok("dropout", 64, torch.bfloat16, dev)
+    assert len(w) == 1 and "did not finish within" in str(w[0].message)
+    # a passing child: its last line carries the error
+    import subprocess
+    done = subprocess.CompletedProcess([], 0, stdout="noise\nMLB200_SELFTEST_ERR 2.5e-03\n", stderr="")
+    monkeypatch.setattr(subprocess, "run", lambda *a, **k: done)
+    assert attention_sm100.feature_ok("decode", 64, torch.bfloat16, dev)
+    assert os.environ["MLB200_ATTN_SELFTEST_DECODE_HD64"] == "1"
 
 
 @pytest.mark.parametrize("s,window,p", [(256, None, 0.0), (77, None, 0.1), (200, 64, 0.25)])

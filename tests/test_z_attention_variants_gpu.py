@@ -206,7 +206,9 @@ res["used"] = dict(decode_kernel=float(attention_sm100._feature_state.get(("deco
 
 def _run_check(name):
     code = PRELUDE % {"root": ROOT} + CHECKS[name] + '\nprint("RESULT " + json.dumps(res))\n'
-    env = dict(os.environ, MLB200_FORCE_CPU="0", MLB200_DISABLE_KERNELS="0")
+    # (this process is already a throw-away one: the first-use self-tests may run in it directly)
+    env = dict(os.environ, MLB200_FORCE_CPU="0", MLB200_DISABLE_KERNELS="0", MLB200_ATTN_SELFTEST_INPROC="1")
+    env = {k: v for k, v in env.items() if not k.startswith("MLB200_ATTN_SELFTEST_") or k.endswith("_INPROC")}
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=420)
     assert r.returncode == 0, r.stderr[-3000:]
     res = json.loads([l for l in r.stdout.splitlines() if l.startswith("RESULT ")][-1][len("RESULT "):])
