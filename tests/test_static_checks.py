@@ -6,6 +6,8 @@ import builtins
 import glob
 import os
 
+import pytest
+
 ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), os.pardir))
 SKIP = (os.sep + "baseline" + os.sep, os.sep + "_build" + os.sep, "gpurun_out", os.sep + ".git" + os.sep)
 
@@ -84,3 +86,22 @@ def test_every_args_attribute_is_a_flag_or_assigned_somewhere(monkeypatch):
                 used.setdefault(m.group(1), set()).add(os.path.relpath(path, ROOT))
     unknown = {k: sorted(v)[:3] for k, v in used.items() if k not in dests and k not in assigned}
     assert not unknown, unknown
+
+
+def test_build_restores_the_reference_tree_of_the_benchmark_arm(tmp_path, monkeypatch):
+    """``baseline/_ref`` (the unmodified reference that ``bench.py --impl reference`` drives) is git-ignored, so a
+    fresh checkout lacks it: ``__graft_entry__.build()`` copies it back, verbatim, and leaves an existing one alone."""
+    import filecmp
+    import __graft_entry__ as entry
+    if not os.path.isdir("/root/reference/megatron"):
+        pytest.skip("no reference checkout on this machine")
+    monkeypatch.setattr(entry, "ROOT", str(tmp_path))
+    entry._ensure_reference_tree()
+    ref = tmp_path / "baseline" / "_ref"
+    assert (ref / "megatron" / "training.py").is_file() and (ref / "finetune.py").is_file()
+    cmp = filecmp.dircmp("/root/reference/megatron", str(ref / "megatron"), ignore=["__pycache__"])
+    assert not cmp.left_only and not cmp.right_only and not cmp.diff_files
+    marker = ref / "finetune.py"
+    marker.write_text("# kept")
+    entry._ensure_reference_tree()
+    assert marker.read_text() == "# kept"
