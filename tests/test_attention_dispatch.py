@@ -129,7 +129,7 @@ def test_selftests_admit_working_kernels_and_reject_broken_ones(fake, monkeypatc
     monkeypatch.setattr(attention_sm100, "_feature_state", {})
     n = len(fake.calls)
     assert not attention_sm100.feature_ok("decode", 128, torch.bfloat16, dev) and len(fake.calls) == n
-    monkeypatch.delenv("MLB200_ATTN_SELFTEST_DECODE_HD128")
+    os.environ.pop("MLB200_ATTN_SELFTEST_DECODE_HD128")    # not monkeypatch.delenv: its undo would put the "0" back after the test
     # ... and so is one that raises; the environment switch overrides both ways
     monkeypatch.setattr(attention_sm100, "_feature_state", {})
     monkeypatch.setattr(fake, "attn_decode", lambda *a: (_ for _ in ()).throw(RuntimeError("launch failed")))

@@ -149,6 +149,8 @@ def test_python_attention_path_on_the_real_kernels(monkeypatch, tmp_path_factory
     monkeypatch.setattr(attention_sm100, "_feature_state", {})
     for var in ("MLB200_ATTN", "MLB200_DISABLE_KERNELS", "MLB200_ATTN_FP16", "MLB200_ATTN_DROPOUT", "MLB200_ATTN_DECODE"):
         monkeypatch.delenv(var, raising=False)
+    for var in [k for k in os.environ if k.startswith("MLB200_ATTN_SELFTEST_")]:
+        os.environ.pop(var)      # verdicts inherited from whatever ran earlier in this process say nothing about these kernels
     dev = torch.device("cpu")
     assert attention_sm100.feature_ok("dropout", 128, torch.bfloat16, dev)
     assert attention_sm100.feature_ok("fp16", 64, torch.float16, dev)
