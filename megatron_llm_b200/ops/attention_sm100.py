@@ -103,7 +103,7 @@ def _selftest_isolated(feature: str, hn: int, device) -> float:
     env["MLB200_ATTN_SELFTEST_INPROC"] = "1"
     for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID"):
         env.pop(k, None)
-    limit = float(os.environ.get("MLB200_ATTN_SELFTEST_TIMEOUT", "300"))
+    limit = float(os.environ.get("MLB200_ATTN_SELFTEST_TIMEOUT", "180"))
     try:
         r = subprocess.run([sys.executable, "-m", "megatron_llm_b200.ops.attention_sm100", feature, str(hn), str(index)],
                            env=env, capture_output=True, text=True, timeout=limit)

@@ -103,7 +103,11 @@ def test_fp16_with_dynamic_loss_scaling_trains():
     argv = CONFIGS["llama"].replace("--bf16", "--fp16 --initial_loss_scale 4096 --loss_scale_window 2")
     script = SCRIPT.replace("for step in range(3):", "for step in range(5):")
     for disable in (False, True):
-        env = dict(os.environ, MLB200_DISABLE_KERNELS="1" if disable else "0", MLB200_FORCE_CPU="0")
+        # (fp16 ATTENTION stays on the path this test was validated with on hardware, the library: the tcgen05 fp16
+        # attention variant was written after the last GPU run and has its own, isolated first-run checks in
+        # tests/test_z_attention_variants_gpu.py -- this test is about the fp16 GEMMs / optimizer / loss scaler)
+        env = dict(os.environ, MLB200_DISABLE_KERNELS="1" if disable else "0", MLB200_FORCE_CPU="0",
+                   MLB200_ATTN_FP16="0")
         code = script % {"root": ROOT, "port": "29614", "argv": argv, "seq": 256}
         r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
